@@ -1,0 +1,136 @@
+/*
+ * tfswa_b200.h - C ABI of libtfswa_b200.so: the TFSWA-UNet hot path on NVIDIA B200 (sm_100a).
+ *
+ * The reference (chynggi/TFSWA-UNet) has no FFI layer: its hot path sits behind the Python
+ * nn.Module surface (src/models/attention.py, blocks.py, tfswa_unet.py) and dispatches ATen ops.
+ * Each entry point below replaces the ATen op sequence of one reference call site (cited per
+ * function).  The Python mirror of the reference modules (tfswa-unet_b200/*.py) binds these
+ * with ctypes; INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *  - Every pointer is a DEVICE pointer owned by the caller (PyTorch's caching allocator);
+ *    the library allocates nothing persistent on the device.
+ *  - "act" tensors are NHWC ("tokens x channels", token m = (b*H + h)*W + w), element type
+ *    given by `dtype` (TFSWA_F32 or TFSWA_BF16).  Weights, biases, statistics are fp32.
+ *  - Every call takes the caller's cudaStream_t (as void*), launches asynchronously and never
+ *    synchronises.  Re-entrant; no global device state.
+ *  - Return 0 on success, negative on error; tfswa_last_error() returns a thread-local message.
+ *    Nothing throws or exits across the ABI.  There is NO CPU fallback.
+ */
+#ifndef TFSWA_B200_H
+#define TFSWA_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TFSWA_F32 0
+#define TFSWA_BF16 1
+
+#define TFSWA_OK 0
+#define TFSWA_EINVAL (-1)   /* bad argument / unsupported shape */
+#define TFSWA_ECUDA (-2)    /* CUDA runtime error at launch */
+
+/* prologue applied to the A operand of tfswa_linear_* while it is staged on chip */
+#define TFSWA_PRO_NONE 0
+#define TFSWA_PRO_LNHAT 1    /* (x - mean_row) * rstd_row from row_stats; LN affine is folded into W/bias by the host */
+#define TFSWA_PRO_GELU 2     /* exact erf GELU */
+#define TFSWA_PRO_AFFINE 4   /* x*in_scale[k] + in_shift[k] (train-mode BatchNorm apply); may be OR-ed with the others, applied first */
+/* epilogue */
+#define TFSWA_EPI_NONE 0
+#define TFSWA_EPI_GELU 1
+
+/* attention geometries */
+#define TFSWA_GEOM_TSA 0     /* sequences along H (reference dim 2), one per (b, w)   attention.py:143 */
+#define TFSWA_GEOM_FSA 1     /* sequences along W (reference dim 3), one per (b, h)   attention.py:217 */
+#define TFSWA_GEOM_SWA 2     /* ws x ws windows of the zero-padded, cyclically shifted map   attention.py:358-375 */
+
+const char* tfswa_last_error(void);
+const char* tfswa_version(void);
+/* 1 if a kernel image for the current device exists in this library (sm_100a only). */
+int tfswa_device_supported(void);
+
+/* ---- token linear: Y = epi(pro(X) W^T + bias) (+R1) (+R2) ---------------------------------
+ * Replaces nn.Linear / 1x1 nn.Conv2d call sites: attention.py:70 (qkv), :86 (proj), :121-128 (MLP),
+ * blocks.py:53-56 (input_proj), :85-89 (fusion, K = 3C over the never-materialised concat).
+ * `batch` independent problems (the three branches) are addressed by element strides *_bs. */
+typedef struct {
+  const void* x;  int64_t ldx;  int64_t x_bs;     /* (M,K) act, row stride ldx */
+  const float* w;               int64_t w_bs;     /* (N,K) fp32 row-major (nn.Linear layout) */
+  const float* bias;            int64_t bias_bs;  /* (N) or NULL */
+  const float* row_stats;       int64_t rs_bs;    /* (M,2) {mean,rstd} for TFSWA_PRO_LNHAT */
+  const float* in_scale; const float* in_shift;   /* (K) for TFSWA_PRO_AFFINE */
+  const void* r1; int64_t ldr1; int64_t r1_bs;    /* residual added after the epilogue, or NULL */
+  const void* r2; int64_t ldr2; int64_t r2_bs;
+  void* y;        int64_t ldy;  int64_t y_bs;     /* (M,N) act */
+  void* pre;      int64_t ldpre; int64_t pre_bs;  /* optional copy of the pre-epilogue value (saved for backward) */
+  float* col_stats;                                /* optional (2,N): atomically accumulates sum / sum-of-squares of the pre-epilogue value (train-mode BN) */
+  int64_t M; int32_t N; int32_t K;
+  int32_t prologue; int32_t epilogue; int32_t batch; int32_t dtype;
+} tfswa_linear_args;
+int tfswa_linear_fwd(const tfswa_linear_args* a, void* stream);
+
+/* per-row LayerNorm statistics {mean, rstd} over K channels, eps 1e-5 (F.layer_norm, attention.py:146,159) */
+int tfswa_row_stats(const void* x, int64_t ldx, int64_t x_bs, float* stats, int64_t st_bs,
+                    int64_t M, int32_t K, int32_t batch, int32_t dtype, void* stream);
+
+/* ---- attention core: O = softmax(Q K^T / sqrt(d)) V per head, never materialising the scores --
+ * Replaces attention.py:70-85 together with the token regrouping of :143/:162 (TSA), :217/:236 (FSA)
+ * and :358-375/:390-401 (SW-MSA pad + roll + window partition/reverse).
+ * qkv: (M, ldq) act with q|k|v each C wide starting at column 0|C|2C of the given pointer.
+ * out: (M, ldo) act, C wide.  lse (optional): (M, heads) fp32 log2-domain logsumexp for backward.
+ * SWA: pad_kv = (2C) fp32 k|v of a zero-padded token (= folded qkv bias); rel_bias optional
+ * (heads, ws*ws, ws*ws) fp32; use_shift_mask adds the Swin {0,-100} mask (both OFF = reference). */
+typedef struct {
+  const void* qkv; int64_t ldq;
+  void* out;       int64_t ldo;
+  float* lse;
+  const float* pad_kv;
+  const float* rel_bias;
+  int32_t B, H, W, C, heads;
+  int32_t geom, ws, shift, use_shift_mask, dtype;
+} tfswa_attn_args;
+int tfswa_attn_fwd(const tfswa_attn_args* a, void* stream);
+
+/* ---- convolutions (implicit GEMM over NHWC) ---------------------------------------------------
+ * kind: 0 = 3x3 s1 p1 (output_head.0, tfswa_unet.py:140), 1 = 4x4 s2 p1 (DownsampleBlock, blocks.py:157),
+ *       2 = transposed 4x4 s2 p1 (UpsampleBlock, blocks.py:172).
+ * w: fp32, re-laid-out by the host to (Cout, kh, kw, Cin) for kinds 0/1 and to (4 phases, Cout, 2, 2, Cin)
+ * for kind 2 (phase = (oy&1)*2 + (ox&1)).  y = epi(conv + bias); pre/col_stats as in tfswa_linear_args. */
+typedef struct {
+  const void* x; void* y; void* pre;
+  const float* w; const float* bias; float* col_stats;
+  int32_t B, Hin, Win, Cin, Hout, Wout, Cout;
+  int32_t kind, epilogue, dtype;
+} tfswa_conv_args;
+int tfswa_conv_fwd(const tfswa_conv_args* a, void* stream);
+
+/* stem: Conv2d(Cin,Cout,7,p=3) on the NCHW fp32 network input -> NHWC act (tfswa_unet.py:58-62).
+ * w: (Cout, Cin, 7, 7) fp32 in nn.Conv2d layout. */
+int tfswa_stem_fwd(const float* x_nchw, const float* w, const float* bias, void* y, void* pre, float* col_stats,
+                   int32_t B, int32_t Cin, int32_t H, int32_t W, int32_t Cout, int32_t epilogue, int32_t dtype, void* stream);
+
+/* head tail: u = GELU(v*scale + shift); logits = W3 u + b3; masks = sigmoid(logits) -> NCHW fp32
+ * (output_head.1-4, tfswa_unet.py:141-144).  scale/shift NULL = identity (eval: BN folded upstream). */
+int tfswa_head_tail_fwd(const void* v, const float* scale, const float* shift, const float* w3, const float* b3,
+                        float* masks_nchw, float* logits_nchw, int32_t B, int32_t H, int32_t W, int32_t C, int32_t Cout,
+                        int32_t dtype, void* stream);
+
+/* ---- BatchNorm helpers (train mode) ------------------------------------------------------------
+ * finalize: from col_stats (2,C) over `count` values: scale = gamma*rsqrt(var+eps), shift = beta - mean*scale,
+ * and the running-stat update (momentum, unbiased variance) in place.  save_mean_rstd (2,C) for backward. */
+int tfswa_bn_finalize(const float* col_stats, int64_t count, const float* gamma, const float* beta,
+                      float* running_mean, float* running_var, float momentum, float eps,
+                      float* scale, float* shift, float* save_mean_rstd, int32_t C, void* stream);
+/* y = act(v*scale[c] + shift[c]) (+r1) (+r2): BN apply + GELU + residuals over (M,C) act */
+int tfswa_affine_act(const void* v, const float* scale, const float* shift, const void* r1, const void* r2, void* y,
+                     int64_t M, int32_t C, int32_t epilogue, int32_t dtype, void* stream);
+
+/* bilinear resize, align_corners=False, NHWC act (F.interpolate at tfswa_unet.py:210-216) */
+int tfswa_bilinear_fwd(const void* x, void* y, int32_t B, int32_t Hin, int32_t Win, int32_t Hout, int32_t Wout,
+                       int32_t C, int32_t dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

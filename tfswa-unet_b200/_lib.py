@@ -1,0 +1,88 @@
+"""ctypes binding of libtfswa_b200.so (the C ABI declared in include/tfswa_b200.h).
+
+The library is loaded lazily; a missing library or a failing call raises ``RuntimeError`` - there is
+deliberately no fallback implementation.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libtfswa_b200.so")
+
+F32, BF16 = 0, 1
+PRO_NONE, PRO_LNHAT, PRO_GELU, PRO_AFFINE = 0, 1, 2, 4
+EPI_NONE, EPI_GELU = 0, 1
+GEOM_TSA, GEOM_FSA, GEOM_SWA = 0, 1, 2
+
+_i64, _i32, _p, _f = C.c_int64, C.c_int32, C.c_void_p, C.c_float
+
+
+class LinearArgs(C.Structure):
+    _fields_ = [("x", _p), ("ldx", _i64), ("x_bs", _i64),
+                ("w", _p), ("w_bs", _i64),
+                ("bias", _p), ("bias_bs", _i64),
+                ("row_stats", _p), ("rs_bs", _i64),
+                ("in_scale", _p), ("in_shift", _p),
+                ("r1", _p), ("ldr1", _i64), ("r1_bs", _i64),
+                ("r2", _p), ("ldr2", _i64), ("r2_bs", _i64),
+                ("y", _p), ("ldy", _i64), ("y_bs", _i64),
+                ("pre", _p), ("ldpre", _i64), ("pre_bs", _i64),
+                ("col_stats", _p),
+                ("M", _i64), ("N", _i32), ("K", _i32),
+                ("prologue", _i32), ("epilogue", _i32), ("batch", _i32), ("dtype", _i32)]
+
+
+class AttnArgs(C.Structure):
+    _fields_ = [("qkv", _p), ("ldq", _i64), ("out", _p), ("ldo", _i64), ("lse", _p),
+                ("pad_kv", _p), ("rel_bias", _p),
+                ("B", _i32), ("H", _i32), ("W", _i32), ("C", _i32), ("heads", _i32),
+                ("geom", _i32), ("ws", _i32), ("shift", _i32), ("use_shift_mask", _i32), ("dtype", _i32)]
+
+
+class ConvArgs(C.Structure):
+    _fields_ = [("x", _p), ("y", _p), ("pre", _p), ("w", _p), ("bias", _p), ("col_stats", _p),
+                ("B", _i32), ("Hin", _i32), ("Win", _i32), ("Cin", _i32), ("Hout", _i32), ("Wout", _i32), ("Cout", _i32),
+                ("kind", _i32), ("epilogue", _i32), ("dtype", _i32)]
+
+
+# name -> (restype, argtypes); every symbol include/tfswa_b200.h declares
+SIGNATURES = {
+    "tfswa_last_error": (C.c_char_p, []),
+    "tfswa_version": (C.c_char_p, []),
+    "tfswa_device_supported": (C.c_int, []),
+    "tfswa_linear_fwd": (C.c_int, [C.POINTER(LinearArgs), _p]),
+    "tfswa_row_stats": (C.c_int, [_p, _i64, _i64, _p, _i64, _i64, _i32, _i32, _i32, _p]),
+    "tfswa_attn_fwd": (C.c_int, [C.POINTER(AttnArgs), _p]),
+    "tfswa_conv_fwd": (C.c_int, [C.POINTER(ConvArgs), _p]),
+    "tfswa_stem_fwd": (C.c_int, [_p, _p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p]),
+    "tfswa_head_tail_fwd": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _p]),
+    "tfswa_bn_finalize": (C.c_int, [_p, _i64, _p, _p, _p, _p, _f, _f, _p, _p, _p, _i32, _p]),
+    "tfswa_affine_act": (C.c_int, [_p, _p, _p, _p, _p, _p, _i64, _i32, _i32, _i32, _p]),
+    "tfswa_bilinear_fwd": (C.c_int, [_p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p]),
+}
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a). tfswa_unet_b200 has no CPU or PyTorch fallback.")
+        l = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(l, name)   # AttributeError here = header/library mismatch
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib().tfswa_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"tfswa_b200 {what} failed (rc={rc}): {msg}")

@@ -1,0 +1,310 @@
+// fp32-accumulate SIMT implicit GEMM over NHWC tokens:  Y = epi(pro(A) W^T + bias) (+R1) (+R2)
+//
+// This is the full-precision ("fp32 parity") engine and the generic fallback for shapes the
+// tcgen05 kernels do not cover.  A rows are tokens; the A gather is a template policy so the same
+// kernel serves nn.Linear / 1x1 convs (attention.py:70,86,121-128; blocks.py:53,85), the 3x3 head
+// conv (tfswa_unet.py:140), the 4x4/s2 down conv (blocks.py:157) and the 4-phase transposed conv
+// (blocks.py:172).  Tiles: TM x TN outputs per CTA (256 threads, 8x4 per thread), K in chunks of 16
+// through double-buffered shared memory; 128-bit global accesses throughout.
+#include "common.cuh"
+
+namespace tfswa {
+
+enum { KIND_LINEAR = 0, KIND_CONV3 = 1, KIND_DOWN = 2, KIND_UP = 3 };
+
+struct IgemmParams {
+  const void* x; int64_t ldx;
+  const float* w; const float* bias;
+  const float* row_stats; const float* in_scale; const float* in_shift;
+  const void* r1; int64_t ldr1; const void* r2; int64_t ldr2;
+  void* y; int64_t ldy; void* pre; int64_t ldpre;
+  float* col_stats;
+  int64_t M; int N; int K;
+  int prologue; int epilogue;
+  // batch strides (elements)
+  int64_t x_bs, w_bs, bias_bs, rs_bs, r1_bs, r2_bs, y_bs, pre_bs;
+  // conv geometry
+  int B, Hin, Win, Cin, Hout, Wout;
+};
+
+constexpr int TK = 16;
+constexpr int NTHREADS = 256;
+
+// Element offset into x of the 8-element run of A starting at logical (row m, k), or -1 for zero padding.
+template <int KIND>
+__device__ __forceinline__ int64_t a_offset(const IgemmParams& p, int64_t m, int k, int phase) {
+  if (KIND == KIND_LINEAR) return m * p.ldx + k;
+  const int tap = k / p.Cin, ci = k - tap * p.Cin;
+  const int hw = (KIND == KIND_UP) ? p.Hin * p.Win : p.Hout * p.Wout;
+  const int wdim = (KIND == KIND_UP) ? p.Win : p.Wout;
+  const int b = (int)(m / hw);
+  const int rem = (int)(m - (int64_t)b * hw);
+  const int oy = rem / wdim, ox = rem - oy * wdim;
+  int iy, ix;
+  if (KIND == KIND_CONV3) { iy = oy + tap / 3 - 1; ix = ox + tap % 3 - 1; }
+  else if (KIND == KIND_DOWN) { iy = 2 * oy + (tap >> 2) - 1; ix = 2 * ox + (tap & 3) - 1; }
+  else {  // KIND_UP: (oy, ox) index the phase grid; tap = a*2 + b
+    const int py = phase >> 1, px = phase & 1, a = tap >> 1, bb = tap & 1;
+    iy = py ? (a ? oy : oy + 1) : (a ? oy - 1 : oy);
+    ix = px ? (bb ? ox : ox + 1) : (bb ? ox - 1 : ox);
+  }
+  if (iy < 0 || iy >= p.Hin || ix < 0 || ix >= p.Win) return -1;
+  return (((int64_t)b * p.Hin + iy) * p.Win + ix) * p.Cin + ci;
+}
+
+template <int KIND>
+__device__ __forceinline__ int64_t out_row_offset(const IgemmParams& p, int64_t m, int phase, int64_t ld) {
+  if (KIND != KIND_UP) return m * ld;
+  const int hw = p.Hin * p.Win;
+  const int b = (int)(m / hw);
+  const int rem = (int)(m - (int64_t)b * hw);
+  const int oy2 = rem / p.Win, ox2 = rem - oy2 * p.Win;
+  const int oy = 2 * oy2 + (phase >> 1), ox = 2 * ox2 + (phase & 1);
+  return (((int64_t)b * p.Hout + oy) * p.Wout + ox) * ld;
+}
+
+template <typename T, int KIND, int TN>
+__global__ void __launch_bounds__(NTHREADS) igemm_kernel(const IgemmParams p) {
+  constexpr int TXN = TN / 4;            // threads across N
+  constexpr int TYN = NTHREADS / TXN;    // threads across M
+  constexpr int TM = TYN * 8;
+  constexpr int A_VEC = TM * TK / 8 / NTHREADS;   // load8 vectors per thread per chunk
+  constexpr int LDA = TM + 4, LDB = TN + 4;
+  __shared__ __align__(16) float As[2][TK][LDA];
+  __shared__ __align__(16) float Bs[2][TK][LDB];
+  __shared__ float s_stats[2][TN];
+
+  const int tid = threadIdx.x;
+  const int z = blockIdx.z;               // batch index (linear) or phase (up-conv)
+  const int phase = (KIND == KIND_UP) ? z : 0;
+  const int64_t m0 = (int64_t)blockIdx.x * TM;
+  const int n0 = blockIdx.y * TN;
+  const T* x = (const T*)p.x + (KIND == KIND_LINEAR ? z * p.x_bs : 0);
+  const float* w = p.w + (int64_t)z * p.w_bs;
+  const float* rs = p.row_stats ? p.row_stats + (int64_t)z * p.rs_bs : nullptr;
+
+  const int ty = tid / TXN, tx = tid % TXN;
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  // per-thread A-load coordinates
+  int a_row[A_VEC]; const int a_kseg = (tid & 1) * 8;
+  float a_mean[A_VEC], a_rstd[A_VEC];
+#pragma unroll
+  for (int i = 0; i < A_VEC; ++i) {
+    a_row[i] = (tid + i * NTHREADS) >> 1;
+    a_mean[i] = 0.f; a_rstd[i] = 1.f;
+    const int64_t m = m0 + a_row[i];
+    if ((p.prologue & TFSWA_PRO_LNHAT) && m < p.M) { a_mean[i] = rs[m * 2]; a_rstd[i] = rs[m * 2 + 1]; }
+  }
+  const int b_n = tid >> 2, b_kseg = (tid & 3) * 4;
+  const bool b_active = (tid < TN * 4);
+
+  float a_reg[A_VEC][8];
+  float4 b_reg = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  auto load_chunk = [&](int k0) {
+#pragma unroll
+    for (int i = 0; i < A_VEC; ++i) {
+      const int64_t m = m0 + a_row[i];
+      const int k = k0 + a_kseg;
+      int64_t off = -1;
+      if (m < p.M && k < p.K) off = a_offset<KIND>(p, m, k, phase);
+      if (off >= 0) {
+        load8(x + off, a_reg[i]);
+        if (KIND == KIND_LINEAR && p.prologue != TFSWA_PRO_NONE) {
+          if (p.prologue & TFSWA_PRO_AFFINE) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) a_reg[i][j] = a_reg[i][j] * p.in_scale[k + j] + p.in_shift[k + j];
+          }
+          if (p.prologue & TFSWA_PRO_LNHAT) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) a_reg[i][j] = (a_reg[i][j] - a_mean[i]) * a_rstd[i];
+          }
+          if (p.prologue & TFSWA_PRO_GELU) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) a_reg[i][j] = gelu_erf(a_reg[i][j]);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a_reg[i][j] = 0.f;
+      }
+    }
+    if (b_active) {
+      const int n = n0 + b_n, k = k0 + b_kseg;
+      if (n < p.N && k < p.K) b_reg = *reinterpret_cast<const float4*>(w + (int64_t)n * p.K + k);
+      else b_reg = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  auto store_chunk = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < A_VEC; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) As[buf][a_kseg + j][a_row[i]] = a_reg[i][j];
+    if (b_active) {
+      Bs[buf][b_kseg + 0][b_n] = b_reg.x; Bs[buf][b_kseg + 1][b_n] = b_reg.y;
+      Bs[buf][b_kseg + 2][b_n] = b_reg.z; Bs[buf][b_kseg + 3][b_n] = b_reg.w;
+    }
+  };
+
+  const int nchunks = (p.K + TK - 1) / TK;
+  load_chunk(0);
+  store_chunk(0);
+  __syncthreads();
+  for (int kc = 0; kc < nchunks; ++kc) {
+    const int buf = kc & 1;
+    if (kc + 1 < nchunks) load_chunk((kc + 1) * TK);
+#pragma unroll
+    for (int k = 0; k < TK; ++k) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 8]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 8 + 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+    }
+    if (kc + 1 < nchunks) store_chunk(buf ^ 1);
+    __syncthreads();
+  }
+
+  // ---------------- epilogue ----------------
+  const int n = n0 + tx * 4;
+  const bool n_ok = n < p.N;   // N % 4 == 0 is required by the host wrapper
+  float bias[4] = {0.f, 0.f, 0.f, 0.f};
+  if (p.bias && n_ok) {
+    const float4 t = *reinterpret_cast<const float4*>(p.bias + (int64_t)(KIND == KIND_LINEAR ? z : 0) * p.bias_bs + n);
+    bias[0] = t.x; bias[1] = t.y; bias[2] = t.z; bias[3] = t.w;
+  }
+  if (p.col_stats) {
+    for (int i = tid; i < 2 * TN; i += NTHREADS) (&s_stats[0][0])[i] = 0.f;
+    __syncthreads();
+  }
+  float cs[4] = {0.f, 0.f, 0.f, 0.f}, cq[4] = {0.f, 0.f, 0.f, 0.f};
+  T* y = (T*)p.y + (KIND == KIND_LINEAR ? z * p.y_bs : 0);
+  T* pre = p.pre ? (T*)p.pre + (KIND == KIND_LINEAR ? z * p.pre_bs : 0) : nullptr;
+  const T* r1 = p.r1 ? (const T*)p.r1 + (KIND == KIND_LINEAR ? z * p.r1_bs : 0) : nullptr;
+  const T* r2 = p.r2 ? (const T*)p.r2 + (KIND == KIND_LINEAR ? z * p.r2_bs : 0) : nullptr;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int64_t m = m0 + ty * 8 + i;
+    if (m >= p.M || !n_ok) continue;
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      v[j] = acc[i][j] + bias[j];
+      cs[j] += v[j]; cq[j] += v[j] * v[j];
+    }
+    if (pre) store4(pre + out_row_offset<KIND>(p, m, phase, p.ldpre) + n, v);
+    if (p.epilogue == TFSWA_EPI_GELU) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = gelu_erf(v[j]);
+    }
+    if (r1) { float t[4]; load4(r1 + m * p.ldr1 + n, t);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] += t[j]; }
+    if (r2) { float t[4]; load4(r2 + m * p.ldr2 + n, t);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] += t[j]; }
+    store4(y + out_row_offset<KIND>(p, m, phase, p.ldy) + n, v);
+  }
+  if (p.col_stats) {
+    if (n_ok) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { atomicAdd(&s_stats[0][tx * 4 + j], cs[j]); atomicAdd(&s_stats[1][tx * 4 + j], cq[j]); }
+    }
+    __syncthreads();
+    for (int i = tid; i < 2 * TN; i += NTHREADS) {
+      const int which = i / TN, c = i % TN;
+      if (n0 + c < p.N) atomicAdd(p.col_stats + (int64_t)which * p.N + n0 + c, s_stats[which][c]);
+    }
+  }
+}
+
+template <typename T, int KIND>
+static int launch_igemm(const IgemmParams& p, int zdim, cudaStream_t st) {
+  if (p.N <= 32) {
+    constexpr int TN = 32, TM = (NTHREADS / (TN / 4)) * 8;
+    dim3 grid((unsigned)ceil_div64(p.M, TM), (p.N + TN - 1) / TN, zdim);
+    igemm_kernel<T, KIND, TN><<<grid, NTHREADS, 0, st>>>(p);
+  } else {
+    constexpr int TN = 64, TM = (NTHREADS / (TN / 4)) * 8;
+    dim3 grid((unsigned)ceil_div64(p.M, TM), (p.N + TN - 1) / TN, zdim);
+    igemm_kernel<T, KIND, TN><<<grid, NTHREADS, 0, st>>>(p);
+  }
+  return check_launch("igemm");
+}
+
+}  // namespace tfswa
+
+using namespace tfswa;
+
+extern "C" {
+
+int tfswa_linear_fwd(const tfswa_linear_args* a, void* stream) {
+  TFSWA_REQUIRE(a && a->x && a->w && a->y, "linear: null pointer");
+  TFSWA_REQUIRE(a->M > 0 && a->N > 0 && a->K > 0 && a->batch > 0, "linear: empty problem");
+  TFSWA_REQUIRE(a->K % 8 == 0 && a->N % 4 == 0, "linear: need K%%8==0 and N%%4==0 (K=%d N=%d)", a->K, a->N);
+  TFSWA_REQUIRE(a->ldx % 8 == 0 && a->ldy % 4 == 0 && a->x_bs % 8 == 0 && a->y_bs % 4 == 0,
+                "linear: leading dims / batch strides must keep 16-byte alignment");
+  TFSWA_REQUIRE(!(a->prologue & TFSWA_PRO_LNHAT) || a->row_stats, "linear: PRO_LNHAT needs row_stats");
+  TFSWA_REQUIRE(!(a->prologue & TFSWA_PRO_AFFINE) || (a->in_scale && a->in_shift), "linear: PRO_AFFINE needs in_scale/in_shift");
+  TFSWA_REQUIRE(!a->r1 || a->ldr1 % 4 == 0, "linear: ldr1 alignment");
+  TFSWA_REQUIRE(!a->r2 || a->ldr2 % 4 == 0, "linear: ldr2 alignment");
+  TFSWA_REQUIRE(!a->pre || a->ldpre % 4 == 0, "linear: ldpre alignment");
+  TFSWA_REQUIRE(!a->col_stats || a->batch == 1, "linear: col_stats only with batch==1");
+  TFSWA_REQUIRE(a->batch <= 65535, "linear: batch too large");
+  IgemmParams p = {};
+  p.x = a->x; p.ldx = a->ldx; p.w = a->w; p.bias = a->bias; p.row_stats = a->row_stats;
+  p.in_scale = a->in_scale; p.in_shift = a->in_shift;
+  p.r1 = a->r1; p.ldr1 = a->ldr1; p.r2 = a->r2; p.ldr2 = a->ldr2;
+  p.y = a->y; p.ldy = a->ldy; p.pre = a->pre; p.ldpre = a->ldpre; p.col_stats = a->col_stats;
+  p.M = a->M; p.N = a->N; p.K = a->K; p.prologue = a->prologue; p.epilogue = a->epilogue;
+  p.x_bs = a->x_bs; p.w_bs = a->w_bs; p.bias_bs = a->bias_bs; p.rs_bs = a->rs_bs; p.r1_bs = a->r1_bs; p.r2_bs = a->r2_bs;
+  p.y_bs = a->y_bs; p.pre_bs = a->pre_bs;
+  if (a->dtype == TFSWA_F32) return launch_igemm<float, KIND_LINEAR>(p, a->batch, (cudaStream_t)stream);
+  if (a->dtype == TFSWA_BF16) return launch_igemm<bf16, KIND_LINEAR>(p, a->batch, (cudaStream_t)stream);
+  TFSWA_REQUIRE(false, "linear: bad dtype %d", a->dtype);
+}
+
+int tfswa_conv_fwd(const tfswa_conv_args* a, void* stream) {
+  TFSWA_REQUIRE(a && a->x && a->w && a->y, "conv: null pointer");
+  TFSWA_REQUIRE(a->B > 0 && a->Hin > 0 && a->Win > 0, "conv: empty problem");
+  TFSWA_REQUIRE(a->Cin % 16 == 0 && a->Cout % 4 == 0, "conv: need Cin%%16==0, Cout%%4==0 (Cin=%d Cout=%d)", a->Cin, a->Cout);
+  IgemmParams p = {};
+  p.x = a->x; p.w = a->w; p.bias = a->bias; p.y = a->y; p.pre = a->pre; p.col_stats = a->col_stats;
+  p.ldy = a->Cout; p.ldpre = a->Cout; p.N = a->Cout; p.epilogue = a->epilogue;
+  p.B = a->B; p.Hin = a->Hin; p.Win = a->Win; p.Cin = a->Cin; p.Hout = a->Hout; p.Wout = a->Wout;
+  int kind, zdim = 1;
+  if (a->kind == 0) {
+    TFSWA_REQUIRE(a->Hout == a->Hin && a->Wout == a->Win, "conv3x3: output size must equal input size");
+    kind = KIND_CONV3; p.K = 9 * a->Cin; p.M = (int64_t)a->B * a->Hout * a->Wout;
+  } else if (a->kind == 1) {
+    TFSWA_REQUIRE(a->Hout == (a->Hin - 2) / 2 + 1 && a->Wout == (a->Win - 2) / 2 + 1, "down conv: bad output size");
+    kind = KIND_DOWN; p.K = 16 * a->Cin; p.M = (int64_t)a->B * a->Hout * a->Wout;
+  } else if (a->kind == 2) {
+    TFSWA_REQUIRE(a->Hout == 2 * a->Hin && a->Wout == 2 * a->Win, "up conv: output must be 2x input");
+    TFSWA_REQUIRE(!a->col_stats || true, "unused");
+    kind = KIND_UP; p.K = 4 * a->Cin; p.M = (int64_t)a->B * a->Hin * a->Win; zdim = 4;
+    p.w_bs = (int64_t)a->Cout * 4 * a->Cin;
+  } else TFSWA_REQUIRE(false, "conv: bad kind %d", a->kind);
+  cudaStream_t st = (cudaStream_t)stream;
+#define TFSWA_DISPATCH(T)                                                  \
+  switch (kind) {                                                          \
+    case KIND_CONV3: return launch_igemm<T, KIND_CONV3>(p, zdim, st);      \
+    case KIND_DOWN: return launch_igemm<T, KIND_DOWN>(p, zdim, st);        \
+    default: return launch_igemm<T, KIND_UP>(p, zdim, st);                 \
+  }
+  if (a->dtype == TFSWA_F32) { TFSWA_DISPATCH(float) }
+  if (a->dtype == TFSWA_BF16) { TFSWA_DISPATCH(bf16) }
+#undef TFSWA_DISPATCH
+  TFSWA_REQUIRE(false, "conv: bad dtype %d", a->dtype);
+}
+
+}  // extern "C"

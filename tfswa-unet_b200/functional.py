@@ -1,0 +1,127 @@
+"""Autograd-aware front of the C-ABI primitives.
+
+Each primitive is one ``torch.autograd.Function`` whose forward and backward are C-ABI kernel calls
+(``ops``); PyTorch only owns the graph bookkeeping and the memory.  Under ``torch.no_grad()`` (inference)
+the raw ops are called directly.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+from torch import nn
+
+from . import _lib as L
+from . import ops
+
+Tensor = torch.Tensor
+
+_KIND = {"conv3": 0, "down": 1, "up": 2}
+
+
+def _needs_grad(*ts) -> bool:
+    return torch.is_grad_enabled() and any(t is not None and torch.is_tensor(t) and t.requires_grad for t in ts)
+
+
+def _no_backward(what: str):
+    raise NotImplementedError(f"tfswa_unet_b200: backward of {what} is not available in this build")
+
+
+# ------------------------------------------------------------------------------------------------
+def row_stats(x: Tensor) -> Tensor:
+    # statistics are treated as saved constants of the forward; the LN-hat backward in LinearFn
+    # accounts for their dependence on x analytically.
+    return ops.row_stats(x.detach())
+
+
+def linear(x: Tensor, w: Tensor, bias: Optional[Tensor] = None, *, prologue: int = 0, epilogue: int = 0,
+           row_stats: Optional[Tensor] = None, r1: Optional[Tensor] = None, r2: Optional[Tensor] = None,
+           want_col_stats: bool = False):
+    if _needs_grad(x, w, bias, r1, r2):
+        from .autograd import LinearFn
+        return LinearFn.apply(x, w, bias, row_stats, r1, r2, prologue, epilogue, want_col_stats)
+    if want_col_stats:
+        stats = torch.zeros((2, w.shape[1]), dtype=torch.float32, device=x.device)
+        pre = ops.linear(x, w, bias, prologue=prologue, row_stats=row_stats, col_stats=stats)
+        return pre, stats
+    return ops.linear(x, w, bias, prologue=prologue, epilogue=epilogue, row_stats=row_stats, r1=r1, r2=r2)
+
+
+def attention(qkv: Tensor, B: int, H: int, W: int, C: int, heads: int, geom: int, *, ws: int = 8, shift: int = 0,
+              pad_kv: Optional[Tensor] = None, rel_bias: Optional[Tensor] = None, use_shift_mask: bool = False) -> Tensor:
+    """qkv (M, 3C) view -> (M, C)."""
+    if _needs_grad(qkv, pad_kv, rel_bias):
+        from .autograd import AttentionFn
+        return AttentionFn.apply(qkv, pad_kv, rel_bias, B, H, W, C, heads, geom, ws, shift, use_shift_mask)
+    out = torch.empty((B * H * W, C), dtype=qkv.dtype, device=qkv.device)
+    pk = None if pad_kv is None else pad_kv.contiguous()
+    return ops.attention(qkv, out, B, H, W, C, heads, geom, ws=ws, shift=shift, pad_kv=pk, rel_bias=rel_bias,
+                         use_shift_mask=use_shift_mask)
+
+
+def attention3(qkv3: Tensor, B: int, H: int, W: int, C: int, heads: int, *, ws: int, shift: int, pad_kv: Tensor,
+               rel_bias: Optional[Tensor] = None, use_shift_mask: bool = False) -> Tensor:
+    """qkv3 (M, 3 branches, 3C) -> (M, 3, C): TSA, FSA and SW-MSA cores writing the concat buffer directly."""
+    if _needs_grad(qkv3, pad_kv, rel_bias):
+        from .autograd import Attention3Fn
+        return Attention3Fn.apply(qkv3, pad_kv, rel_bias, B, H, W, C, heads, ws, shift, use_shift_mask)
+    M = B * H * W
+    att = torch.empty((M, 3, C), dtype=qkv3.dtype, device=qkv3.device)
+    pk = pad_kv.contiguous()
+    ops.attention(qkv3[:, 0, :], att[:, 0, :], B, H, W, C, heads, L.GEOM_TSA)
+    ops.attention(qkv3[:, 1, :], att[:, 1, :], B, H, W, C, heads, L.GEOM_FSA)
+    ops.attention(qkv3[:, 2, :], att[:, 2, :], B, H, W, C, heads, L.GEOM_SWA, ws=ws, shift=shift, pad_kv=pk,
+                  rel_bias=rel_bias, use_shift_mask=use_shift_mask)
+    return att
+
+
+def bn_finalize(stats: Tensor, count: int, bn: nn.BatchNorm2d):
+    """Train-mode BatchNorm2d: (scale, shift) from batch statistics + in-place running-stat update."""
+    track = bn.track_running_stats and bn.running_mean is not None
+    if track:
+        bn.num_batches_tracked.add_(1)
+        momentum = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked.item())
+    else:
+        momentum = 0.0
+    if _needs_grad(stats, bn.weight, bn.bias):
+        from .autograd import BNFinalizeFn
+        return BNFinalizeFn.apply(stats, bn.weight, bn.bias, bn.running_mean if track else None,
+                                  bn.running_var if track else None, count, momentum, bn.eps)
+    sc, sh, _ = ops.bn_finalize(stats, count, bn.weight.detach().float().contiguous(), bn.bias.detach().float().contiguous(),
+                                bn.running_mean if track else None, bn.running_var if track else None, momentum, bn.eps)
+    return sc, sh
+
+
+def affine_act(v: Tensor, scale: Optional[Tensor], shift: Optional[Tensor], *, epilogue: int = 0,
+               r1: Optional[Tensor] = None, r2: Optional[Tensor] = None) -> Tensor:
+    if _needs_grad(v, scale, shift, r1, r2):
+        from .autograd import AffineActFn
+        return AffineActFn.apply(v, scale, shift, r1, r2, epilogue)
+    return ops.affine_act(v, scale, shift, epilogue=epilogue, r1=r1, r2=r2)
+
+
+def conv(x: Tensor, wl: Tensor, b: Tensor, kind: str, out_hw, dtype: torch.dtype, *, epilogue: int = 0,
+         want_col_stats: bool = False):
+    if _needs_grad(x, wl, b):
+        from .autograd import ConvFn
+        return ConvFn.apply(x, wl, b, kind, tuple(out_hw), dtype, epilogue, want_col_stats)
+    stats = torch.zeros((2, b.shape[0]), dtype=torch.float32, device=x.device) if want_col_stats else None
+    if kind == "stem":
+        y = ops.stem(x, wl, b, dtype, epilogue=epilogue, col_stats=stats)
+    else:
+        y = ops.conv(x, wl, b, _KIND[kind], out_hw, epilogue=epilogue, col_stats=stats)
+    return (y, stats) if want_col_stats else y
+
+
+def head_tail(v: Tensor, w3: Tensor, b3: Tensor, scale: Optional[Tensor], shift: Optional[Tensor], want_logits: bool = False):
+    if _needs_grad(v, w3, b3, scale, shift):
+        from .autograd import HeadTailFn
+        return HeadTailFn.apply(v, w3, b3, scale, shift, want_logits)
+    return ops.head_tail(v, w3, b3, scale, shift, want_logits=want_logits)
+
+
+def bilinear(x: Tensor, out_hw) -> Tensor:
+    if _needs_grad(x):
+        from .autograd import BilinearFn
+        return BilinearFn.apply(x, tuple(out_hw))
+    return ops.bilinear(x, out_hw)

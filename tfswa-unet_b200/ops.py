@@ -1,0 +1,204 @@
+"""Raw (non-autograd) Python wrappers over the C ABI.  Tensors are CUDA tensors owned by PyTorch;
+the library only sees device pointers, sizes and the current stream.
+
+Activation convention ("native" tensors): NHWC memory, viewed either as a logical-NCHW torch tensor
+with channels_last strides, or as (M, C) / (M, nb, K) token matrices, M = B*H*W.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib as L
+
+Tensor = torch.Tensor
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _dt(t: Tensor) -> int:
+    if t.dtype == torch.bfloat16:
+        return L.BF16
+    if t.dtype == torch.float32:
+        return L.F32
+    raise TypeError(f"unsupported activation dtype {t.dtype}")
+
+
+def _cuda(*ts) -> None:
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("tfswa_unet_b200 runs on CUDA (sm_100a) tensors only - there is no CPU fallback")
+
+
+def _p(t: Optional[Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _f32c(t: Optional[Tensor]) -> Optional[Tensor]:
+    if t is None:
+        return None
+    if t.dtype != torch.float32 or not t.is_contiguous():
+        raise TypeError("weights / statistics must be contiguous fp32 tensors")
+    return t
+
+
+def _tok3(t: Tensor, name: str) -> Tuple[int, int]:
+    """(ld, batch_stride) of a (M, nb, K) token tensor whose last dim is dense."""
+    if t.dim() != 3 or t.stride(2) != 1:
+        raise ValueError(f"{name}: expected (M, nb, K) with a dense last dim, got {tuple(t.shape)} / {t.stride()}")
+    return t.stride(0), (t.stride(1) if t.shape[1] > 1 else 0)
+
+
+def linear(x: Tensor, w: Tensor, bias: Optional[Tensor] = None, *, prologue: int = 0, epilogue: int = 0,
+           row_stats: Optional[Tensor] = None, in_scale: Optional[Tensor] = None, in_shift: Optional[Tensor] = None,
+           r1: Optional[Tensor] = None, r2: Optional[Tensor] = None, save_pre: bool = False,
+           col_stats: Optional[Tensor] = None, out: Optional[Tensor] = None):
+    """y[:, b] = epi(pro(x[:, b]) @ w[b].T + bias[b]) + r1[:, b] + r2[:, b]   (see tfswa_linear_fwd)."""
+    _cuda(x, w)
+    M, nb, K = x.shape
+    nbw, N, Kw = w.shape
+    if nbw != nb or Kw != K:
+        raise ValueError(f"linear: x {tuple(x.shape)} vs w {tuple(w.shape)}")
+    _f32c(w), _f32c(bias), _f32c(row_stats), _f32c(in_scale), _f32c(in_shift), _f32c(col_stats)
+    y = out if out is not None else torch.empty((M, nb, N), dtype=x.dtype, device=x.device)
+    pre = torch.empty((M, nb, N), dtype=x.dtype, device=x.device) if save_pre else None
+    a = L.LinearArgs()
+    a.x = x.data_ptr(); a.ldx, a.x_bs = _tok3(x, "x")
+    a.w = w.data_ptr(); a.w_bs = N * K
+    a.bias = _p(bias); a.bias_bs = N
+    a.row_stats = _p(row_stats); a.rs_bs = 2 * M
+    a.in_scale = _p(in_scale); a.in_shift = _p(in_shift)
+    for name, r in (("r1", r1), ("r2", r2)):
+        if r is not None:
+            if r.dtype != x.dtype or r.shape[0] != M or r.shape[2] != N or r.shape[1] not in (1, nb):
+                raise ValueError(f"linear: residual {name} {tuple(r.shape)}/{r.dtype} incompatible")
+            ld, bs = _tok3(r, name)
+            setattr(a, name, r.data_ptr()); setattr(a, "ld" + name, ld); setattr(a, name + "_bs", bs)
+    a.y = y.data_ptr(); a.ldy, a.y_bs = _tok3(y, "y")
+    if pre is not None:
+        a.pre = pre.data_ptr(); a.ldpre, a.pre_bs = _tok3(pre, "pre")
+    a.col_stats = _p(col_stats)
+    a.M, a.N, a.K = M, N, K
+    a.prologue, a.epilogue, a.batch, a.dtype = prologue, epilogue, nb, _dt(x)
+    L.check(L.lib().tfswa_linear_fwd(C.byref(a), _stream()), "linear_fwd")
+    return (y, pre) if save_pre else y
+
+
+def row_stats(x: Tensor) -> Tensor:
+    """(M, nb, K) -> (nb, M, 2) fp32 {mean, rstd} over K (LayerNorm statistics, eps 1e-5)."""
+    _cuda(x)
+    M, nb, K = x.shape
+    ld, bs = _tok3(x, "x")
+    st = torch.empty((nb, M, 2), dtype=torch.float32, device=x.device)
+    L.check(L.lib().tfswa_row_stats(x.data_ptr(), ld, bs, st.data_ptr(), 2 * M, M, K, nb, _dt(x), _stream()), "row_stats")
+    return st
+
+
+def attention(qkv: Tensor, out: Tensor, B: int, H: int, W: int, C_: int, heads: int, geom: int, *, ws: int = 8,
+              shift: int = 0, pad_kv: Optional[Tensor] = None, rel_bias: Optional[Tensor] = None,
+              use_shift_mask: bool = False, lse: Optional[Tensor] = None) -> Tensor:
+    """qkv: (M, >=3C) view with q|k|v at columns 0|C|2C; out: (M, C) view (both row-strided, dense rows)."""
+    _cuda(qkv, out)
+    if qkv.dim() != 2 or out.dim() != 2 or qkv.stride(1) != 1 or out.stride(1) != 1:
+        raise ValueError("attention: qkv/out must be 2-D row-strided views")
+    if qkv.shape[0] != B * H * W or out.shape[0] != B * H * W or qkv.shape[1] != 3 * C_ or out.shape[1] != C_:
+        raise ValueError(f"attention: bad shapes qkv {tuple(qkv.shape)} out {tuple(out.shape)}")
+    _f32c(pad_kv), _f32c(rel_bias), _f32c(lse)
+    a = L.AttnArgs()
+    a.qkv, a.ldq, a.out, a.ldo = qkv.data_ptr(), qkv.stride(0), out.data_ptr(), out.stride(0)
+    a.lse, a.pad_kv, a.rel_bias = _p(lse), _p(pad_kv), _p(rel_bias)
+    a.B, a.H, a.W, a.C, a.heads = B, H, W, C_, heads
+    a.geom, a.ws, a.shift, a.use_shift_mask, a.dtype = geom, ws, shift, int(use_shift_mask), _dt(qkv)
+    L.check(L.lib().tfswa_attn_fwd(C.byref(a), _stream()), "attn_fwd")
+    return out
+
+
+def conv(x: Tensor, w: Tensor, bias: Tensor, kind: int, out_hw: Tuple[int, int], *, epilogue: int = 0,
+         save_pre: bool = False, col_stats: Optional[Tensor] = None):
+    """x: native (B, Cin, Hin, Win) channels_last; w already re-laid-out (see tfswa_conv_args)."""
+    _cuda(x, w)
+    B, Cin, Hin, Win = x.shape
+    Hout, Wout = out_hw
+    Cout = bias.shape[0]
+    _f32c(w), _f32c(bias), _f32c(col_stats)
+    y = torch.empty((B, Cout, Hout, Wout), dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
+    pre = torch.empty_like(y) if save_pre else None
+    a = L.ConvArgs()
+    a.x, a.y, a.pre, a.w, a.bias, a.col_stats = x.data_ptr(), y.data_ptr(), _p(pre), w.data_ptr(), bias.data_ptr(), _p(col_stats)
+    a.B, a.Hin, a.Win, a.Cin, a.Hout, a.Wout, a.Cout = B, Hin, Win, Cin, Hout, Wout, Cout
+    a.kind, a.epilogue, a.dtype = kind, epilogue, _dt(x)
+    L.check(L.lib().tfswa_conv_fwd(C.byref(a), _stream()), "conv_fwd")
+    return (y, pre) if save_pre else y
+
+
+def stem(x_nchw: Tensor, w: Tensor, bias: Tensor, dtype: torch.dtype, *, epilogue: int = 0, save_pre: bool = False,
+         col_stats: Optional[Tensor] = None):
+    _cuda(x_nchw, w)
+    if x_nchw.dtype != torch.float32 or not x_nchw.is_contiguous():
+        raise TypeError("stem: model input must be a contiguous fp32 NCHW tensor")
+    B, Cin, H, W = x_nchw.shape
+    Cout = w.shape[0]
+    _f32c(w), _f32c(bias), _f32c(col_stats)
+    y = torch.empty((B, Cout, H, W), dtype=dtype, device=x_nchw.device, memory_format=torch.channels_last)
+    pre = torch.empty_like(y) if save_pre else None
+    L.check(L.lib().tfswa_stem_fwd(x_nchw.data_ptr(), w.data_ptr(), bias.data_ptr(), y.data_ptr(), _p(pre), _p(col_stats),
+                                   B, Cin, H, W, Cout, epilogue, _dt(y), _stream()), "stem_fwd")
+    return (y, pre) if save_pre else y
+
+
+def head_tail(v: Tensor, w3: Tensor, b3: Tensor, scale: Optional[Tensor] = None, shift: Optional[Tensor] = None,
+              want_logits: bool = False):
+    _cuda(v, w3)
+    B, C_, H, W = v.shape
+    Cout = w3.shape[0]
+    _f32c(w3), _f32c(b3), _f32c(scale), _f32c(shift)
+    masks = torch.empty((B, Cout, H, W), dtype=torch.float32, device=v.device)
+    logits = torch.empty_like(masks) if want_logits else None
+    L.check(L.lib().tfswa_head_tail_fwd(v.data_ptr(), _p(scale), _p(shift), w3.data_ptr(), b3.data_ptr(), masks.data_ptr(),
+                                        _p(logits), B, H, W, C_, Cout, _dt(v), _stream()), "head_tail_fwd")
+    return (masks, logits) if want_logits else masks
+
+
+def bn_finalize(col_stats: Tensor, count: int, gamma: Tensor, beta: Tensor, running_mean: Optional[Tensor],
+                running_var: Optional[Tensor], momentum: float, eps: float):
+    """-> (scale, shift, save_mean_rstd); updates running stats in place (train-mode BatchNorm2d)."""
+    _cuda(col_stats)
+    Cn = gamma.shape[0]
+    scale = torch.empty(Cn, dtype=torch.float32, device=col_stats.device)
+    shift = torch.empty_like(scale)
+    save = torch.empty((2, Cn), dtype=torch.float32, device=col_stats.device)
+    L.check(L.lib().tfswa_bn_finalize(col_stats.data_ptr(), count, gamma.data_ptr(), beta.data_ptr(), _p(running_mean),
+                                      _p(running_var), momentum, eps, scale.data_ptr(), shift.data_ptr(), save.data_ptr(),
+                                      Cn, _stream()), "bn_finalize")
+    return scale, shift, save
+
+
+def affine_act(v: Tensor, scale: Optional[Tensor], shift: Optional[Tensor], *, epilogue: int = 0,
+               r1: Optional[Tensor] = None, r2: Optional[Tensor] = None) -> Tensor:
+    """native (B,C,H,W) channels_last (or any dense (..., C) token tensor): y = act(v*scale+shift)+r1+r2."""
+    _cuda(v)
+    Cn = v.shape[1] if v.dim() == 4 else v.shape[-1]
+    y = torch.empty_like(v)
+    def dense(t):
+        return t.is_contiguous(memory_format=torch.channels_last) if t.dim() == 4 else t.is_contiguous()
+    if not dense(v):
+        raise ValueError("affine_act: v must be a dense NHWC tensor")
+    for r in (r1, r2):
+        if r is not None and (r.shape != v.shape or not dense(r) or r.dtype != v.dtype):
+            raise ValueError("affine_act: residual must match v's shape, layout and dtype")
+    L.check(L.lib().tfswa_affine_act(v.data_ptr(), _p(scale), _p(shift), _p(r1), _p(r2), y.data_ptr(), v.numel() // Cn, Cn,
+                                     epilogue, _dt(v), _stream()), "affine_act")
+    return y
+
+
+def bilinear(x: Tensor, out_hw: Tuple[int, int]) -> Tensor:
+    _cuda(x)
+    B, Cn, Hin, Win = x.shape
+    y = torch.empty((B, Cn, out_hw[0], out_hw[1]), dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
+    L.check(L.lib().tfswa_bilinear_fwd(x.data_ptr(), y.data_ptr(), B, Hin, Win, out_hw[0], out_hw[1], Cn, _dt(x), _stream()),
+            "bilinear_fwd")
+    return y
