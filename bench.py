@@ -1,0 +1,329 @@
+#!/usr/bin/env python
+"""bench.py - headline benchmark of the TFSWA-UNet hot path on B200 (contract: see DESIGN.md section 6).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[2], "C3"): full-model forward of TFSWAUNet(2,2,[2,2,6,2],[32,64,128,256],8,4,8),
+eval mode, on a batch of 8 synthetic 6-second stereo segments per GPU (n_fft 2048, hop 512 -> (8,2,1025,517)),
+random-init weights, bf16 activations with fp32 accumulation.  metric = separated audio-seconds per second
+(= N * 8 * 6 s / step time), whole job over all N GPUs, weak scaling (no data-path collective: segments are
+independent; ranks only meet in the timing barrier).
+
+A "step" is one forward over one batch.  `value` times it with inputs resident in HBM; `e2e` times the same call
+through the public module API with pinned-host inputs (H2D) and the masks read back (D2H) inside the timed region.
+`--impl reference` times the reference's own CPU path (the oracle port of it: /root/reference is not on the GPU
+box) on the host cores, on a bounded crop of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+SEG_SECONDS = 6.0
+H_BINS, W_FRAMES = 1025, 517
+BATCH = 8
+SEC_PER_FRAME = SEG_SECONDS / W_FRAMES      # 512 / 44100 s
+METRIC = "separated audio-seconds/sec (fwd)"
+UNIT = "audio-s/s"
+MODEL_ARGS = dict(in_channels=2, out_channels=2, depths=[2, 2, 6, 2], dims=[32, 64, 128, 256], window_size=8,
+                  shift_size=4, num_heads=8)
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"],
+                "bf16_tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi in the background during the timed region)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0: float, t1: float):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for t, line in self.rows:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 6 or not (t0 - 0.05 <= t <= t1 + 0.05):
+                continue
+            try:
+                sm.append(float(parts[0])); smax = float(parts[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the oracle port of the reference's eager CPU path on a bounded crop
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_model():
+    from oracle import tfswa_oracle as O
+    import tfswa_unet_b200 as T
+    torch.manual_seed(0)
+    m = T.TFSWAUNet(**MODEL_ARGS).eval()      # parameter container only (random init, reference _init_weights recipe)
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    return O, sd
+
+
+def cpu_forward_seconds(O, sd, frames: int, repeats: int = 1):
+    x = torch.randn(1, 2, H_BINS, frames)
+    best = None
+    with torch.no_grad():
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            O.unet_forward(x, sd)
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+    return best
+
+
+def pick_crop(O, sd, budget_s: float):
+    """choose the number of STFT frames (multiple of 8, >= 8) so one forward costs about `budget_s` on this host"""
+    t8 = cpu_forward_seconds(O, sd, 8)
+    # cost grows faster than linearly in the number of frames (FSA is quadratic in it) -> 0.5 safety factor;
+    # capped at 128 frames so the unchunked oracle's (frames, 8, 1025, 1025) fp32 scores stay below ~5 GB of host RAM
+    frames = int(max(8, min(128, 0.5 * (budget_s / max(t8, 1e-3)) * 8)) // 8 * 8)
+    return max(frames, 8), t8
+
+
+def cpu_baseline(budget_s: float = 15.0):
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    O, sd = cpu_reference_model()
+    frames, _ = pick_crop(O, sd, budget_s)
+    dt = cpu_forward_seconds(O, sd, frames)
+    return {"value": frames * SEC_PER_FRAME / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"one eval forward of a (1,2,{H_BINS},{frames}) crop of a 6 s segment "
+                      f"({frames * SEC_PER_FRAME:.2f} audio-s) in {dt:.1f} s, fp32 torch CPU, oracle/tfswa_oracle.py"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    O, sd = cpu_reference_model()
+    budget = max(2.0, 150.0 / max(1, args.steps + args.warmup))
+    frames, _ = pick_crop(O, sd, budget)
+    for _ in range(args.warmup):
+        cpu_forward_seconds(O, sd, frames)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_forward_seconds(O, sd, frames)
+    dt = (time.perf_counter() - t0) / max(1, args.steps)
+    value = frames * SEC_PER_FRAME / dt
+    sample = (f"each step = one eval forward of a (1,2,{H_BINS},{frames}) crop of a 6 s segment "
+              f"({frames * SEC_PER_FRAME:.2f} audio-s), fp32 torch CPU with {cores} threads (oracle port of the reference eager path)")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "C3 crop: TFSWAUNet fwd, eval, CPU", "frames": frames, "bins": H_BINS, "batch": 1},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import tfswa_unet_b200 as T
+    from tfswa_unet_b200 import ops
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a B200: the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist = dist_
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    T.set_precision(args.precision)
+    torch.manual_seed(0)
+    model = T.TFSWAUNet(**MODEL_ARGS).eval().to(dev)
+    B = args.batch
+    g = torch.Generator().manual_seed(1234 + rank)
+    x_host = torch.randn((B, 2, H_BINS, W_FRAMES), generator=g).pin_memory()
+    x_dev = x_host.to(dev)
+    out_host = torch.empty((B, 2, H_BINS, W_FRAMES), dtype=torch.float32).pin_memory()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            y = model(x_dev)
+        assert bool(torch.isfinite(y).all()), "non-finite masks"
+        # ---------------- timed region: device-resident inputs ----------------
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+            time.sleep(0.3)
+        ops.enable_timing(True)
+        ops.reset_launch_count()
+        barrier()
+        t_wall0 = time.time()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            y = model(x_dev)
+        e1.record()
+        barrier()
+        t_wall1 = time.time()
+        ms = e0.elapsed_time(e1)
+        launches = ops.reset_launch_count()
+        kern = ops.collect_timing()
+        ops.enable_timing(False)
+        clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+        # ---------------- e2e: pinned host input -> H2D -> model -> D2H masks ----------------
+        for _ in range(2):
+            out_host.copy_(model(x_host.to(dev, non_blocking=True)), non_blocking=True)
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for _ in range(args.steps):
+            xd = x_host.to(dev, non_blocking=True)
+            out_host.copy_(model(xd), non_blocking=True)
+        f1.record()
+        barrier()
+        ms_e2e = f0.elapsed_time(f1)
+
+    if dist is not None:
+        t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = float(t[0]), float(t[1])
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    peaks = load_peaks()
+    step_ms = ms / args.steps
+    audio_s = world * B * SEG_SECONDS
+    value = audio_s / (step_ms / 1e3)
+    e2e_value = audio_s / (ms_e2e / args.steps / 1e3)
+
+    # ---- roofline of the dominant kernel class (largest share of the timed region) ----
+    total_kernel_ms = sum(k["ms"] for k in kern.values()) or 1.0
+    classes = {}
+    for tag, k in kern.items():
+        cls = tag.split("[")[0]
+        c = classes.setdefault(cls, {"ms": 0.0, "launches": 0, "flops": 0, "bytes": 0})
+        for f in c:
+            c[f] += k[f]
+    dom_name, dom = max(classes.items(), key=lambda kv: kv[1]["ms"])
+    prof = {}
+    prof_path = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(prof_path):
+        with open(prof_path) as f:
+            prof = json.load(f)
+    if dom["flops"] > 0 and dom_name in ("tfswa_linear_fwd", "linear", "attn", "tfswa_attn_fwd", "tfswa_conv_fwd", "fused"):
+        achieved = dom["flops"] / (dom["ms"] / 1e3) / 1e12
+        peak = peaks["bf16_tflops_sustained"]
+        roof = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak}
+    else:
+        achieved = dom["bytes"] / (dom["ms"] / 1e3) / 1e9
+        peak = peaks["hbm_gbs"]
+        roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak}
+    roof.update({"traffic": prof.get(dom_name, {}).get("dram_bytes_per_launch"), "kernel": dom_name,
+                 "launches_per_step": dom["launches"] / args.steps, "avg_launch_ms": dom["ms"] / max(1, dom["launches"]),
+                 "share_of_step": dom["ms"] / total_kernel_ms, "peak_source": peaks["source"],
+                 "algorithmic_per_step": {"flops": dom["flops"] / args.steps, "bytes": dom["bytes"] / args.steps}})
+    breakdown = {cls: {"ms_per_step": c["ms"] / args.steps, "share": c["ms"] / total_kernel_ms,
+                       "launches_per_step": c["launches"] / args.steps,
+                       "tflops": (c["flops"] / (c["ms"] / 1e3) / 1e12) if c["ms"] > 0 and c["flops"] else None}
+                 for cls, c in sorted(classes.items(), key=lambda kv: -kv[1]["ms"])}
+
+    from oracle.tfswa_oracle import count_model_flops
+    flops = count_model_flops(B, 2, 2, H_BINS, W_FRAMES)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": args.precision if args.precision == "bf16" else "f32", "data": "synthetic",
+        "config": {"workload": f"C3: TFSWAUNet(2,2,[2,2,6,2],[32,64,128,256],8,4,8) eval forward, batch {B} x 6 s segments "
+                               f"(n_fft 2048, hop 512 -> (B,2,{H_BINS},{W_FRAMES})) per GPU, random-init weights",
+                   "batch_per_gpu": B, "segment_seconds": SEG_SECONDS,
+                   "l2": "working set >> 126 MB L2 (stage-1 token tensor alone is 271 MB bf16); no explicit flush needed",
+                   "parallelism": f"dp{world} (independent segments, no data-path collective)"},
+        "model_tflop_per_step": flops / 1e12 * world, "achieved_model_tflops": flops / 1e12 * world / (step_ms / 1e3),
+        "roofline": roof, "kernel_breakdown": breakdown,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": x_host.numel() * 4 * world,
+                "d2h_bytes_per_step": out_host.numel() * 4 * world, "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": launches, "clocks": clocks,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline()
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

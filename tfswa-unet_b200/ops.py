@@ -20,6 +20,49 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+# ---- launch accounting: every C-ABI compute call is exactly one kernel launch -------------------
+LAUNCHES = 0
+_TIMING = None          # None, or {kernel tag: [(start_event, end_event, work_dict), ...]}
+_TAG = None
+
+
+def reset_launch_count() -> int:
+    global LAUNCHES
+    n, LAUNCHES = LAUNCHES, 0
+    return n
+
+
+def enable_timing(on: bool) -> None:
+    """Per-launch CUDA-event timing on the launching stream (used by bench.py for the roofline figures)."""
+    global _TIMING
+    _TIMING = {} if on else None
+
+
+def collect_timing():
+    """-> {tag: {"launches": n, "ms": total, "flops": F, "bytes": B}}; call after torch.cuda.synchronize()."""
+    out = {}
+    for tag, recs in (_TIMING or {}).items():
+        ms = sum(s.elapsed_time(e) for s, e, _ in recs)
+        out[tag] = {"launches": len(recs), "ms": ms, "flops": sum(w.get("flops", 0) for _, _, w in recs),
+                    "bytes": sum(w.get("bytes", 0) for _, _, w in recs)}
+    return out
+
+
+def _call(name: str, *args, tag: str = None, work: dict = None) -> None:
+    global LAUNCHES
+    fn = getattr(L.lib(), name)
+    if _TIMING is not None:
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        rc = fn(*args)
+        e.record()
+        _TIMING.setdefault(tag or name, []).append((s, e, work or {}))
+    else:
+        rc = fn(*args)
+    LAUNCHES += 1
+    L.check(rc, name)
+
+
 def _dt(t: Tensor) -> int:
     if t.dtype == torch.bfloat16:
         return L.BF16
@@ -84,7 +127,8 @@ def linear(x: Tensor, w: Tensor, bias: Optional[Tensor] = None, *, prologue: int
     a.col_stats = _p(col_stats)
     a.M, a.N, a.K = M, N, K
     a.prologue, a.epilogue, a.batch, a.dtype = prologue, epilogue, nb, _dt(x)
-    L.check(L.lib().tfswa_linear_fwd(C.byref(a), _stream()), "linear_fwd")
+    _call("tfswa_linear_fwd", C.byref(a), _stream(), tag=f"linear[K={K},N={N},nb={nb}]",
+          work={"flops": 2 * M * N * K * nb, "bytes": x.element_size() * M * nb * (K + N)})
     return (y, pre) if save_pre else y
 
 
@@ -94,7 +138,7 @@ def row_stats(x: Tensor) -> Tensor:
     M, nb, K = x.shape
     ld, bs = _tok3(x, "x")
     st = torch.empty((nb, M, 2), dtype=torch.float32, device=x.device)
-    L.check(L.lib().tfswa_row_stats(x.data_ptr(), ld, bs, st.data_ptr(), 2 * M, M, K, nb, _dt(x), _stream()), "row_stats")
+    _call("tfswa_row_stats", x.data_ptr(), ld, bs, st.data_ptr(), 2 * M, M, K, nb, _dt(x), _stream())
     return st
 
 
@@ -113,8 +157,19 @@ def attention(qkv: Tensor, out: Tensor, B: int, H: int, W: int, C_: int, heads: 
     a.lse, a.pad_kv, a.rel_bias = _p(lse), _p(pad_kv), _p(rel_bias)
     a.B, a.H, a.W, a.C, a.heads = B, H, W, C_, heads
     a.geom, a.ws, a.shift, a.use_shift_mask, a.dtype = geom, ws, shift, int(use_shift_mask), _dt(qkv)
-    L.check(L.lib().tfswa_attn_fwd(C.byref(a), _stream()), "attn_fwd")
+    _call("tfswa_attn_fwd", C.byref(a), _stream(), tag=f"attn[{('tsa', 'fsa', 'swa')[geom]},d={C_ // heads}]",
+          work=_attn_work(B, H, W, C_, geom, ws, qkv.element_size()))
     return out
+
+
+def _attn_work(B, H, W, C_, geom, ws, esize):
+    """algorithmic work of one attention launch: 4*tokens*N*C FLOPs (QK^T + PV), one exp per score element per head"""
+    if geom == L.GEOM_SWA:
+        Hp, Wp = -(-H // ws) * ws, -(-W // ws) * ws
+        toks, N = B * Hp * Wp, ws * ws
+    else:
+        toks, N = B * H * W, (H if geom == L.GEOM_TSA else W)
+    return {"flops": 4 * toks * N * C_, "bytes": esize * B * H * W * 4 * C_, "exps": toks * N}
 
 
 def conv(x: Tensor, w: Tensor, bias: Tensor, kind: int, out_hw: Tuple[int, int], *, epilogue: int = 0,
@@ -131,7 +186,7 @@ def conv(x: Tensor, w: Tensor, bias: Tensor, kind: int, out_hw: Tuple[int, int],
     a.x, a.y, a.pre, a.w, a.bias, a.col_stats = x.data_ptr(), y.data_ptr(), _p(pre), w.data_ptr(), bias.data_ptr(), _p(col_stats)
     a.B, a.Hin, a.Win, a.Cin, a.Hout, a.Wout, a.Cout = B, Hin, Win, Cin, Hout, Wout, Cout
     a.kind, a.epilogue, a.dtype = kind, epilogue, _dt(x)
-    L.check(L.lib().tfswa_conv_fwd(C.byref(a), _stream()), "conv_fwd")
+    _call("tfswa_conv_fwd", C.byref(a), _stream())
     return (y, pre) if save_pre else y
 
 
@@ -145,8 +200,8 @@ def stem(x_nchw: Tensor, w: Tensor, bias: Tensor, dtype: torch.dtype, *, epilogu
     _f32c(w), _f32c(bias), _f32c(col_stats)
     y = torch.empty((B, Cout, H, W), dtype=dtype, device=x_nchw.device, memory_format=torch.channels_last)
     pre = torch.empty_like(y) if save_pre else None
-    L.check(L.lib().tfswa_stem_fwd(x_nchw.data_ptr(), w.data_ptr(), bias.data_ptr(), y.data_ptr(), _p(pre), _p(col_stats),
-                                   B, Cin, H, W, Cout, epilogue, _dt(y), _stream()), "stem_fwd")
+    _call("tfswa_stem_fwd", x_nchw.data_ptr(), w.data_ptr(), bias.data_ptr(), y.data_ptr(), _p(pre), _p(col_stats),
+                                   B, Cin, H, W, Cout, epilogue, _dt(y), _stream())
     return (y, pre) if save_pre else y
 
 
@@ -158,8 +213,8 @@ def head_tail(v: Tensor, w3: Tensor, b3: Tensor, scale: Optional[Tensor] = None,
     _f32c(w3), _f32c(b3), _f32c(scale), _f32c(shift)
     masks = torch.empty((B, Cout, H, W), dtype=torch.float32, device=v.device)
     logits = torch.empty_like(masks) if want_logits else None
-    L.check(L.lib().tfswa_head_tail_fwd(v.data_ptr(), _p(scale), _p(shift), w3.data_ptr(), b3.data_ptr(), masks.data_ptr(),
-                                        _p(logits), B, H, W, C_, Cout, _dt(v), _stream()), "head_tail_fwd")
+    _call("tfswa_head_tail_fwd", v.data_ptr(), _p(scale), _p(shift), w3.data_ptr(), b3.data_ptr(), masks.data_ptr(),
+                                        _p(logits), B, H, W, C_, Cout, _dt(v), _stream())
     return (masks, logits) if want_logits else masks
 
 
@@ -171,9 +226,9 @@ def bn_finalize(col_stats: Tensor, count: int, gamma: Tensor, beta: Tensor, runn
     scale = torch.empty(Cn, dtype=torch.float32, device=col_stats.device)
     shift = torch.empty_like(scale)
     save = torch.empty((2, Cn), dtype=torch.float32, device=col_stats.device)
-    L.check(L.lib().tfswa_bn_finalize(col_stats.data_ptr(), count, gamma.data_ptr(), beta.data_ptr(), _p(running_mean),
+    _call("tfswa_bn_finalize", col_stats.data_ptr(), count, gamma.data_ptr(), beta.data_ptr(), _p(running_mean),
                                       _p(running_var), momentum, eps, scale.data_ptr(), shift.data_ptr(), save.data_ptr(),
-                                      Cn, _stream()), "bn_finalize")
+                                      Cn, _stream())
     return scale, shift, save
 
 
@@ -190,8 +245,8 @@ def affine_act(v: Tensor, scale: Optional[Tensor], shift: Optional[Tensor], *, e
     for r in (r1, r2):
         if r is not None and (r.shape != v.shape or not dense(r) or r.dtype != v.dtype):
             raise ValueError("affine_act: residual must match v's shape, layout and dtype")
-    L.check(L.lib().tfswa_affine_act(v.data_ptr(), _p(scale), _p(shift), _p(r1), _p(r2), y.data_ptr(), v.numel() // Cn, Cn,
-                                     epilogue, _dt(v), _stream()), "affine_act")
+    _call("tfswa_affine_act", v.data_ptr(), _p(scale), _p(shift), _p(r1), _p(r2), y.data_ptr(), v.numel() // Cn, Cn,
+                                     epilogue, _dt(v), _stream())
     return y
 
 
