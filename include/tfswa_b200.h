@@ -70,6 +70,13 @@ typedef struct {
 } tfswa_linear_args;
 int tfswa_linear_fwd(const tfswa_linear_args* a, void* stream);
 
+/* Same contract on the tcgen05 tensor cores (bf16 activations only; TMA-fed, TMEM accumulators).  w_bf16: (batch,N,K)
+ * bf16 copy of the weights.  TFSWA_PRO_LNHAT is applied algebraically in the epilogue,
+ *   LN_hat(x) W^T = rstd*(x W^T - mean*wsum),  wsum[n] = sum_k w_bf16[n][k]  ((batch,N) fp32),
+ * so the MMA reads the raw activations.  Supports prologue NONE/LNHAT, epilogue NONE/GELU, r1, r2; returns
+ * TFSWA_EINVAL for pre / col_stats / AFFINE / GELU-prologue requests (use tfswa_linear_fwd for those). */
+int tfswa_linear_tc_fwd(const tfswa_linear_args* a, const void* w_bf16, const float* wsum, void* stream);
+
 /* per-row LayerNorm statistics {mean, rstd} over K channels, eps 1e-5 (F.layer_norm, attention.py:146,159) */
 int tfswa_row_stats(const void* x, int64_t ldx, int64_t x_bs, float* stats, int64_t st_bs,
                     int64_t M, int32_t K, int32_t batch, int32_t dtype, void* stream);

@@ -53,6 +53,7 @@ SIGNATURES = {
     "tfswa_version": (C.c_char_p, []),
     "tfswa_device_supported": (C.c_int, []),
     "tfswa_linear_fwd": (C.c_int, [C.POINTER(LinearArgs), _p]),
+    "tfswa_linear_tc_fwd": (C.c_int, [C.POINTER(LinearArgs), _p, _p, _p]),
     "tfswa_row_stats": (C.c_int, [_p, _i64, _i64, _p, _i64, _i64, _i32, _i32, _i32, _p]),
     "tfswa_attn_fwd": (C.c_int, [C.POINTER(AttnArgs), _p]),
     "tfswa_conv_fwd": (C.c_int, [C.POINTER(ConvArgs), _p]),

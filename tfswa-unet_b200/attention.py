@@ -64,9 +64,9 @@ class MultiHeadAttention(nn.Module):
         if not x.is_cuda:
             raise RuntimeError("tfswa_unet_b200 modules run on CUDA (sm_100a) tensors only - there is no CPU fallback")
         xt = x.to(dt).reshape(R * N, 1, C)
-        qkv = Fn.linear(xt, self.qkv.weight.float()[None].contiguous(), None)
+        qkv = Fn.linear(xt, Fn.LinW(self.qkv.weight[None], None))
         att = Fn.attention(qkv[:, 0, :], R, 1, N, C, self.num_heads, L.GEOM_FSA)      # rows = (b, h=0), sequence along W=N
-        y = Fn.linear(att[:, None, :], self.proj.weight.float()[None].contiguous(), self.proj.bias.float()[None].contiguous())
+        y = Fn.linear(att[:, None, :], Fn.LinW(self.proj.weight[None], self.proj.bias[None]))
         return y.reshape(R, N, C).to(x.dtype)
 
 

@@ -1,0 +1,258 @@
+// Token GEMM on the 5th-generation tensor cores:  Y = epi(LN?(X) W^T + bias) (+R1) (+R2), bf16 in, fp32 accumulate.
+//
+//   * X (tokens x K) and W (N x K) tiles are brought to shared memory by TMA (cp.async.bulk.tensor, 128B/64B swizzle)
+//     through a multi-stage mbarrier ring; one elected thread issues tcgen05.mma (M=128, N=BN<=256, K=16) with the
+//     accumulator in TMEM; four epilogue warps read it back with tcgen05.ld (one token row per thread).
+//   * LayerNorm never touches the A operand: with the LN affine folded into W by the host,
+//        LN_hat(x) W^T = rstd * (x W^T - mean * rowsum(W)),
+//     so the MMA consumes the raw bf16 activations and the epilogue applies (mean, rstd, wsum) per row/column.
+//     (This is also more accurate than rounding the normalised activations to bf16 before the MMA.)
+//   * bias, exact-erf GELU and up to two residual streams are fused in the epilogue.
+//
+// Replaces the ATen mm/addmm + layer_norm + gelu + add sequences at attention.py:70,86,121-128,146,159 and the
+// 1x1 convs of blocks.py:53-56,85-89.  One output tile (128 x BN) per CTA, 2-3 CTAs resident per SM so one CTA's
+// epilogue overlaps another's loads/MMAs; these GEMMs are HBM-bound (K <= 1024), so the aim is bytes/s, not MMA issue.
+#include "common.cuh"
+#include "sm100.cuh"
+#include <mutex>
+
+namespace tfswa {
+
+using namespace sm100;
+
+// ------------------------------------------------------------------------------------------------
+// host: driver entry point + tensor-map helper
+// ------------------------------------------------------------------------------------------------
+PFN_encodeTiled get_encode_tiled() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (PFN_encodeTiled)p;
+  });
+  return fn;
+}
+
+int make_tmap_bf16_3d(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows, uint64_t batch, uint64_t row_stride_elems,
+                      uint64_t batch_stride_elems, uint32_t box_cols, uint32_t box_rows) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return TFSWA_ECUDA; }
+  cuuint64_t dims[3] = {cols, rows, batch};
+  uint64_t bstride = batch > 1 ? batch_stride_elems : row_stride_elems * rows;
+  cuuint64_t strides[2] = {row_stride_elems * 2, bstride * 2};
+  cuuint32_t box[3] = {box_cols, box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  const uint32_t span = box_cols * 2;
+  CUtensorMapSwizzle sw = span == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (span == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  if (((uintptr_t)base & 15) || (strides[0] & 15) || (strides[1] & 15)) {
+    set_error("tensor map: base/strides must be 16-byte aligned"); return TFSWA_EINVAL;
+  }
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (CUresult %d)", (int)r); return TFSWA_ECUDA; }
+  return TFSWA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+struct TcLinearParams {
+  const float* bias; int64_t bias_bs;
+  const float* row_stats; int64_t rs_bs;
+  const float* wsum; int64_t wsum_bs;
+  const bf16* r1; int64_t ldr1, r1_bs;
+  const bf16* r2; int64_t ldr2, r2_bs;
+  bf16* y; int64_t ldy, y_bs;
+  int64_t M; int N, K;
+  int BN, BK, KB, stages;
+  int epilogue, ln;
+  uint32_t tmem_cols;
+};
+
+constexpr int TC_BM = 128;
+constexpr int TC_THREADS = 192;     // warp 0: TMA + TMEM alloc, warp 1: MMA issue, warps 2-5: epilogue
+constexpr int TC_MAX_STAGES = 4;
+
+__global__ void __launch_bounds__(TC_THREADS) tc_linear_kernel(const __grid_constant__ CUtensorMap tmx,
+                                                               const __grid_constant__ CUtensorMap tmw,
+                                                               const TcLinearParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_full[TC_MAX_STAGES], bar_empty[TC_MAX_STAGES], bar_acc;
+  __shared__ uint32_t s_tmem;
+  __shared__ float s_bias[256], s_wsum[256];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t m0 = (int64_t)blockIdx.x * TC_BM;
+  const int n0 = blockIdx.y * p.BN;
+  const int z = blockIdx.z;
+  const uint32_t a_bytes = TC_BM * p.BK * 2, b_bytes = p.BN * p.BK * 2;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;     // shared-space address, 1024-aligned
+  uint8_t* tiles = smem_raw + (base - smem_u32(smem_raw));
+
+  if (warp == 0) {
+    if (lane == 0) {
+      prefetch_tmap(&tmx);
+      prefetch_tmap(&tmw);
+      for (int s = 0; s < p.stages; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
+      mbar_init(&bar_acc, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(&s_tmem, p.tmem_cols);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = s_tmem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------- TMA producer ----------------
+      for (int kb = 0; kb < p.KB; ++kb) {
+        const int s = kb % p.stages;
+        if (kb >= p.stages) mbar_wait(&bar_empty[s], ((kb / p.stages) - 1) & 1);
+        mbar_arrive_expect_tx(&bar_full[s], a_bytes + b_bytes);
+        uint8_t* sa = tiles + (size_t)s * (a_bytes + b_bytes);
+        tma_load_3d(sa, &tmx, &bar_full[s], kb * p.BK, (int)m0, z);
+        tma_load_3d(sa + a_bytes, &tmw, &bar_full[s], kb * p.BK, n0, z);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ---------------- MMA issuer ----------------
+      const uint32_t idesc = umma_idesc_bf16(TC_BM, p.BN);
+      const uint32_t row_bytes = p.BK * 2;
+      for (int kb = 0; kb < p.KB; ++kb) {
+        const int s = kb % p.stages;
+        mbar_wait(&bar_full[s], (kb / p.stages) & 1);
+        tc_fence_after();
+        const uint32_t sa = base + s * (a_bytes + b_bytes);
+        const uint64_t adesc = umma_smem_desc(sa, row_bytes);
+        const uint64_t bdesc = umma_smem_desc(sa + a_bytes, row_bytes);
+        for (int k = 0; k < p.BK / 16; ++k) {
+          // advance 16 elements (32 B) along K inside the swizzle atom: +2 in the (addr >> 4) field
+          umma_bf16_ss(tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+        }
+        umma_commit(&bar_empty[s]);          // frees this smem stage when the MMAs above have read it
+      }
+      umma_commit(&bar_acc);                 // accumulator complete
+    }
+  } else {
+    // ---------------- epilogue: TMEM -> registers -> bias / LN algebra / GELU / residuals -> global ----------------
+    const int et = threadIdx.x - 64;         // 0..127
+    for (int i = et; i < p.BN; i += 128) {
+      s_bias[i] = p.bias ? p.bias[(int64_t)z * p.bias_bs + n0 + i] : 0.f;
+      s_wsum[i] = p.ln ? p.wsum[(int64_t)z * p.wsum_bs + n0 + i] : 0.f;
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    const int quad = warp & 3;               // TMEM lane quadrant this warp may access
+    const int64_t m = m0 + quad * 32 + lane;
+    const bool row_ok = m < p.M;
+    float mean = 0.f, rstd = 1.f;
+    if (p.ln && row_ok) {
+      const float2 st = *reinterpret_cast<const float2*>(p.row_stats + (int64_t)z * p.rs_bs + m * 2);
+      mean = st.x; rstd = st.y;
+    }
+    bf16* yrow = p.y + (int64_t)z * p.y_bs + m * p.ldy + n0;
+    const bf16* r1row = p.r1 ? p.r1 + (int64_t)z * p.r1_bs + m * p.ldr1 + n0 : nullptr;
+    const bf16* r2row = p.r2 ? p.r2 + (int64_t)z * p.r2_bs + m * p.ldr2 + n0 : nullptr;
+
+    mbar_wait(&bar_acc, 0);
+    tc_fence_after();
+    for (int c = 0; c < p.BN; c += 16) {
+      uint32_t raw[16];
+      __syncwarp();                                      // tcgen05.ld is .sync.aligned: keep the warp converged
+      tmem_ld_x16(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)c, raw);
+      tmem_ld_wait();
+      if (row_ok) {
+      float v[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        float a = __uint_as_float(raw[j]);
+        if (p.ln) a = rstd * (a - mean * s_wsum[c + j]);
+        a += s_bias[c + j];
+        if (p.epilogue == TFSWA_EPI_GELU) a = gelu_erf(a);
+        v[j] = a;
+      }
+      if (r1row) {
+        float t[8];
+        load8(r1row + c, t);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] += t[j];
+        load8(r1row + c + 8, t);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[8 + j] += t[j];
+      }
+      if (r2row) {
+        float t[8];
+        load8(r2row + c, t);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] += t[j];
+        load8(r2row + c + 8, t);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[8 + j] += t[j];
+      }
+      float lo[8], hi[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { lo[j] = v[j]; hi[j] = v[8 + j]; }
+      store8(yrow + c, lo);
+      store8(yrow + c + 8, hi);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, p.tmem_cols);
+}
+
+static int pick_bn(int N) {
+  for (int bn = 256; bn >= 16; bn -= 16)
+    if (N % bn == 0) return bn;
+  return 0;
+}
+
+}  // namespace tfswa
+
+using namespace tfswa;
+
+extern "C" int tfswa_linear_tc_fwd(const tfswa_linear_args* a, const void* w_bf16, const float* wsum, void* stream) {
+  TFSWA_REQUIRE(a && a->x && w_bf16 && a->y, "linear_tc: null pointer");
+  TFSWA_REQUIRE(a->dtype == TFSWA_BF16, "linear_tc: bf16 activations only");
+  TFSWA_REQUIRE(a->M > 0 && a->batch > 0 && a->batch <= 65535, "linear_tc: empty problem");
+  TFSWA_REQUIRE(a->K % 32 == 0 && a->K >= 32 && a->N % 16 == 0, "linear_tc: need K%%32==0 and N%%16==0 (K=%d N=%d)", a->K, a->N);
+  TFSWA_REQUIRE(a->prologue == TFSWA_PRO_NONE || a->prologue == TFSWA_PRO_LNHAT, "linear_tc: prologue %d unsupported", a->prologue);
+  TFSWA_REQUIRE(a->prologue != TFSWA_PRO_LNHAT || (a->row_stats && wsum), "linear_tc: LN needs row_stats and wsum");
+  TFSWA_REQUIRE(!a->pre && !a->col_stats, "linear_tc: pre/col_stats outputs are not produced by this kernel");
+  TFSWA_REQUIRE(a->ldy % 8 == 0 && a->y_bs % 8 == 0 && a->ldx % 8 == 0 && a->x_bs % 8 == 0, "linear_tc: 16-byte alignment of ld/strides");
+  TFSWA_REQUIRE((!a->r1 || (a->ldr1 % 8 == 0 && a->r1_bs % 8 == 0)) && (!a->r2 || (a->ldr2 % 8 == 0 && a->r2_bs % 8 == 0)),
+                "linear_tc: residual alignment");
+  TcLinearParams p = {};
+  p.BN = pick_bn(a->N);
+  TFSWA_REQUIRE(p.BN >= 16, "linear_tc: no N tile for N=%d", a->N);
+  p.BK = (a->K % 64 == 0) ? 64 : 32;
+  p.KB = a->K / p.BK;
+  const int stage_bytes = (TC_BM + p.BN) * p.BK * 2;
+  p.stages = p.KB < TC_MAX_STAGES ? p.KB : TC_MAX_STAGES;
+  while (p.stages > 1 && p.stages * stage_bytes > 96 * 1024) --p.stages;
+  p.tmem_cols = 32;
+  while ((int)p.tmem_cols < p.BN) p.tmem_cols <<= 1;
+  p.bias = a->bias; p.bias_bs = a->bias_bs; p.row_stats = a->row_stats; p.rs_bs = a->rs_bs; p.wsum = wsum; p.wsum_bs = a->N;
+  p.r1 = (const bf16*)a->r1; p.ldr1 = a->ldr1; p.r1_bs = a->r1_bs; p.r2 = (const bf16*)a->r2; p.ldr2 = a->ldr2; p.r2_bs = a->r2_bs;
+  p.y = (bf16*)a->y; p.ldy = a->ldy; p.y_bs = a->y_bs;
+  p.M = a->M; p.N = a->N; p.K = a->K; p.epilogue = a->epilogue; p.ln = a->prologue == TFSWA_PRO_LNHAT;
+  CUtensorMap tmx, tmw;
+  int rc = make_tmap_bf16_3d(&tmx, a->x, a->K, a->M, a->batch, a->ldx, a->x_bs, p.BK, TC_BM);
+  if (rc) return rc;
+  rc = make_tmap_bf16_3d(&tmw, w_bf16, a->K, a->N, a->batch, a->K, (uint64_t)a->N * a->K, p.BK, p.BN);
+  if (rc) return rc;
+  const size_t smem = (size_t)p.stages * stage_bytes + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(tc_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) { set_error("linear_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return TFSWA_ECUDA; }
+    attr_set = true;
+  }
+  dim3 grid((unsigned)ceil_div64(a->M, TC_BM), a->N / p.BN, a->batch);
+  tc_linear_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(tmx, tmw, p);
+  return check_launch("linear_tc");
+}

@@ -106,21 +106,33 @@ def prep_block(blk: nn.Module, training: bool):
     if not training:
         wi, bi = _bn_fold(wi, bi, blk.input_proj[1])
         wf, bf = _bn_fold(wf, bf, blk.fusion[1])
-    c = lambda t: t.float().contiguous()
+    st = lambda k: torch.stack([b[k] for b in brs])
     return {
-        "wi": c(wi)[None], "bi": c(bi)[None],
-        "w9": c(torch.cat([b["wqkv"] for b in brs], 0))[None], "b9": c(torch.cat([b["bqkv"] for b in brs], 0))[None],
-        "wp": c(torch.stack([b["wp"] for b in brs])), "bp": c(torch.stack([b["bp"] for b in brs])),
-        "w1": c(torch.stack([b["w1"] for b in brs])), "b1": c(torch.stack([b["b1"] for b in brs])),
-        "w2": c(torch.stack([b["w2"] for b in brs])), "b2": c(torch.stack([b["b2"] for b in brs])),
-        "wf": c(wf)[None], "bf": c(bf)[None],
+        "in": Fn.LinW(wi[None], bi[None]),
+        "qkv": Fn.LinW(torch.cat([b["wqkv"] for b in brs], 0)[None], torch.cat([b["bqkv"] for b in brs], 0)[None]),
+        "proj": Fn.LinW(st("wp"), st("bp")),
+        "fc1": Fn.LinW(st("w1"), st("b1")),
+        "fc2": Fn.LinW(st("w2"), st("b2")),
+        "fuse": Fn.LinW(wf[None], bf[None]),
     }
 
 
 def prep_single_branch(br: nn.Module):
     p = prep_branch(br)
-    c = lambda t: t.float().contiguous()
-    return {k: c(v)[None] for k, v in p.items()}
+    return {"qkv": Fn.LinW(p["wqkv"][None], p["bqkv"][None]), "proj": Fn.LinW(p["wp"][None], p["bp"][None]),
+            "fc1": Fn.LinW(p["w1"][None], p["b1"][None]), "fc2": Fn.LinW(p["w2"][None], p["b2"][None])}
+
+
+def _mlp(y: Tensor, fc1, fc2) -> Tensor:
+    """y + fc2(GELU(fc1(LN_hat(y))))  (attention.py:121-128,159).  Without autograd the GELU runs in fc1's epilogue
+    (hidden stored post-activation); with autograd the pre-activation is what is stored, and fc2 applies GELU on load."""
+    st2 = Fn.row_stats(y)
+    grad = torch.is_grad_enabled() and (y.requires_grad or fc1.w.requires_grad)
+    if grad:
+        u = Fn.linear(y, fc1, prologue=L.PRO_LNHAT, row_stats=st2)
+        return Fn.linear(u, fc2, prologue=L.PRO_GELU, r1=y)
+    h = Fn.linear(y, fc1, prologue=L.PRO_LNHAT, epilogue=L.EPI_GELU, row_stats=st2)
+    return Fn.linear(h, fc2, r1=y)
 
 
 def _bn_train(count: int, stats: Tensor, bn: nn.BatchNorm2d):
@@ -138,13 +150,11 @@ def branch_forward(x: Tensor, p: dict, geom: int, heads: int, ws: int = 8, shift
     M = B * H * W
     xt = tokens(x)[:, None, :]                                              # (M,1,C)
     st1 = Fn.row_stats(xt)
-    qkv = Fn.linear(xt, p["wqkv"], p["bqkv"], prologue=L.PRO_LNHAT, row_stats=st1)      # (M,1,3C)
+    qkv = Fn.linear(xt, p["qkv"], prologue=L.PRO_LNHAT, row_stats=st1)                  # (M,1,3C)
     att = Fn.attention(qkv[:, 0, :], B, H, W, C, heads, geom, ws=ws, shift=shift,
-                       pad_kv=p["bqkv"][0, C:], rel_bias=rel_bias, use_shift_mask=use_shift_mask)   # (M,C)
-    y = Fn.linear(att[:, None, :], p["wp"], p["bp"], r1=xt)
-    st2 = Fn.row_stats(y)
-    u = Fn.linear(y, p["w1"], p["b1"], prologue=L.PRO_LNHAT, row_stats=st2)             # fc1 pre-activation
-    z = Fn.linear(u, p["w2"], p["b2"], prologue=L.PRO_GELU, r1=y)
+                       pad_kv=p["qkv"].b[0, C:], rel_bias=rel_bias, use_shift_mask=use_shift_mask)   # (M,C)
+    y = Fn.linear(att[:, None, :], p["proj"], r1=xt)
+    z = _mlp(y, p["fc1"], p["fc2"])
     return untokens(z[:, 0, :], B, H, W)
 
 
@@ -158,32 +168,30 @@ def block_forward(blk: nn.Module, x: Tensor, skip: Optional[Tensor], p: dict) ->
     xt = tokens(x)[:, None, :]
     # input_proj: 1x1 conv + BN (no activation)                                   blocks.py:53-56,115
     if training:
-        pre, stats = Fn.linear(xt, p["wi"], p["bi"], want_col_stats=True)
+        pre, stats = Fn.linear(xt, p["in"], want_col_stats=True)
         sc, sh = _bn_train(M, stats, blk.input_proj[1])
         x1 = Fn.affine_act(pre, sc, sh)
     else:
-        x1 = Fn.linear(xt, p["wi"], p["bi"])
+        x1 = Fn.linear(xt, p["in"])
     # LN statistics once, q|k|v of all three branches in one GEMM
     st1 = Fn.row_stats(x1)
-    qkv = Fn.linear(x1, p["w9"], p["b9"], prologue=L.PRO_LNHAT, row_stats=st1)          # (M,1,9C)
+    qkv = Fn.linear(x1, p["qkv"], prologue=L.PRO_LNHAT, row_stats=st1)                  # (M,1,9C)
     qkv3 = qkv.view(M, 3, 3 * C)
-    b9 = p["b9"].view(3, 3 * C)
+    b9 = p["qkv"].b.view(3, 3 * C)
     att = Fn.attention3(qkv3, B, H, W, C, blk.num_heads, ws=blk.window_size, shift=blk.shift_size,
                         pad_kv=b9[2, C:], use_shift_mask=getattr(blk.swa, "use_shift_mask", False),
                         rel_bias=getattr(blk.swa, "rel_bias", None))                      # (M,3,C)
-    y = Fn.linear(att, p["wp"], p["bp"], r1=x1)                                          # + residual  (M,3,C)
-    st2 = Fn.row_stats(y)
-    u = Fn.linear(y, p["w1"], p["b1"], prologue=L.PRO_LNHAT, row_stats=st2)             # (M,3,4C) pre-GELU
-    z = Fn.linear(u, p["w2"], p["b2"], prologue=L.PRO_GELU, r1=y)                        # (M,3,C) == cat along C
+    y = Fn.linear(att, p["proj"], r1=x1)                                                 # + residual  (M,3,C)
+    z = _mlp(y, p["fc1"], p["fc2"])                                                      # (M,3,C) == cat along C
     zc = z.view(M, 1, 3 * C)
     skt = None if skip is None else tokens(skip)[:, None, :]
     # fusion: 1x1 conv (3C->C) + BN + GELU, + identity (+ skip)                    blocks.py:85-89,123-146
     if training:
-        pre, stats = Fn.linear(zc, p["wf"], p["bf"], want_col_stats=True)
+        pre, stats = Fn.linear(zc, p["fuse"], want_col_stats=True)
         sc, sh = _bn_train(M, stats, blk.fusion[1])
         out = Fn.affine_act(pre, sc, sh, epilogue=L.EPI_GELU, r1=xt, r2=skt)
     else:
-        out = Fn.linear(zc, p["wf"], p["bf"], epilogue=L.EPI_GELU, r1=xt, r2=skt)
+        out = Fn.linear(zc, p["fuse"], epilogue=L.EPI_GELU, r1=xt, r2=skt)
     return untokens(out[:, 0, :], B, H, W)
 
 

@@ -34,12 +34,38 @@ def row_stats(x: Tensor) -> Tensor:
     return ops.row_stats(x.detach())
 
 
-def linear(x: Tensor, w: Tensor, bias: Optional[Tensor] = None, *, prologue: int = 0, epilogue: int = 0,
+class LinW:
+    """Prepared weights of one (batched) token linear: fp32 master copy (nb,N,K) + bias (nb,N), and on demand the
+    bf16 copy + per-output row sums the tcgen05 kernel consumes."""
+    __slots__ = ("w", "b", "_tc")
+
+    def __init__(self, w: Tensor, b: Optional[Tensor]):
+        self.w = w.float().contiguous()
+        self.b = None if b is None else b.float().contiguous()
+        self._tc = None
+
+    def tc(self):
+        if self._tc is None:
+            with torch.no_grad():
+                wb = self.w.detach().to(torch.bfloat16).contiguous()
+                self._tc = (wb, wb.float().sum(-1).contiguous())
+        return self._tc
+
+
+USE_TC = True   # tcgen05 path for bf16 activations (set False to force the SIMT engine, e.g. for A/B tests)
+
+
+def linear(x: Tensor, lw: LinW, *, prologue: int = 0, epilogue: int = 0,
            row_stats: Optional[Tensor] = None, r1: Optional[Tensor] = None, r2: Optional[Tensor] = None,
            want_col_stats: bool = False):
+    w, bias = lw.w, lw.b
     if _needs_grad(x, w, bias, r1, r2):
         from .autograd import LinearFn
         return LinearFn.apply(x, w, bias, row_stats, r1, r2, prologue, epilogue, want_col_stats)
+    if (USE_TC and x.dtype == torch.bfloat16 and not want_col_stats and prologue in (L.PRO_NONE, L.PRO_LNHAT)
+            and w.shape[2] % 32 == 0 and w.shape[1] % 16 == 0):
+        wb, wsum = lw.tc()
+        return ops.linear_tc(x, wb, wsum, bias, prologue=prologue, epilogue=epilogue, row_stats=row_stats, r1=r1, r2=r2)
     if want_col_stats:
         stats = torch.zeros((2, w.shape[1]), dtype=torch.float32, device=x.device)
         pre = ops.linear(x, w, bias, prologue=prologue, row_stats=row_stats, col_stats=stats)

@@ -132,6 +132,37 @@ def linear(x: Tensor, w: Tensor, bias: Optional[Tensor] = None, *, prologue: int
     return (y, pre) if save_pre else y
 
 
+def linear_tc(x: Tensor, w_bf16: Tensor, wsum: Optional[Tensor], bias: Optional[Tensor] = None, *, prologue: int = 0,
+              epilogue: int = 0, row_stats: Optional[Tensor] = None, r1: Optional[Tensor] = None,
+              r2: Optional[Tensor] = None) -> Tensor:
+    """tcgen05 version of :func:`linear` (bf16 activations, TMA-fed, TMEM accumulators; see tfswa_linear_tc_fwd)."""
+    _cuda(x, w_bf16)
+    M, nb, K = x.shape
+    nbw, N, Kw = w_bf16.shape
+    if nbw != nb or Kw != K or w_bf16.dtype != torch.bfloat16 or not w_bf16.is_contiguous() or x.dtype != torch.bfloat16:
+        raise ValueError(f"linear_tc: x {tuple(x.shape)}/{x.dtype} vs w {tuple(w_bf16.shape)}/{w_bf16.dtype}")
+    _f32c(bias), _f32c(row_stats), _f32c(wsum)
+    y = torch.empty((M, nb, N), dtype=x.dtype, device=x.device)
+    a = L.LinearArgs()
+    a.x = x.data_ptr(); a.ldx, a.x_bs = _tok3(x, "x")
+    a.w = None; a.w_bs = N * K
+    a.bias = _p(bias); a.bias_bs = N
+    a.row_stats = _p(row_stats); a.rs_bs = 2 * M
+    for name, r in (("r1", r1), ("r2", r2)):
+        if r is not None:
+            if r.dtype != x.dtype or r.shape[0] != M or r.shape[2] != N or r.shape[1] not in (1, nb):
+                raise ValueError(f"linear_tc: residual {name} {tuple(r.shape)}/{r.dtype} incompatible")
+            ld, bs = _tok3(r, name)
+            setattr(a, name, r.data_ptr()); setattr(a, "ld" + name, ld); setattr(a, name + "_bs", bs)
+    a.y = y.data_ptr(); a.ldy, a.y_bs = _tok3(y, "y")
+    a.M, a.N, a.K = M, N, K
+    a.prologue, a.epilogue, a.batch, a.dtype = prologue, epilogue, nb, L.BF16
+    _call("tfswa_linear_tc_fwd", C.byref(a), w_bf16.data_ptr(), _p(wsum), _stream(), tag=f"linear_tc[K={K},N={N},nb={nb}]",
+          work={"flops": 2 * M * N * K * nb, "bytes": 2 * M * nb * (K + N) + (2 * M * nb * N if r1 is not None else 0)
+                + (2 * M * nb * N if r2 is not None else 0)})
+    return y
+
+
 def row_stats(x: Tensor) -> Tensor:
     """(M, nb, K) -> (nb, M, 2) fp32 {mean, rstd} over K (LayerNorm statistics, eps 1e-5)."""
     _cuda(x)
