@@ -137,6 +137,50 @@ int tfswa_affine_act(const void* v, const float* scale, const float* shift, cons
 int tfswa_bilinear_fwd(const void* x, void* y, int32_t B, int32_t Hin, int32_t Win, int32_t Hout, int32_t Wout,
                        int32_t C, int32_t dtype, void* stream);
 
+
+/* =====================================================================================================
+ * Backward (autograd of the call sites above).  Gradients w.r.t. weights/biases/statistics are
+ * fp32 and ACCUMULATED with atomics into caller-zeroed buffers; activation gradients are written in the
+ * activation dtype.  The data gradient of a linear / conv is itself a forward call with transposed weights
+ * (tfswa_linear_fwd / tfswa_conv_fwd: the stride-2 conv's data gradient is kind 2 with Hout in {2Hin, 2Hin+1},
+ * the transposed conv's is kind 1, the 3x3 conv's is kind 0 with flipped taps), so only the pieces below are new.
+ * ===================================================================================================== */
+
+/* dW[b][n][k] += sum_m G[m,b,n] * pro(X)[m,b,k];  dbias[b][n] += sum_m G[m,b,n].  `a` describes X exactly as in the
+ * forward call (x, ldx, x_bs, prologue, row_stats, in_scale/in_shift, M, N, K, batch, dtype); G = gradient of the
+ * pre-epilogue output, (M, ldg) with batch stride g_bs.  dbias may be NULL. */
+int tfswa_linear_wgrad(const tfswa_linear_args* a, const void* g, int64_t ldg, int64_t g_bs, float* dw, float* dbias, void* stream);
+/* same for the convolutions of tfswa_conv_fwd; dw has the layout of tfswa_conv_args.w; g = (B,Hout,Wout,Cout) */
+int tfswa_conv_wgrad(const tfswa_conv_args* a, const void* g, float* dw, float* dbias, void* stream);
+
+/* mode 0: out = g * gelu'(pre)   (gradient through a GELU epilogue)
+ * mode 1: out = g + ds[c] + 2*pre*ds[C+c]   (adds what reaches `pre` through the train-mode BN column sums) */
+int tfswa_act_bwd(const void* g, const void* pre, const float* ds, void* out, int64_t M, int32_t C, int32_t mode, int32_t dtype, void* stream);
+/* backward of tfswa_affine_act: dv, and (optional) dscale/dshift (C) accumulated */
+int tfswa_affine_act_bwd(const void* dy, const void* v, const float* scale, const float* shift, void* dv, float* dscale,
+                         float* dshift, int64_t M, int32_t C, int32_t epilogue, int32_t dtype, void* stream);
+/* LayerNorm input gradient for TFSWA_PRO_LNHAT: dx = rstd*(da - mean_k(da) - xhat*mean_k(da*xhat)) per row */
+int tfswa_lnhat_bwd(const void* da, int64_t ldd, int64_t d_bs, const void* x, int64_t ldx, int64_t x_bs, const float* stats,
+                    int64_t st_bs, void* dx, int64_t ldo, int64_t o_bs, int64_t M, int32_t K, int32_t batch, int32_t dtype, void* stream);
+/* out[m][:] = sum_b g[m][b][:]  (gradient of a residual broadcast over the branch dimension), dense (M,nb,N) */
+int tfswa_sum_batch(const void* g, void* out, int64_t M, int32_t nb, int32_t N, int32_t dtype, void* stream);
+int tfswa_bilinear_bwd(const void* dy, void* dx, int32_t B, int32_t Hin, int32_t Win, int32_t Hout, int32_t Wout, int32_t C,
+                       int32_t dtype, void* stream);
+
+/* attention backward: `a` as in the forward call with a->out = O and a->lse = the saved log2-domain logsumexp.
+ * dout: (M, ldo) gradient of O; dqkv: (M, ldq) receives dq|dk|dv; dsum: (M, heads) fp32 scratch (dO.O);
+ * dpad: (2C) fp32, accumulates the gradient of pad_kv (may be NULL when nothing is padded). */
+int tfswa_attn_bwd(const tfswa_attn_args* a, const void* dout, void* dqkv, float* dsum, float* dpad, void* stream);
+
+/* stem backward: g = gradient of the conv output (NHWC act); dw (Cout,Cin,7,7) and dbias accumulated;
+ * dx_nchw (optional) = gradient of the fp32 NCHW network input */
+int tfswa_stem_bwd(const float* x_nchw, const float* w, const void* g, float* dx_nchw, float* dw, float* dbias, int32_t B,
+                   int32_t Cin, int32_t H, int32_t W, int32_t Cout, int32_t dtype, void* stream);
+/* head tail backward: from dmasks (and/or dlogits), NCHW fp32 -> dv (act), dw3 (Cout,C), db3 (Cout), dscale/dshift (C) accumulated */
+int tfswa_head_tail_bwd(const void* v, const float* scale, const float* shift, const float* w3, const float* b3,
+                        const float* dmasks_nchw, const float* dlogits_nchw, void* dv, float* dw3, float* db3, float* dscale,
+                        float* dshift, int32_t B, int32_t H, int32_t W, int32_t C, int32_t Cout, int32_t dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

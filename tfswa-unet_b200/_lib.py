@@ -62,6 +62,17 @@ SIGNATURES = {
     "tfswa_bn_finalize": (C.c_int, [_p, _i64, _p, _p, _p, _p, _f, _f, _p, _p, _p, _i32, _p]),
     "tfswa_affine_act": (C.c_int, [_p, _p, _p, _p, _p, _p, _i64, _i32, _i32, _i32, _p]),
     "tfswa_bilinear_fwd": (C.c_int, [_p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p]),
+    # backward
+    "tfswa_linear_wgrad": (C.c_int, [C.POINTER(LinearArgs), _p, _i64, _i64, _p, _p, _p]),
+    "tfswa_conv_wgrad": (C.c_int, [C.POINTER(ConvArgs), _p, _p, _p, _p]),
+    "tfswa_act_bwd": (C.c_int, [_p, _p, _p, _p, _i64, _i32, _i32, _i32, _p]),
+    "tfswa_affine_act_bwd": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _i64, _i32, _i32, _i32, _p]),
+    "tfswa_lnhat_bwd": (C.c_int, [_p, _i64, _i64, _p, _i64, _i64, _p, _i64, _p, _i64, _i64, _i64, _i32, _i32, _i32, _p]),
+    "tfswa_sum_batch": (C.c_int, [_p, _p, _i64, _i32, _i32, _i32, _p]),
+    "tfswa_bilinear_bwd": (C.c_int, [_p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p]),
+    "tfswa_attn_bwd": (C.c_int, [C.POINTER(AttnArgs), _p, _p, _p, _p, _p]),
+    "tfswa_stem_bwd": (C.c_int, [_p, _p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _p]),
+    "tfswa_head_tail_bwd": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _p]),
 }
 
 _lib = None

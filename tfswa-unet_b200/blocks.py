@@ -60,8 +60,8 @@ class _Resample(nn.Module):
         native = E.is_native(x, dt)
         xi = x if native else E.to_native(x, dt)
         seq = getattr(self, self._seq)
-        wl, b = E.cached_prep(self, "conv", lambda: E.prep_conv_bn(seq[0], seq[1], self._kind, self.training), self.training)
-        y = E.conv_bn_gelu(xi, seq[0], seq[1], self._kind, wl, b, self.training, out_hw, dt)
+        prep = E.cached_prep(self, "conv", lambda: E.prep_conv_bn(seq[0], seq[1], self._kind, self.training), self.training)
+        y = E.conv_bn_gelu(xi, seq[1], self._kind, prep, self.training, out_hw, dt)
         return y if native else E.from_native(y, x)
 
 

@@ -26,44 +26,66 @@ int check_launch(const char* what) {
 // ---------------------------------------------------------------------------------------------
 // row statistics: one warp per row, K <= 1024, 128-bit loads, shuffle reduction (HBM-bound)
 // ---------------------------------------------------------------------------------------------
-template <typename T>
+// LPR lanes cooperate on one row (LPR = K/8 rounded up to a power of two, <= 32), so a warp covers 32/LPR rows and
+// every lane issues 128-bit loads even at K = 32.
+template <typename T, int LPR>
 __global__ void row_stats_kernel(const T* __restrict__ x, int64_t ldx, int64_t x_bs, float* __restrict__ st,
                                  int64_t st_bs, int64_t M, int K) {
+  constexpr int RPW = 32 / LPR;                 // rows per warp
+  constexpr int VPL = LPR == 32 ? 4 : 1;        // 8-element vectors per lane (K <= 1024)
   const int warps = blockDim.x >> 5;
-  const int64_t row = (int64_t)blockIdx.x * warps + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
-  if (row >= M) return;
-  const T* p = x + (int64_t)blockIdx.y * x_bs + row * ldx;
-  // two-pass in registers: K/8 <= 128 vectors, each lane holds up to 4 vectors of 8
-  float v[4][8];
+  const int sub = lane / LPR, l = lane % LPR;
+  const int64_t row = ((int64_t)blockIdx.x * warps + (threadIdx.x >> 5)) * RPW + sub;
+  const bool ok = row < M;
+  const T* p = x + (int64_t)blockIdx.y * x_bs + (ok ? row : 0) * ldx;
+  float v[VPL][8];
   float s = 0.f;
   const int nvec = K >> 3;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int vi = lane + i * 32;
-    if (vi < nvec) {
+  for (int i = 0; i < VPL; ++i) {
+    const int vi = l + i * LPR;
+    if (ok && vi < nvec) {
       load8(p + vi * 8, v[i]);
 #pragma unroll
       for (int j = 0; j < 8; ++j) s += v[i][j];
     }
   }
-  s = warp_sum(s);
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   const float mean = s / (float)K;
   float q = 0.f;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int vi = lane + i * 32;
-    if (vi < nvec) {
+  for (int i = 0; i < VPL; ++i) {
+    const int vi = l + i * LPR;
+    if (ok && vi < nvec) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) { const float d = v[i][j] - mean; q += d * d; }
     }
   }
-  q = warp_sum(q);
-  if (lane == 0) {
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  if (ok && l == 0) {
     float* o = st + (int64_t)blockIdx.y * st_bs + row * 2;
-    o[0] = mean;
-    o[1] = rsqrtf(q / (float)K + 1e-5f);
+    *reinterpret_cast<float2*>(o) = make_float2(mean, rsqrtf(q / (float)K + 1e-5f));
   }
+}
+
+template <typename T>
+static void launch_row_stats(const T* x, int64_t ldx, int64_t x_bs, float* st, int64_t st_bs, int64_t M, int K, int batch,
+                             cudaStream_t s) {
+  const int warps = 8;
+  const int nvec = K / 8;
+#define TFSWA_RS(LPR)                                                                                   \
+  {                                                                                                     \
+    dim3 grid((unsigned)ceil_div64(M, (int64_t)warps * (32 / LPR)), batch);                             \
+    row_stats_kernel<T, LPR><<<grid, warps * 32, 0, s>>>(x, ldx, x_bs, st, st_bs, M, K);                \
+  }
+  if (nvec <= 4) TFSWA_RS(4)
+  else if (nvec <= 8) TFSWA_RS(8)
+  else if (nvec <= 16) TFSWA_RS(16)
+  else TFSWA_RS(32)
+#undef TFSWA_RS
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -182,12 +204,8 @@ int tfswa_row_stats(const void* x, int64_t ldx, int64_t x_bs, float* stats, int6
   TFSWA_REQUIRE(x && stats && M > 0 && batch > 0, "row_stats: null pointer or empty problem");
   TFSWA_REQUIRE(K % 8 == 0 && K >= 8 && K <= 1024, "row_stats: K=%d must be a multiple of 8 in [8,1024]", K);
   TFSWA_REQUIRE(ldx % 8 == 0 && x_bs % 8 == 0, "row_stats: ldx/x_bs must be multiples of 8 elements");
-  const int warps = 8;
-  dim3 grid((unsigned)ceil_div64(M, warps), batch);
-  if (dtype == TFSWA_F32)
-    row_stats_kernel<float><<<grid, warps * 32, 0, (cudaStream_t)stream>>>((const float*)x, ldx, x_bs, stats, st_bs, M, K);
-  else if (dtype == TFSWA_BF16)
-    row_stats_kernel<bf16><<<grid, warps * 32, 0, (cudaStream_t)stream>>>((const bf16*)x, ldx, x_bs, stats, st_bs, M, K);
+  if (dtype == TFSWA_F32) launch_row_stats<float>((const float*)x, ldx, x_bs, stats, st_bs, M, K, batch, (cudaStream_t)stream);
+  else if (dtype == TFSWA_BF16) launch_row_stats<bf16>((const bf16*)x, ldx, x_bs, stats, st_bs, M, K, batch, (cudaStream_t)stream);
   else TFSWA_REQUIRE(false, "row_stats: bad dtype %d", dtype);
   return check_launch("row_stats");
 }

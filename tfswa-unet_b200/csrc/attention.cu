@@ -12,61 +12,9 @@
 // All lanes of a warp have the same head, so every K/V shared-memory read is a broadcast.
 // The softmax runs in the exp2 domain (scale*log2e folded into q); at head_dim 4..8 this kernel is
 // bound by MUFU.EX2 + the online-softmax bookkeeping, not by the dot products.
-#include "common.cuh"
-#include <math_constants.h>
+#include "attn_common.cuh"
 
 namespace tfswa {
-
-constexpr int QT = 64;    // queries per CTA
-constexpr int KT = 128;   // keys per shared-memory tile
-
-__device__ __forceinline__ float fast_exp2(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-
-struct AttnParams {
-  const void* qkv; int64_t ldq;
-  void* out; int64_t ldo;
-  float* lse;
-  const float* pad_kv;
-  const float* rel_bias;
-  int B, H, W, C, heads;
-  int geom, ws, shift, use_shift_mask;
-  int Hp, Wp, nWh, nWw;
-  float qscale;   // head_dim^-0.5 * log2(e)
-};
-
-// token index of element n of the sequence/window `row`; valid=false for zero-padded window tokens
-template <bool WINDOW>
-__device__ __forceinline__ int64_t token_of(const AttnParams& p, int row, int n, bool& valid) {
-  valid = true;
-  if (!WINDOW) {
-    if (p.geom == TFSWA_GEOM_TSA) {
-      const int b = row / p.W, w = row - b * p.W;
-      return ((int64_t)b * p.H + n) * p.W + w;
-    }
-    return (int64_t)row * p.W + n;
-  }
-  const int per_img = p.nWh * p.nWw;
-  const int b = row / per_img;
-  const int r = row - b * per_img;
-  const int wh = r / p.nWw, ww = r - wh * p.nWw;
-  int hp = wh * p.ws + n / p.ws + p.shift;
-  int wp = ww * p.ws + n % p.ws + p.shift;
-  if (hp >= p.Hp) hp -= p.Hp;
-  if (wp >= p.Wp) wp -= p.Wp;
-  valid = (hp < p.H) && (wp < p.W);
-  return ((int64_t)b * p.H + hp) * p.W + wp;
-}
-
-// Swin region id of shifted-frame coordinate (ys, xs): 3x3 regions split at (size-ws) and (size-shift)
-__device__ __forceinline__ int swin_region(const AttnParams& p, int ys, int xs) {
-  const int rh = ys < p.Hp - p.ws ? 0 : (ys < p.Hp - p.shift ? 1 : 2);
-  const int rw = xs < p.Wp - p.ws ? 0 : (xs < p.Wp - p.shift ? 1 : 2);
-  return rh * 3 + rw;
-}
 
 template <typename T, int D, bool WINDOW, bool EXTRAS>
 __global__ void __launch_bounds__(QT * (32 / D)) attn_fwd_kernel(const AttnParams p) {

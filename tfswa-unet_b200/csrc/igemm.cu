@@ -25,6 +25,9 @@ struct IgemmParams {
   int64_t x_bs, w_bs, bias_bs, rs_bs, r1_bs, r2_bs, y_bs, pre_bs;
   // conv geometry
   int B, Hin, Win, Cin, Hout, Wout;
+  int Hq, Wq;      // KIND_UP: phase grid = ceil(Hout/2) x ceil(Wout/2)
+  // weight-gradient mode
+  const void* g; int64_t ldg; int64_t g_bs; float* dw; float* dbias; int64_t rows_per_cta; int msplit;
 };
 
 constexpr int TK = 16;
@@ -35,8 +38,8 @@ template <int KIND>
 __device__ __forceinline__ int64_t a_offset(const IgemmParams& p, int64_t m, int k, int phase) {
   if (KIND == KIND_LINEAR) return m * p.ldx + k;
   const int tap = k / p.Cin, ci = k - tap * p.Cin;
-  const int hw = (KIND == KIND_UP) ? p.Hin * p.Win : p.Hout * p.Wout;
-  const int wdim = (KIND == KIND_UP) ? p.Win : p.Wout;
+  const int hw = (KIND == KIND_UP) ? p.Hq * p.Wq : p.Hout * p.Wout;
+  const int wdim = (KIND == KIND_UP) ? p.Wq : p.Wout;
   const int b = (int)(m / hw);
   const int rem = (int)(m - (int64_t)b * hw);
   const int oy = rem / wdim, ox = rem - oy * wdim;
@@ -47,19 +50,22 @@ __device__ __forceinline__ int64_t a_offset(const IgemmParams& p, int64_t m, int
     const int py = phase >> 1, px = phase & 1, a = tap >> 1, bb = tap & 1;
     iy = py ? (a ? oy : oy + 1) : (a ? oy - 1 : oy);
     ix = px ? (bb ? ox : ox + 1) : (bb ? ox - 1 : ox);
+    if (2 * oy + py >= p.Hout || 2 * ox + px >= p.Wout) return -1;   // phase-grid cell outside the output
   }
   if (iy < 0 || iy >= p.Hin || ix < 0 || ix >= p.Win) return -1;
   return (((int64_t)b * p.Hin + iy) * p.Win + ix) * p.Cin + ci;
 }
 
+// element offset of output row m (-1: the phase-grid cell lies outside the output, nothing to store)
 template <int KIND>
 __device__ __forceinline__ int64_t out_row_offset(const IgemmParams& p, int64_t m, int phase, int64_t ld) {
   if (KIND != KIND_UP) return m * ld;
-  const int hw = p.Hin * p.Win;
+  const int hw = p.Hq * p.Wq;
   const int b = (int)(m / hw);
   const int rem = (int)(m - (int64_t)b * hw);
-  const int oy2 = rem / p.Win, ox2 = rem - oy2 * p.Win;
+  const int oy2 = rem / p.Wq, ox2 = rem - oy2 * p.Wq;
   const int oy = 2 * oy2 + (phase >> 1), ox = 2 * ox2 + (phase & 1);
+  if (oy >= p.Hout || ox >= p.Wout) return -1;
   return (((int64_t)b * p.Hout + oy) * p.Wout + ox) * ld;
 }
 
@@ -195,6 +201,8 @@ __global__ void __launch_bounds__(NTHREADS) igemm_kernel(const IgemmParams p) {
   for (int i = 0; i < 8; ++i) {
     const int64_t m = m0 + ty * 8 + i;
     if (m >= p.M || !n_ok) continue;
+    const int64_t yoff = out_row_offset<KIND>(p, m, phase, p.ldy);
+    if (yoff < 0) continue;
     float v[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -212,7 +220,7 @@ __global__ void __launch_bounds__(NTHREADS) igemm_kernel(const IgemmParams p) {
     if (r2) { float t[4]; load4(r2 + m * p.ldr2 + n, t);
 #pragma unroll
       for (int j = 0; j < 4; ++j) v[j] += t[j]; }
-    store4(y + out_row_offset<KIND>(p, m, phase, p.ldy) + n, v);
+    store4(y + yoff + n, v);
   }
   if (p.col_stats) {
     if (n_ok) {
@@ -239,6 +247,119 @@ static int launch_igemm(const IgemmParams& p, int zdim, cudaStream_t st) {
     igemm_kernel<T, KIND, TN><<<grid, NTHREADS, 0, st>>>(p);
   }
   return check_launch("igemm");
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// weight gradient:  dW[n][k] += sum_m G[m][n] * pro(A)[m][k]   (and dbias[n] += sum_m G[m][n])
+// The reduction runs over millions of tokens while the result is at most 256 x 1024: split M across CTAs
+// (msplit), accumulate a 64x64 tile per CTA in registers and finish with fp32 atomics.  The A gather and the
+// prologues are the forward's, so nn.Linear, 1x1 and k x k convolutions share this kernel.
+// ------------------------------------------------------------------------------------------------
+constexpr int WG_T = 64;      // tile edge (n and k)
+constexpr int WG_MC = 16;     // rows per shared-memory chunk
+
+template <typename T, int KIND>
+__global__ void __launch_bounds__(NTHREADS) wgrad_kernel(const IgemmParams p) {
+  __shared__ __align__(16) float Gs[WG_MC][WG_T + 4];
+  __shared__ __align__(16) float As[WG_MC][WG_T + 4];
+  const int tid = threadIdx.x;
+  const int k0 = blockIdx.x * WG_T, n0 = blockIdx.y * WG_T;
+  const int zb = blockIdx.z / p.msplit, split = blockIdx.z % p.msplit;   // zb: batch (linear) or phase (up-conv)
+  const int phase = (KIND == KIND_UP) ? zb : 0;
+  const T* x = (const T*)p.x + (KIND == KIND_LINEAR ? zb * p.x_bs : 0);
+  const T* g = (const T*)p.g + (KIND == KIND_LINEAR ? zb * p.g_bs : 0);
+  const float* rs = p.row_stats ? p.row_stats + (int64_t)zb * p.rs_bs : nullptr;
+  float* dw = p.dw + (int64_t)zb * p.w_bs;
+  const int64_t m_begin = (int64_t)split * p.rows_per_cta;
+  const int64_t m_end = m_begin + p.rows_per_cta < p.M ? m_begin + p.rows_per_cta : p.M;
+
+  const int tn = tid / 16, tk = tid % 16;          // 4 n x 4 k outputs per thread
+  const int lr = tid / 16, lc = (tid % 16) * 4;    // loader: row lr, columns lc..lc+3
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  float bsum[4] = {0.f, 0.f, 0.f, 0.f};
+
+  for (int64_t mc = m_begin; mc < m_end; mc += WG_MC) {
+    const int64_t m = mc + lr;
+    float gv[4] = {0.f, 0.f, 0.f, 0.f}, av[4] = {0.f, 0.f, 0.f, 0.f};
+    if (m < m_end) {
+      const int64_t goff = out_row_offset<KIND>(p, m, phase, p.ldg);
+      if (goff >= 0) {
+        if (n0 + lc < p.N) load4(g + goff + n0 + lc, gv);
+        const int k = k0 + lc;
+        if (k < p.K) {
+          const int64_t off = a_offset<KIND>(p, m, k, phase);
+          if (off >= 0) {
+            load4(x + off, av);
+            if (KIND == KIND_LINEAR && p.prologue != TFSWA_PRO_NONE) {
+              if (p.prologue & TFSWA_PRO_AFFINE) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) av[j] = av[j] * p.in_scale[k + j] + p.in_shift[k + j];
+              }
+              if (p.prologue & TFSWA_PRO_LNHAT) {
+                const float mean = rs[m * 2], rstd = rs[m * 2 + 1];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) av[j] = (av[j] - mean) * rstd;
+              }
+              if (p.prologue & TFSWA_PRO_GELU) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) av[j] = gelu_erf(av[j]);
+              }
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+    *reinterpret_cast<float4*>(&Gs[lr][lc]) = make_float4(gv[0], gv[1], gv[2], gv[3]);
+    *reinterpret_cast<float4*>(&As[lr][lc]) = make_float4(av[0], av[1], av[2], av[3]);
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < WG_MC; ++r) {
+      const float4 g4 = *reinterpret_cast<const float4*>(&Gs[r][tn * 4]);
+      const float4 a4 = *reinterpret_cast<const float4*>(&As[r][tk * 4]);
+      const float gg[4] = {g4.x, g4.y, g4.z, g4.w};
+      const float aa[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(gg[i], aa[j], acc[i][j]);
+        if (tk == 0) bsum[i] += gg[i];
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int n = n0 + tn * 4 + i;
+    if (n >= p.N) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = k0 + tk * 4 + j;
+      if (k < p.K) atomicAdd(dw + (int64_t)n * p.K + k, acc[i][j]);
+    }
+    if (p.dbias && tk == 0 && blockIdx.x == 0 && (KIND != KIND_UP || true))
+      atomicAdd(p.dbias + (int64_t)(KIND == KIND_LINEAR ? zb : 0) * p.bias_bs + n, bsum[i]);
+  }
+}
+
+template <typename T, int KIND>
+static int launch_wgrad(IgemmParams& p, int zdim, cudaStream_t st) {
+  const int kt = (p.K + WG_T - 1) / WG_T, nt = (p.N + WG_T - 1) / WG_T;
+  int64_t want = 148 * 16 / ((int64_t)kt * nt * zdim);
+  if (want < 1) want = 1;
+  int64_t max_split = (p.M + 255) / 256;
+  if (want > max_split) want = max_split;
+  if (want > 4096) want = 4096;
+  p.msplit = (int)want;
+  p.rows_per_cta = ((p.M + p.msplit - 1) / p.msplit + WG_MC - 1) / WG_MC * WG_MC;
+  p.msplit = (int)((p.M + p.rows_per_cta - 1) / p.rows_per_cta);
+  dim3 grid(kt, nt, zdim * p.msplit);
+  wgrad_kernel<T, KIND><<<grid, NTHREADS, 0, st>>>(p);
+  return check_launch("wgrad");
 }
 
 }  // namespace tfswa
@@ -289,9 +410,12 @@ int tfswa_conv_fwd(const tfswa_conv_args* a, void* stream) {
     TFSWA_REQUIRE(a->Hout == (a->Hin - 2) / 2 + 1 && a->Wout == (a->Win - 2) / 2 + 1, "down conv: bad output size");
     kind = KIND_DOWN; p.K = 16 * a->Cin; p.M = (int64_t)a->B * a->Hout * a->Wout;
   } else if (a->kind == 2) {
-    TFSWA_REQUIRE(a->Hout == 2 * a->Hin && a->Wout == 2 * a->Win, "up conv: output must be 2x input");
-    TFSWA_REQUIRE(!a->col_stats || true, "unused");
-    kind = KIND_UP; p.K = 4 * a->Cin; p.M = (int64_t)a->B * a->Hin * a->Win; zdim = 4;
+    // forward ConvTranspose2d gives exactly 2x; as the data-gradient of the stride-2 conv the output is the conv's
+    // (possibly odd) input size, 2*Hin or 2*Hin+1
+    TFSWA_REQUIRE(a->Hout >= 2 * a->Hin && a->Hout <= 2 * a->Hin + 1 && a->Wout >= 2 * a->Win && a->Wout <= 2 * a->Win + 1,
+                  "up conv: output must be 2x (or 2x+1) the input");
+    p.Hq = (a->Hout + 1) / 2; p.Wq = (a->Wout + 1) / 2;
+    kind = KIND_UP; p.K = 4 * a->Cin; p.M = (int64_t)a->B * p.Hq * p.Wq; zdim = 4;
     p.w_bs = (int64_t)a->Cout * 4 * a->Cin;
   } else TFSWA_REQUIRE(false, "conv: bad kind %d", a->kind);
   cudaStream_t st = (cudaStream_t)stream;
@@ -305,6 +429,50 @@ int tfswa_conv_fwd(const tfswa_conv_args* a, void* stream) {
   if (a->dtype == TFSWA_BF16) { TFSWA_DISPATCH(bf16) }
 #undef TFSWA_DISPATCH
   TFSWA_REQUIRE(false, "conv: bad dtype %d", a->dtype);
+}
+
+
+int tfswa_linear_wgrad(const tfswa_linear_args* a, const void* g, int64_t ldg, int64_t g_bs, float* dw, float* dbias, void* stream) {
+  TFSWA_REQUIRE(a && a->x && g && dw, "linear_wgrad: null pointer");
+  TFSWA_REQUIRE(a->M > 0 && a->N > 0 && a->K > 0 && a->batch > 0 && a->batch <= 16, "linear_wgrad: bad problem size");
+  TFSWA_REQUIRE(a->K % 4 == 0 && a->N % 4 == 0 && a->ldx % 4 == 0 && ldg % 4 == 0 && a->x_bs % 4 == 0 && g_bs % 4 == 0,
+                "linear_wgrad: alignment (multiples of 4 elements)");
+  TFSWA_REQUIRE(!(a->prologue & TFSWA_PRO_LNHAT) || a->row_stats, "linear_wgrad: PRO_LNHAT needs row_stats");
+  IgemmParams p = {};
+  p.x = a->x; p.ldx = a->ldx; p.x_bs = a->x_bs; p.row_stats = a->row_stats; p.rs_bs = a->rs_bs;
+  p.in_scale = a->in_scale; p.in_shift = a->in_shift; p.prologue = a->prologue;
+  p.g = g; p.ldg = ldg; p.g_bs = g_bs; p.dw = dw; p.dbias = dbias; p.bias_bs = a->N; p.w_bs = (int64_t)a->N * a->K;
+  p.M = a->M; p.N = a->N; p.K = a->K;
+  if (a->dtype == TFSWA_F32) return launch_wgrad<float, KIND_LINEAR>(p, a->batch, (cudaStream_t)stream);
+  if (a->dtype == TFSWA_BF16) return launch_wgrad<bf16, KIND_LINEAR>(p, a->batch, (cudaStream_t)stream);
+  TFSWA_REQUIRE(false, "linear_wgrad: bad dtype %d", a->dtype);
+}
+
+int tfswa_conv_wgrad(const tfswa_conv_args* a, const void* g, float* dw, float* dbias, void* stream) {
+  TFSWA_REQUIRE(a && a->x && g && dw, "conv_wgrad: null pointer");
+  TFSWA_REQUIRE(a->Cin % 16 == 0 && a->Cout % 4 == 0, "conv_wgrad: need Cin%%16==0, Cout%%4==0");
+  IgemmParams p = {};
+  p.x = a->x; p.g = g; p.ldg = a->Cout; p.dw = dw; p.dbias = dbias; p.N = a->Cout;
+  p.B = a->B; p.Hin = a->Hin; p.Win = a->Win; p.Cin = a->Cin; p.Hout = a->Hout; p.Wout = a->Wout;
+  int kind, zdim = 1;
+  if (a->kind == 0) { kind = KIND_CONV3; p.K = 9 * a->Cin; p.M = (int64_t)a->B * a->Hout * a->Wout; }
+  else if (a->kind == 1) { kind = KIND_DOWN; p.K = 16 * a->Cin; p.M = (int64_t)a->B * a->Hout * a->Wout; }
+  else if (a->kind == 2) {
+    p.Hq = (a->Hout + 1) / 2; p.Wq = (a->Wout + 1) / 2;
+    kind = KIND_UP; p.K = 4 * a->Cin; p.M = (int64_t)a->B * p.Hq * p.Wq; zdim = 4;
+    p.w_bs = (int64_t)a->Cout * 4 * a->Cin;
+  } else TFSWA_REQUIRE(false, "conv_wgrad: bad kind %d", a->kind);
+  cudaStream_t st = (cudaStream_t)stream;
+#define TFSWA_DISPATCH(T)                                                  \
+  switch (kind) {                                                          \
+    case KIND_CONV3: return launch_wgrad<T, KIND_CONV3>(p, zdim, st);      \
+    case KIND_DOWN: return launch_wgrad<T, KIND_DOWN>(p, zdim, st);        \
+    default: return launch_wgrad<T, KIND_UP>(p, zdim, st);                 \
+  }
+  if (a->dtype == TFSWA_F32) { TFSWA_DISPATCH(float) }
+  if (a->dtype == TFSWA_BF16) { TFSWA_DISPATCH(bf16) }
+#undef TFSWA_DISPATCH
+  TFSWA_REQUIRE(false, "conv_wgrad: bad dtype %d", a->dtype);
 }
 
 }  // extern "C"

@@ -199,34 +199,23 @@ def block_forward(blk: nn.Module, x: Tensor, skip: Optional[Tensor], p: dict) ->
 # stem / down / up / head   (tfswa_unet.py:58-62,139-145; blocks.py:156-160,171-175)
 # ----------------------------------------------------------------------------------------------
 def prep_conv_bn(conv: nn.Module, bn: nn.BatchNorm2d, kind: str, training: bool):
+    """-> (w_oihw Cout-first, wl kernel layout, bias); eval mode folds the BatchNorm into weight and bias."""
+    from .autograd import conv_layout
     w, b = conv.weight, conv.bias
-    if kind == "up":            # ConvTranspose2d weight (Cin, Cout, 4, 4) -> (Cout, Cin, 4, 4) view for folding
+    if kind == "up":            # ConvTranspose2d weight (Cin, Cout, 4, 4) -> Cout-first
         w = w.permute(1, 0, 2, 3)
     if not training:
         s = bn.weight * torch.rsqrt(bn.running_var + bn.eps)
         w = w * s[:, None, None, None]
         b = (b - bn.running_mean) * s + bn.bias
-    if kind == "stem":
-        wl = w                                                  # (Cout, Cin, 7, 7) as is
-    elif kind in ("conv3", "down"):
-        wl = w.permute(0, 2, 3, 1)                              # (Cout, kh, kw, Cin)
-    else:
-        # 4 output phases x 2x2 taps (see igemm.cu a_offset<KIND_UP>):
-        # phase parity 0 uses kernel rows (1, 3), parity 1 uses (0, 2); tap a=0 is the nearer input row
-        taps = ((1, 3), (0, 2))
-        ph = []
-        for py in (0, 1):
-            for px in (0, 1):
-                sel = w[:, :, list(taps[py]), :][:, :, :, list(taps[px])]        # (Cout, Cin, 2, 2)
-                ph.append(sel.permute(0, 2, 3, 1))                                # (Cout, 2, 2, Cin)
-        wl = torch.stack(ph)                                                       # (4, Cout, 2, 2, Cin)
-    return wl.float().contiguous(), b.float().contiguous()
+    w = w.float()
+    return w, conv_layout(w.detach(), kind), b.float().contiguous()
 
 
-def conv_bn_gelu(x: Tensor, conv: nn.Module, bn: nn.BatchNorm2d, kind: str, wl: Tensor, b: Tensor, training: bool,
-                 out_hw, dtype: torch.dtype) -> Tensor:
+def conv_bn_gelu(x: Tensor, bn: nn.BatchNorm2d, kind: str, prep, training: bool, out_hw, dtype: torch.dtype) -> Tensor:
+    w, wl, b = prep
     if training:
-        pre, stats = Fn.conv(x, wl, b, kind, out_hw, dtype, want_col_stats=True)
+        pre, stats = Fn.conv(x, w, wl, b, kind, out_hw, dtype, want_col_stats=True)
         sc, sh = _bn_train(pre.shape[0] * pre.shape[2] * pre.shape[3], stats, bn)
         return Fn.affine_act(pre, sc, sh, epilogue=L.EPI_GELU)
-    return Fn.conv(x, wl, b, kind, out_hw, dtype, epilogue=L.EPI_GELU)
+    return Fn.conv(x, w, wl, b, kind, out_hw, dtype, epilogue=L.EPI_GELU)

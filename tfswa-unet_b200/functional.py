@@ -110,9 +110,18 @@ def bn_finalize(stats: Tensor, count: int, bn: nn.BatchNorm2d):
     else:
         momentum = 0.0
     if _needs_grad(stats, bn.weight, bn.bias):
-        from .autograd import BNFinalizeFn
-        return BNFinalizeFn.apply(stats, bn.weight, bn.bias, bn.running_mean if track else None,
-                                  bn.running_var if track else None, count, momentum, bn.eps)
+        # per-channel bookkeeping on C-element vectors (host-side plumbing, differentiable): autograd carries the
+        # gradient back to gamma/beta and, through `stats`, to the conv output (tfswa_act_bwd mode 1)
+        mean = stats[0] / count
+        var = (stats[1] / count - mean * mean).clamp_min(0.0)
+        scale = bn.weight.float() * torch.rsqrt(var + bn.eps)
+        shift = bn.bias.float() - mean * scale
+        if track:
+            with torch.no_grad():
+                unbias = count / max(count - 1, 1)
+                bn.running_mean.mul_(1 - momentum).add_(momentum * mean.detach())
+                bn.running_var.mul_(1 - momentum).add_(momentum * unbias * var.detach())
+        return scale, shift
     sc, sh, _ = ops.bn_finalize(stats, count, bn.weight.detach().float().contiguous(), bn.bias.detach().float().contiguous(),
                                 bn.running_mean if track else None, bn.running_var if track else None, momentum, bn.eps)
     return sc, sh
@@ -126,11 +135,12 @@ def affine_act(v: Tensor, scale: Optional[Tensor], shift: Optional[Tensor], *, e
     return ops.affine_act(v, scale, shift, epilogue=epilogue, r1=r1, r2=r2)
 
 
-def conv(x: Tensor, wl: Tensor, b: Tensor, kind: str, out_hw, dtype: torch.dtype, *, epilogue: int = 0,
+def conv(x: Tensor, w_oihw: Tensor, wl: Tensor, b: Tensor, kind: str, out_hw, dtype: torch.dtype, *, epilogue: int = 0,
          want_col_stats: bool = False):
-    if _needs_grad(x, wl, b):
+    """w_oihw: Cout-first (Cout,Cin,kh,kw) weight (autograd path); wl: the same weight in the kernel's layout."""
+    if _needs_grad(x, w_oihw, b):
         from .autograd import ConvFn
-        return ConvFn.apply(x, wl, b, kind, tuple(out_hw), dtype, epilogue, want_col_stats)
+        return ConvFn.apply(x, w_oihw, b, kind, tuple(out_hw), dtype, epilogue, want_col_stats)
     stats = torch.zeros((2, b.shape[0]), dtype=torch.float32, device=x.device) if want_col_stats else None
     if kind == "stem":
         y = ops.stem(x, wl, b, dtype, epilogue=epilogue, col_stats=stats)

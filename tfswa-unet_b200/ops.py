@@ -288,3 +288,134 @@ def bilinear(x: Tensor, out_hw: Tuple[int, int]) -> Tensor:
     L.check(L.lib().tfswa_bilinear_fwd(x.data_ptr(), y.data_ptr(), B, Hin, Win, out_hw[0], out_hw[1], Cn, _dt(x), _stream()),
             "bilinear_fwd")
     return y
+
+
+# ================================================================================================
+# backward wrappers
+# ================================================================================================
+def _dense_tok(t: Tensor) -> Tensor:
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def linear_wgrad(x: Tensor, g: Tensor, *, prologue: int = 0, row_stats: Optional[Tensor] = None, want_bias: bool = True):
+    """dW (nb,N,K), dbias (nb,N) fp32 for y = pro(x) W^T + b given g = dL/d(pre-epilogue y)."""
+    _cuda(x, g)
+    M, nb, K = x.shape
+    N = g.shape[2]
+    dw = torch.zeros((nb, N, K), dtype=torch.float32, device=x.device)
+    db = torch.zeros((nb, N), dtype=torch.float32, device=x.device) if want_bias else None
+    a = L.LinearArgs()
+    a.x = x.data_ptr(); a.ldx, a.x_bs = _tok3(x, "x")
+    a.row_stats = _p(row_stats); a.rs_bs = 2 * M
+    a.M, a.N, a.K = M, N, K
+    a.prologue, a.batch, a.dtype = prologue, nb, _dt(x)
+    ldg, g_bs = _tok3(g, "g")
+    _call("tfswa_linear_wgrad", C.byref(a), g.data_ptr(), ldg, g_bs, dw.data_ptr(), _p(db), _stream(),
+          tag=f"wgrad[K={K},N={N},nb={nb}]", work={"flops": 2 * M * N * K * nb})
+    return dw, db
+
+
+def conv_wgrad(x: Tensor, g: Tensor, kind: int, wl_shape, want_bias: bool = True):
+    _cuda(x, g)
+    B, Cin, Hin, Win = x.shape
+    _, Cout, Hout, Wout = g.shape
+    dw = torch.zeros(tuple(wl_shape), dtype=torch.float32, device=x.device)
+    db = torch.zeros((Cout,), dtype=torch.float32, device=x.device) if want_bias else None
+    a = L.ConvArgs()
+    a.x = x.data_ptr()
+    a.B, a.Hin, a.Win, a.Cin, a.Hout, a.Wout, a.Cout = B, Hin, Win, Cin, Hout, Wout, Cout
+    a.kind, a.dtype = kind, _dt(x)
+    _call("tfswa_conv_wgrad", C.byref(a), g.data_ptr(), dw.data_ptr(), _p(db), _stream())
+    return dw, db
+
+
+def act_bwd(g: Tensor, pre: Tensor, mode: int = 0, ds: Optional[Tensor] = None) -> Tensor:
+    """mode 0: g*gelu'(pre); mode 1: g + ds[0][c] + 2*pre*ds[1][c]; dense tensors of identical shape/layout."""
+    _cuda(g, pre)
+    if g.shape != pre.shape or g.dtype != pre.dtype:
+        raise ValueError("act_bwd: g/pre mismatch")
+    Cn = g.shape[1] if g.dim() == 4 else g.shape[-1]
+    out = torch.empty_like(pre)
+    _call("tfswa_act_bwd", g.data_ptr(), pre.data_ptr(), _p(_f32c(ds)), out.data_ptr(), g.numel() // Cn, Cn, mode, _dt(g), _stream())
+    return out
+
+
+def affine_act_bwd(dy: Tensor, v: Tensor, scale: Optional[Tensor], shift: Optional[Tensor], epilogue: int, want_params: bool):
+    _cuda(dy, v)
+    Cn = v.shape[1] if v.dim() == 4 else v.shape[-1]
+    dv = torch.empty_like(v)
+    dsc = torch.zeros(Cn, dtype=torch.float32, device=v.device) if want_params else None
+    dsh = torch.zeros(Cn, dtype=torch.float32, device=v.device) if want_params else None
+    _call("tfswa_affine_act_bwd", dy.data_ptr(), v.data_ptr(), _p(scale), _p(shift), dv.data_ptr(), _p(dsc), _p(dsh),
+          v.numel() // Cn, Cn, epilogue, _dt(v), _stream())
+    return dv, dsc, dsh
+
+
+def lnhat_bwd(da: Tensor, x: Tensor, stats: Tensor) -> Tensor:
+    _cuda(da, x)
+    M, nb, K = x.shape
+    dx = torch.empty((M, nb, K), dtype=x.dtype, device=x.device)
+    ldd, dbs = _tok3(da, "da"); ldx, xbs = _tok3(x, "x"); ldo, obs = _tok3(dx, "dx")
+    _call("tfswa_lnhat_bwd", da.data_ptr(), ldd, dbs, x.data_ptr(), ldx, xbs, stats.data_ptr(), 2 * M, dx.data_ptr(), ldo, obs,
+          M, K, nb, _dt(x), _stream())
+    return dx
+
+
+def sum_batch(g: Tensor) -> Tensor:
+    """(M, nb, N) dense -> (M, 1, N)"""
+    _cuda(g)
+    g = _dense_tok(g)
+    M, nb, N = g.shape
+    out = torch.empty((M, 1, N), dtype=g.dtype, device=g.device)
+    _call("tfswa_sum_batch", g.data_ptr(), out.data_ptr(), M, nb, N, _dt(g), _stream())
+    return out
+
+
+def bilinear_bwd(dy: Tensor, in_hw: Tuple[int, int]) -> Tensor:
+    _cuda(dy)
+    B, Cn, Hout, Wout = dy.shape
+    dx = torch.empty((B, Cn, in_hw[0], in_hw[1]), dtype=dy.dtype, device=dy.device, memory_format=torch.channels_last)
+    _call("tfswa_bilinear_bwd", dy.data_ptr(), dx.data_ptr(), B, in_hw[0], in_hw[1], Hout, Wout, Cn, _dt(dy), _stream())
+    return dx
+
+
+def attention_bwd(qkv: Tensor, out: Tensor, lse: Tensor, dout: Tensor, dqkv: Tensor, dsum: Tensor, B: int, H: int, W: int,
+                  C_: int, heads: int, geom: int, *, ws: int = 8, shift: int = 0, pad_kv: Optional[Tensor] = None,
+                  dpad: Optional[Tensor] = None) -> None:
+    _cuda(qkv, out, dout, dqkv)
+    if out.stride(0) != dout.stride(0) or qkv.stride(0) != dqkv.stride(0):
+        raise ValueError("attention_bwd: (out, dout) and (qkv, dqkv) must share their row strides")
+    a = L.AttnArgs()
+    a.qkv, a.ldq, a.out, a.ldo = qkv.data_ptr(), qkv.stride(0), out.data_ptr(), out.stride(0)
+    a.lse, a.pad_kv = lse.data_ptr(), _p(pad_kv)
+    a.B, a.H, a.W, a.C, a.heads = B, H, W, C_, heads
+    a.geom, a.ws, a.shift, a.use_shift_mask, a.dtype = geom, ws, shift, 0, _dt(qkv)
+    _call("tfswa_attn_bwd", C.byref(a), dout.data_ptr(), dqkv.data_ptr(), dsum.data_ptr(), _p(dpad), _stream(),
+          tag=f"attn_bwd[{('tsa', 'fsa', 'swa')[geom]},d={C_ // heads}]")
+
+
+def stem_bwd(x_nchw: Tensor, w: Tensor, g: Tensor, want_dx: bool):
+    _cuda(x_nchw, g)
+    B, Cin, H, W = x_nchw.shape
+    Cout = w.shape[0]
+    dw = torch.zeros_like(w)
+    db = torch.zeros((Cout,), dtype=torch.float32, device=w.device)
+    dx = torch.empty_like(x_nchw) if want_dx else None
+    _call("tfswa_stem_bwd", x_nchw.data_ptr(), w.data_ptr(), g.data_ptr(), _p(dx), dw.data_ptr(), db.data_ptr(), B, Cin, H, W,
+          Cout, _dt(g), _stream())
+    return dx, dw, db
+
+
+def head_tail_bwd(v: Tensor, scale: Optional[Tensor], shift: Optional[Tensor], w3: Tensor, b3: Tensor,
+                  dmasks: Optional[Tensor], dlogits: Optional[Tensor]):
+    _cuda(v, w3)
+    B, C_, H, W = v.shape
+    Cout = w3.shape[0]
+    dv = torch.empty_like(v)
+    dw3 = torch.zeros_like(w3)
+    db3 = torch.zeros_like(b3)
+    dsc = torch.zeros(C_, dtype=torch.float32, device=v.device) if scale is not None else None
+    dsh = torch.zeros(C_, dtype=torch.float32, device=v.device) if scale is not None else None
+    _call("tfswa_head_tail_bwd", v.data_ptr(), _p(scale), _p(shift), w3.data_ptr(), b3.data_ptr(), _p(dmasks), _p(dlogits),
+          dv.data_ptr(), dw3.data_ptr(), db3.data_ptr(), _p(dsc), _p(dsh), B, H, W, C_, Cout, _dt(v), _stream())
+    return dv, dw3, db3, dsc, dsh

@@ -75,8 +75,8 @@ class TFSWAUNet(nn.Module):
         training = self.training
         xin = x.float().contiguous()
         # stem: NCHW fp32 -> native NHWC activations
-        wl, b = E.cached_prep(self.stem, "conv", lambda: E.prep_conv_bn(self.stem[0], self.stem[1], "stem", training), training)
-        h = E.conv_bn_gelu(xin, self.stem[0], self.stem[1], "stem", wl, b, training, tuple(x.shape[2:]), dt)
+        prep = E.cached_prep(self.stem, "conv", lambda: E.prep_conv_bn(self.stem[0], self.stem[1], "stem", training), training)
+        h = E.conv_bn_gelu(xin, self.stem[1], "stem", prep, training, tuple(x.shape[2:]), dt)
         skips = []
         for blocks, down in zip(self.encoder_stages, self.downsample_layers):
             for blk in blocks:
@@ -94,15 +94,15 @@ class TFSWAUNet(nn.Module):
                 h = blk(h, skip=skip) if i == 0 else blk(h)                      # tfswa_unet.py:221-224
         # head: conv3x3 (+BN folded in eval) -> GELU -> conv1x1 -> sigmoid, written as NCHW fp32
         conv0, bn, conv3 = self.output_head[0], self.output_head[1], self.output_head[3]
-        wl, b = E.cached_prep(self.output_head, "conv", lambda: E.prep_conv_bn(conv0, bn, "conv3", training), training)
+        w, wl, b = E.cached_prep(self.output_head, "conv", lambda: E.prep_conv_bn(conv0, bn, "conv3", training), training)
         w3 = conv3.weight.reshape(self.out_channels, -1).float().contiguous()
         b3 = conv3.bias.float().contiguous()
         if training:
-            pre, stats = Fn.conv(h, wl, b, "conv3", tuple(h.shape[2:]), dt, want_col_stats=True)
+            pre, stats = Fn.conv(h, w, wl, b, "conv3", tuple(h.shape[2:]), dt, want_col_stats=True)
             sc, sh = E._bn_train(pre.shape[0] * pre.shape[2] * pre.shape[3], stats, bn)
             out = Fn.head_tail(pre, w3, b3, sc, sh, want_logits=return_logits)
         else:
-            v = Fn.conv(h, wl, b, "conv3", tuple(h.shape[2:]), dt)
+            v = Fn.conv(h, w, wl, b, "conv3", tuple(h.shape[2:]), dt)
             out = Fn.head_tail(v, w3, b3, None, None, want_logits=return_logits)
         return out
 
