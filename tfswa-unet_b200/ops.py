@@ -20,6 +20,9 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+USE_TC_ATTENTION = True   # tcgen05 attention for axial geometries at head_dim 4/8 (bf16); False forces the SIMT kernel
+
+
 # ---- launch accounting: every C-ABI compute call is exactly one kernel launch -------------------
 LAUNCHES = 0
 _TIMING = None          # None, or {kernel tag: [(start_event, end_event, work_dict), ...]}
@@ -188,7 +191,10 @@ def attention(qkv: Tensor, out: Tensor, B: int, H: int, W: int, C_: int, heads: 
     a.lse, a.pad_kv, a.rel_bias = _p(lse), _p(pad_kv), _p(rel_bias)
     a.B, a.H, a.W, a.C, a.heads = B, H, W, C_, heads
     a.geom, a.ws, a.shift, a.use_shift_mask, a.dtype = geom, ws, shift, int(use_shift_mask), _dt(qkv)
-    _call("tfswa_attn_fwd", C.byref(a), _stream(), tag=f"attn[{('tsa', 'fsa', 'swa')[geom]},d={C_ // heads}]",
+    d = C_ // heads
+    tc = USE_TC_ATTENTION and qkv.dtype == torch.bfloat16 and geom != L.GEOM_SWA and d in (4, 8) and heads * d == C_
+    _call("tfswa_attn_tc_fwd" if tc else "tfswa_attn_fwd", C.byref(a), _stream(),
+          tag=f"{'attn_tc' if tc else 'attn'}[{('tsa', 'fsa', 'swa')[geom]},d={d}]",
           work=_attn_work(B, H, W, C_, geom, ws, qkv.element_size()))
     return out
 
