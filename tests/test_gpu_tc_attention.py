@@ -60,6 +60,49 @@ def test_tc_attention_matches_simt_and_reference(B, H, W, C, geom):
     assert float((lse_tc - lse_s).abs().max()) <= 3e-2, "log-sum-exp mismatch"
 
 
+@pytest.mark.parametrize("B,H,W,C,geom", [(1, 300, 2, 32, 0), (1, 2, 517, 32, 1), (1, 3, 200, 64, 1)])
+def test_tc_attention_exact_two_pass_path(B, H, W, C, geom):
+    """the in-kernel fallback (exact row maxima) selected explicitly must agree with the bounded fast path"""
+    from tfswa_unet_b200 import ops
+    M = B * H * W
+    qkv = seeded((M, 3 * C), 21, 1.5).cuda().to(torch.bfloat16)
+    a = torch.empty((M, C), dtype=torch.bfloat16, device="cuda")
+    b = torch.empty_like(a)
+    la = torch.empty((M, 8), dtype=torch.float32, device="cuda")
+    lb = torch.empty_like(la)
+    ops.attention(qkv, a, B, H, W, C, 8, geom, lse=la)
+    ops.attention(qkv, b, B, H, W, C, 8, geom, lse=lb, use_shift_mask=True)      # test hook: force the exact path
+    torch.cuda.synchronize()
+    ref = _ref(qkv, B, H, W, C, 8, geom)
+    scale = float(ref.abs().max())
+    assert float((b.float() - ref).abs().max()) <= 2e-2 * scale
+    assert float((a.float() - b.float()).abs().max()) <= 2e-2 * scale
+    assert float((la - lb).abs().max()) <= 3e-2
+
+
+def test_tc_attention_loose_bound_falls_back_to_exact():
+    """q = (a,a,0,0), k = +-(b,-b,0,0): every score is 0 but the per-channel bound is 2ab*scale*log2e >> 126,
+    so every exponential underflows on the fast path and the CTA must redo the rows with the exact maximum"""
+    from tfswa_unet_b200 import ops
+    B, H, W, C, heads = 1, 70, 1, 32, 8
+    M = B * H * W
+    qkv = torch.zeros((M, 3 * C), device="cuda")
+    for h in range(heads):
+        qkv[:, 4 * h] = 16.0
+        qkv[:, 4 * h + 1] = 16.0
+        sign = torch.where(torch.arange(M, device="cuda") % 2 == 0, 1.0, -1.0)
+        qkv[:, C + 4 * h] = 16.0 * sign
+        qkv[:, C + 4 * h + 1] = -16.0 * sign
+    qkv[:, 2 * C:] = seeded((M, C), 5).cuda()
+    qkv = qkv.to(torch.bfloat16)
+    out = torch.empty((M, C), dtype=torch.bfloat16, device="cuda")
+    ops.attention(qkv, out, B, H, W, C, heads, 0)
+    torch.cuda.synchronize()
+    ref = qkv[:, 2 * C:].float().mean(0, keepdim=True).expand(M, C)     # all scores equal -> uniform attention
+    assert torch.isfinite(out.float()).all()
+    assert float((out.float() - ref).abs().max()) <= 2e-2 * float(ref.abs().max()) + 1e-2
+
+
 def test_tc_attention_large_negative_scores_do_not_overflow():
     """all true scores << 0 while absent (zero) keys of the tail tile score 0: the tail clamp must keep P finite"""
     from tfswa_unet_b200 import ops

@@ -25,6 +25,7 @@ struct AttnParams {
   int geom, ws, shift, use_shift_mask;
   int Hp, Wp, nWh, nWw;
   float qscale;   // head_dim^-0.5 * log2(e)
+  int force_exact; // tc attention: skip the row-max bound and run the exact two-pass path (tests)
   // backward
   const void* dout; const void* o; void* dqkv; float* dsum; float* dpad; float scale;
 };

@@ -6,12 +6,18 @@
 //        k_j of head h' in K-slots [d*h', d*h'+d) and zeros elsewhere, so D[q, (h', j)] = q_h' . k_{j,h'} -
 //        one MMA (N = 4*KT) yields the scores of all 4 heads; TMEM holds S (fp32).
 //   P  : softmax threads (one query row each, two threads per row splitting the columns) read S with tcgen05.ld,
-//        p = ex2(s*c - m*c) with ex2.approx.ftz.bf16x2 (two exps per MUFU op, P is bf16 for the PV MMA anyway) and
-//        write P as the K-major A operand of the PV MMA.
+//        p = ex2(s*c - m*c) (MUFU.EX2; the packed bf16x2 form was measured to issue as two scalar MUFU ops on
+//        sm_100a, so fp32 ex2 + one pack is both cheaper and more accurate) and write bf16 P as the K-major A
+//        operand of the PV MMA.
 //   O  : per head, D[q, 0..15] += P_h (128 x KT) * V'_h (KT x 16) where V'_h = [v dims | 1 | 0...]: the ones column
 //        makes the tensor core accumulate the softmax denominator (from the same bf16-rounded P as the numerator).
-// Exact maximum, no online rescaling: pass 1 streams S tiles (256 columns) and keeps the row max per head, pass 2
-// recomputes S (128 columns per tile) and accumulates O in TMEM across ALL key tiles; O is read once at the end.
+// No online rescaling: the softmax shift m_i is fixed BEFORE the key loop, so O accumulates in TMEM across all key
+// tiles and is read once.  m_i is an upper bound of the row maximum, sum_d max(q_d kmax_d, q_d kmin_d) with the
+// per-channel extrema of k over the sequence (softmax is shift invariant; an upper bound only costs dynamic range,
+// of which bf16/fp32 exponents have ~2^126).  If a bound is ever so loose that a row's denominator underflows, the
+// CTA repeats the computation with the exact maxima (one extra streaming pass over S, double-buffered in TMEM) -
+// `force_exact` selects that path for testing.  Each thread pulls its 64 scores into registers first, so the S MMA
+// of tile t+1 and the PV MMA of tile t-1 run underneath the exponentials of tile t.
 // Key tails are masked by zeroing V' (incl. its ones column) - the exponentials of absent keys multiply zeros.
 // Operands are staged by the threads themselves (8-row x 16-byte core matrices, no swizzle) because the head
 // expansion / zero padding is not expressible as a TMA box.  Two CTAs per SM (96 KB smem, 256 TMEM columns each)
@@ -47,70 +53,89 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return y;
 }
 
-// Stage the expanded-K operand of `kt` keys starting at key k0 (threads [0, kt)).
-template <int D>
-__device__ __forceinline__ void build_k(const AttnParams& p, uint8_t* ks, int row, int k0, int kt, int N, int quad, int tid) {
-  constexpr int HPQ = 16 / D;
-  if (tid >= kt) return;
-  const int j = tid;
-  uint4 a = make_uint4(0, 0, 0, 0), b = make_uint4(0, 0, 0, 0);
-  if (k0 + j < N) {
-    bool valid; const int64_t tok = token_of<false>(p, row, k0 + j, valid);
-    const uint4* src = reinterpret_cast<const uint4*>((const bf16*)p.qkv + tok * p.ldq + p.C + quad * 16);
-    a = src[0]; b = src[1];
+// ---- operand staging, split into a global->register half and a register->shared half so the global latency of
+// tile t+1 overlaps the softmax of tile t.  Threads [0, KT) carry one key's k (32 B); threads [128, 256) carry one
+// (key, head) slice of v (2*D bytes). ----
+struct KvRegs { uint4 a, b; bool present; };
+
+template <int D, int KT>
+__device__ __forceinline__ KvRegs load_kv(const AttnParams& p, int row, int k0, int N, int quad, int tid) {
+  KvRegs r; r.a = make_uint4(0, 0, 0, 0); r.b = r.a; r.present = false;
+  if (tid < KT) {
+    if (k0 + tid < N) {
+      bool valid; const int64_t tok = token_of<false>(p, row, k0 + tid, valid);
+      const uint4* src = reinterpret_cast<const uint4*>((const bf16*)p.qkv + tok * p.ldq + p.C + quad * 16);
+      r.a = src[0]; r.b = src[1]; r.present = true;
+    }
+  } else if (tid >= 128) {
+    const int idx = tid - 128, j = idx % KT, h = idx / KT;
+    if (k0 + j < N) {
+      bool valid; const int64_t tok = token_of<false>(p, row, k0 + j, valid);
+      const bf16* src = (const bf16*)p.qkv + tok * p.ldq + 2 * p.C + quad * 16 + h * D;
+      if (D == 4) { const uint2 t = *reinterpret_cast<const uint2*>(src); r.a.x = t.x; r.a.y = t.y; }
+      else r.a = *reinterpret_cast<const uint4*>(src);
+      r.present = true;
+    }
   }
+  return r;
+}
+
+// expanded-K operand: row n = h*KT + j holds k_j of head h in K-slots [D*h, D*h+D), zeros elsewhere (zeros are permanent)
+template <int D, int KT>
+__device__ __forceinline__ void store_k(const KvRegs& kv, uint8_t* ks, int tid) {
+  constexpr int HPQ = 16 / D;
+  if (tid >= KT) return;
+  const int j = tid;
   if (D == 4) {
-    const uint2 parts[4] = {make_uint2(a.x, a.y), make_uint2(a.z, a.w), make_uint2(b.x, b.y), make_uint2(b.z, b.w)};
+    const uint2 parts[4] = {make_uint2(kv.a.x, kv.a.y), make_uint2(kv.a.z, kv.a.w), make_uint2(kv.b.x, kv.b.y), make_uint2(kv.b.z, kv.b.w)};
 #pragma unroll
     for (int h = 0; h < HPQ; ++h) {
-      const int n = h * kt + j;
+      const int n = h * KT + j;
       *reinterpret_cast<uint2*>(ks + (n >> 3) * 256 + (h >> 1) * 128 + (n & 7) * 16 + (h & 1) * 8) = parts[h];
     }
   } else {
 #pragma unroll
     for (int h = 0; h < HPQ; ++h) {
-      const int n = h * kt + j;
-      *reinterpret_cast<uint4*>(ks + (n >> 3) * 256 + h * 128 + (n & 7) * 16) = h ? b : a;
+      const int n = h * KT + j;
+      *reinterpret_cast<uint4*>(ks + (n >> 3) * 256 + h * 128 + (n & 7) * 16) = h ? kv.b : kv.a;
     }
   }
 }
 
-// Stage V'_h (16 x kt, K-major) for all heads of the quad (threads [kt, 2kt)); absent keys become all-zero columns.
-template <int D>
-__device__ __forceinline__ void build_v(const AttnParams& p, uint8_t* vs, int row, int k0, int kt, int N, int quad, int tid) {
-  constexpr int HPQ = 16 / D;
-  if (tid < kt || tid >= 2 * kt) return;
-  const int j = tid - kt;
-  const bool present = k0 + j < N;
-  uint4 raw[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
-  if (present) {
-    bool valid; const int64_t tok = token_of<false>(p, row, k0 + j, valid);
-    const uint4* src = reinterpret_cast<const uint4*>((const bf16*)p.qkv + tok * p.ldq + 2 * p.C + quad * 16);
-    raw[0] = src[0]; raw[1] = src[1];
-  }
-  const uint16_t* e = reinterpret_cast<const uint16_t*>(raw);
-  const int head_bytes = 16 * kt * 2, sbo = (kt / 8) * 128;
-  const int koff = (j >> 3) * 128 + (j & 7) * 2;
+// V'_h (16 x KT, K-major) per head: rows 0..D-1 = v dims, row D = 1 (denominator), rest 0; absent keys become
+// all-zero columns, which is how key tails are masked.  One thread per (key, head).
+template <int D, int KT>
+__device__ __forceinline__ void store_v(const KvRegs& kv, uint8_t* vs, int tid) {
+  if (tid < 128) return;
+  const int idx = tid - 128, j = idx % KT, h = idx / KT;
+  const uint16_t* e = reinterpret_cast<const uint16_t*>(&kv.a);
+  constexpr int head_bytes = 16 * KT * 2, sbo = (KT / 8) * 128;
+  uint8_t* base = vs + h * head_bytes + (j >> 3) * 128 + (j & 7) * 2;
 #pragma unroll
-  for (int h = 0; h < HPQ; ++h) {
-    uint8_t* base = vs + h * head_bytes;
-#pragma unroll
-    for (int d = 0; d < D; ++d) *reinterpret_cast<uint16_t*>(base + koff + d * 16) = e[h * D + d];
-    const uint16_t one = present ? (uint16_t)0x3F80 : (uint16_t)0;          // bf16 1.0: the denominator column
-    if (D == 4) *reinterpret_cast<uint16_t*>(base + koff + 4 * 16) = one;
-    else *reinterpret_cast<uint16_t*>(base + sbo + koff) = one;
-  }
+  for (int d = 0; d < D; ++d) *reinterpret_cast<uint16_t*>(base + d * 16) = e[d];
+  const uint16_t one = kv.present ? (uint16_t)0x3F80 : (uint16_t)0;       // bf16 1.0
+  if (D == 4) *reinterpret_cast<uint16_t*>(base + 4 * 16) = one;
+  else *reinterpret_cast<uint16_t*>(base + sbo) = one;
+}
+
+__device__ __forceinline__ float ex2_f32(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 
 template <int D>
 __global__ void __launch_bounds__(TA_THREADS, 2) tc_attn_axial_kernel(const AttnParams p) {
   constexpr int HPQ = 16 / D;            // heads per CTA
-  constexpr int KT2 = 128 / HPQ;         // keys per pass-2 tile (S tile = 128 columns)
-  constexpr int KT1 = 256 / HPQ;         // keys per pass-1 tile (S tile = 256 columns)
+  constexpr int KT = 128 / HPQ;          // keys per tile: one S tile = 128 TMEM columns = HPQ heads x KT keys
   constexpr int HPT = HPQ / 2;           // heads per thread
+  constexpr int P_SBO = (KT / 8) * 128;  // 8-row group stride of the P / V' operands
+  constexpr int P_HEAD = 128 * KT * 2;   // bytes of one head's P tile
+  constexpr int V_HEAD = 16 * KT * 2;
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ __align__(8) uint64_t bar_s, bar_pv[2];
+  __shared__ __align__(8) uint64_t bar_s[2], bar_pv[2];
   __shared__ uint32_t s_tmem;
+  __shared__ float s_kext[2][16];        // per channel of the quad: min / max of k over the whole sequence
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int row = blockIdx.x, q0 = blockIdx.y * TA_QT, quad = blockIdx.z;
@@ -118,164 +143,243 @@ __global__ void __launch_bounds__(TA_THREADS, 2) tc_attn_axial_kernel(const Attn
   const int quarter = warp & 3, half = warp >> 2;
   const int r = quarter * 32 + lane;                 // my query row == my TMEM lane
   const float c = p.qscale;                          // head_dim^-0.5 * log2(e)
+  const int T = (N + KT - 1) / KT;
 
   // ---- setup: zero the operand buffers (their zero patterns are permanent), barriers, TMEM ----
   for (int i = tid; i < (TA_PS - TA_KS) / 16; i += TA_THREADS) reinterpret_cast<uint4*>(smem + TA_KS)[i] = make_uint4(0, 0, 0, 0);
   if (warp == 0) {
-    if (lane == 0) { mbar_init(&bar_s, 1); mbar_init(&bar_pv[0], 1); mbar_init(&bar_pv[1], 1); fence_barrier_init(); }
+    if (lane == 0) {
+      mbar_init(&bar_s[0], 1); mbar_init(&bar_s[1], 1); mbar_init(&bar_pv[0], 1); mbar_init(&bar_pv[1], 1);
+      fence_barrier_init();
+    }
     __syncwarp();
     tmem_alloc(&s_tmem, TA_TMEM_COLS);
   }
-  // Q operand: row r, 16 channels = 2 chunks of 16 B
   bool q_valid = false;
   int64_t q_tok = 0;
-  if (tid < TA_QT) {
-    uint4 a = make_uint4(0, 0, 0, 0), b = a;
-    if (q0 + r < N) {
-      q_tok = token_of<false>(p, row, q0 + r, q_valid);
-      const uint4* src = reinterpret_cast<const uint4*>((const bf16*)p.qkv + q_tok * p.ldq + quad * 16);
-      a = src[0]; b = src[1];
-    }
-    *reinterpret_cast<uint4*>(smem + TA_QS + (r >> 3) * 256 + (r & 7) * 16) = a;
-    *reinterpret_cast<uint4*>(smem + TA_QS + (r >> 3) * 256 + 128 + (r & 7) * 16) = b;
-  } else if (q0 + r < N) {
-    q_tok = token_of<false>(p, row, q0 + r, q_valid);
+  if (q0 + r < N) q_tok = token_of<false>(p, row, q0 + r, q_valid);
+  uint4 qa = make_uint4(0, 0, 0, 0), qb = qa;        // my row's 16 q channels
+  if (q_valid) {
+    const uint4* src = reinterpret_cast<const uint4*>((const bf16*)p.qkv + q_tok * p.ldq + quad * 16);
+    qa = src[0]; qb = src[1];
   }
-  __syncthreads();                                   // zero fill done before any build_* writes
+  if (tid < TA_QT) {                                 // Q operand: row r, 16 channels = 2 chunks of 16 B
+    *reinterpret_cast<uint4*>(smem + TA_QS + (r >> 3) * 256 + (r & 7) * 16) = qa;
+    *reinterpret_cast<uint4*>(smem + TA_QS + (r >> 3) * 256 + 128 + (r & 7) * 16) = qb;
+  }
+  // ---- per-channel extrema of k over the sequence (for the row-max upper bound) ----
+  {
+    float kmn[16], kmx[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { kmn[i] = CUDART_INF_F; kmx[i] = -CUDART_INF_F; }
+    for (int j = tid; j < N; j += TA_THREADS) {
+      bool valid; const int64_t tok = token_of<false>(p, row, j, valid);
+      const uint4* src = reinterpret_cast<const uint4*>((const bf16*)p.qkv + tok * p.ldq + p.C + quad * 16);
+      uint4 raw[2] = {src[0], src[1]};
+      const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(raw);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float lo = __low2float(h2[i]), hi = __high2float(h2[i]);
+        kmn[2 * i] = fminf(kmn[2 * i], lo); kmx[2 * i] = fmaxf(kmx[2 * i], lo);
+        kmn[2 * i + 1] = fminf(kmn[2 * i + 1], hi); kmx[2 * i + 1] = fmaxf(kmx[2 * i + 1], hi);
+      }
+    }
+    float* red = reinterpret_cast<float*>(smem + TA_PS);          // [256][33] floats, P region is idle here
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { red[tid * 33 + i] = kmn[i]; red[tid * 33 + 16 + i] = kmx[i]; }
+    __syncthreads();                                              // also: zero fill done before any operand store
+    // warp w reduces columns 4w..4w+3 over the 256 rows
+#pragma unroll
+    for (int cidx = 0; cidx < 4; ++cidx) {
+      const int col = warp * 4 + cidx;
+      float v = red[lane * 33 + col];
+#pragma unroll
+      for (int k = 1; k < 8; ++k) {
+        const float o = red[(lane + 32 * k) * 33 + col];
+        v = col < 16 ? fminf(v, o) : fmaxf(v, o);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float w = __shfl_xor_sync(0xffffffffu, v, o);
+        v = col < 16 ? fminf(v, w) : fmaxf(v, w);
+      }
+      if (lane == 0) s_kext[col >> 4][col & 15] = v;
+    }
+  }
+  KvRegs kvn = load_kv<D, KT>(p, row, 0, N, quad, tid);
+  __syncthreads();
   const uint32_t sbase = smem_u32(smem);
   const uint64_t qdesc = umma_smem_desc_ns(sbase + TA_QS, 128, 256);
-  uint32_t ns = 0;                                   // number of S commits consumed so far (parity = ns & 1)
+  const uint32_t idesc_s = umma_idesc_bf16(128, 128);
+  uint32_t ns[2] = {0u, 0u}, npv[2] = {0u, 0u};      // barrier completions consumed (wait parity = count & 1)
 
-  // =========================== pass 1: exact row maxima ===========================
-  const int T1 = (N + KT1 - 1) / KT1;
-  build_k<D>(p, smem + TA_KS, row, 0, KT1, N, quad, tid);
-  fence_async_smem();
+  // row-max upper bound per head: s_ij = sum_d q_d k_jd <= sum_d max(q_d kmax_d, q_d kmin_d)   (raw score units)
+  float m[HPT];
+  {
+    uint4 raw[2] = {qa, qb};
+    const __nv_bfloat16* qe = reinterpret_cast<const __nv_bfloat16*>(raw);
+#pragma unroll
+    for (int hh = 0; hh < HPT; ++hh) {
+      const int head = half * HPT + hh;
+      float b = 0.f;
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        const float qv = __bfloat162float(qe[head * D + d]);
+        b += fmaxf(qv * s_kext[1][head * D + d], qv * s_kext[0][head * D + d]);
+      }
+      m[hh] = b;
+    }
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = s_tmem;
   const uint32_t my_taddr = tmem + ((uint32_t)(quarter * 32) << 16);
-  if (tid == 0) {
-    umma_bf16_ss(tmem, qdesc, umma_smem_desc_ns(sbase + TA_KS, 128, 256), umma_idesc_bf16(128, 256), 0u);
-    umma_commit(&bar_s);
-  }
-  float m[HPT];
-#pragma unroll
-  for (int i = 0; i < HPT; ++i) m[i] = -CUDART_INF_F;
-  for (int t = 0; t < T1; ++t) {
-    if (t + 1 < T1) build_k<D>(p, smem + TA_KS + ((t + 1) & 1) * 8192, row, (t + 1) * KT1, KT1, N, quad, tid);
-    mbar_wait(&bar_s, ns & 1); ++ns;
-    tc_fence_after();
-    const int kcount = min(KT1, N - t * KT1);
-#pragma unroll
-    for (int ch = 0; ch < 4; ++ch) {                 // my 128 of the 256 columns, 32 at a time
-      uint32_t s[32];
-      __syncwarp();
-      tmem_ld_x32(my_taddr + half * 128 + ch * 32, s);
-      tmem_ld_wait();
-      const int lc = ch * 32;                        // local column -> (head slot, key)
-      const int hi = lc / KT1, jbase = lc % KT1;
-      float mx = m[hi];
-      if (jbase + 32 <= kcount) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(s[i]));
-      } else {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) if (jbase + i < kcount) mx = fmaxf(mx, __uint_as_float(s[i]));
-      }
-      m[hi] = mx;
-    }
-    fence_async_smem();
-    tc_fence_before();
-    __syncthreads();
-    if (tid == 0 && t + 1 < T1) {
-      tc_fence_after();
-      umma_bf16_ss(tmem, qdesc, umma_smem_desc_ns(sbase + TA_KS + ((t + 1) & 1) * 8192, 128, 256), umma_idesc_bf16(128, 256), 0u);
-      umma_commit(&bar_s);
-    }
-  }
-  float mc[HPT];
-#pragma unroll
-  for (int i = 0; i < HPT; ++i) mc[i] = m[i] * c;
 
-  // =========================== pass 2: P = ex2(S*c - m*c), O += P V' ===========================
-  const int T2 = (N + KT2 - 1) / KT2;
-  constexpr int P_SBO = (KT2 / 8) * 128;             // 8-row group stride of the P / V' operands
-  constexpr int P_HEAD = 128 * KT2 * 2;              // bytes of one head's P tile
-  constexpr int V_HEAD = 16 * KT2 * 2;
-  // the row -> head mapping of the expanded-K operand changes with the tile size: clear pass 1's pattern
-  for (int i = tid; i < (2 * 8192) / 16; i += TA_THREADS) reinterpret_cast<uint4*>(smem + TA_KS)[i] = make_uint4(0, 0, 0, 0);
-  __syncthreads();
-  build_k<D>(p, smem + TA_KS, row, 0, KT2, N, quad, tid);
-  build_v<D>(p, smem + TA_VS, row, 0, KT2, N, quad, tid);
-  fence_async_smem();
-  tc_fence_before();
-  __syncthreads();
-  if (tid == 0) {
-    tc_fence_after();
-    umma_bf16_ss(tmem, qdesc, umma_smem_desc_ns(sbase + TA_KS, 128, 256), umma_idesc_bf16(128, 128), 0u);
-    umma_commit(&bar_s);
-  }
-  for (int t = 0; t < T2; ++t) {
-    const int pb = t & 1;
-    if (t >= 2) mbar_wait(&bar_pv[pb], ((t >> 1) - 1) & 1);        // PV(t-2) has finished reading Ps[pb], Vs[(t+1)%3]
-    if (t + 1 < T2) {
-      build_k<D>(p, smem + TA_KS + ((t + 1) & 1) * 8192, row, (t + 1) * KT2, KT2, N, quad, tid);
-      build_v<D>(p, smem + TA_VS + ((t + 1) % 3) * 4096, row, (t + 1) * KT2, KT2, N, quad, tid);
-    }
-    mbar_wait(&bar_s, ns & 1); ++ns;
-    tc_fence_after();
-    const bool tail = (t + 1) * KT2 > N;             // only the last tile holds absent keys
-    uint8_t* ps = smem + TA_PS + pb * 32768;
-#pragma unroll
-    for (int ch = 0; ch < 2; ++ch) {                 // my 64 of the 128 columns
-      uint32_t s[32];
-      __syncwarp();
-      tmem_ld_x32(my_taddr + half * 64 + ch * 32, s);
-      tmem_ld_wait();
-      const int col = half * 64 + ch * 32;
-      const int head = col / KT2, jbase = col % KT2; // head within the quad, first key of this chunk
-      const float mcc = mc[(ch * 32) / KT2];
-      uint32_t pk[16];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        float x0 = fmaf(__uint_as_float(s[2 * i]), c, -mcc);
-        float x1 = fmaf(__uint_as_float(s[2 * i + 1]), c, -mcc);
-        if (tail) { x0 = fminf(x0, 0.f); x1 = fminf(x1, 0.f); }   // absent keys score 0, which may exceed the max
-        pk[i] = ex2_bf16x2(pack_bf16x2(x0, x1));
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    if (attempt == 1 || p.force_exact) {
+      // ================= exact row maxima (fallback): stream all S tiles once, double-buffered in TMEM =================
+      KvRegs kv0 = load_kv<D, KT>(p, row, 0, N, quad, tid);
+      KvRegs kv1 = load_kv<D, KT>(p, row, KT, N, quad, tid);
+      store_k<D, KT>(kv0, smem + TA_KS, tid);
+      store_k<D, KT>(kv1, smem + TA_KS + 8192, tid);
+      fence_async_smem();
+      tc_fence_before();
+      __syncthreads();
+      if (tid == 0) {
+        tc_fence_after();
+        umma_bf16_ss(tmem, qdesc, umma_smem_desc_ns(sbase + TA_KS, 128, 256), idesc_s, 0u);
+        umma_commit(&bar_s[0]);
+        if (T > 1) {
+          umma_bf16_ss(tmem + 128, qdesc, umma_smem_desc_ns(sbase + TA_KS + 8192, 128, 256), idesc_s, 0u);
+          umma_commit(&bar_s[1]);
+        }
       }
-      uint8_t* dst = ps + head * P_HEAD + (r >> 3) * P_SBO + (r & 7) * 16 + (jbase >> 3) * 128;
 #pragma unroll
-      for (int q4 = 0; q4 < 4; ++q4)
-        *reinterpret_cast<uint4*>(dst + q4 * 128) = make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]);
+      for (int i = 0; i < HPT; ++i) m[i] = -CUDART_INF_F;
+      for (int t = 0; t < T; ++t) {
+        const int b = t & 1;
+        KvRegs kv2 = load_kv<D, KT>(p, row, (t + 2) * KT, N, quad, tid);
+        mbar_wait(&bar_s[b], ns[b] & 1); ++ns[b];
+        tc_fence_after();
+        const int kcount = min(KT, N - t * KT);
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {             // my 64 of the 128 columns
+          uint32_t s[32];
+          __syncwarp();
+          tmem_ld_x32(my_taddr + b * 128 + half * 64 + ch * 32, s);
+          tmem_ld_wait();
+          const int jbase = (half * 64 + ch * 32) % KT;
+          float mx = m[(ch * 32) / KT];
+          if (jbase + 32 <= kcount) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(s[i]));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) if (jbase + i < kcount) mx = fmaxf(mx, __uint_as_float(s[i]));
+          }
+          m[(ch * 32) / KT] = mx;
+        }
+        if (t + 2 < T) store_k<D, KT>(kv2, smem + TA_KS + b * 8192, tid);
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0 && t + 2 < T) {
+          tc_fence_after();
+          umma_bf16_ss(tmem + b * 128, qdesc, umma_smem_desc_ns(sbase + TA_KS + b * 8192, 128, 256), idesc_s, 0u);
+          umma_commit(&bar_s[b]);
+        }
+      }
+      kvn = load_kv<D, KT>(p, row, 0, N, quad, tid);
     }
+    float mc[HPT];
+#pragma unroll
+    for (int i = 0; i < HPT; ++i) mc[i] = m[i] * c;
+
+    // =========================== P = ex2(S*c - m*c), O += P V' ===========================
+    // Per tile: (a) wait S(t), pull my 64 scores into registers; sync; S(t+1) is issued at once and runs under (b);
+    // (b) exponentials -> bf16 P operand; sync; PV(t) is issued and runs under the next tile's (a)/(b).
+    store_k<D, KT>(kvn, smem + TA_KS, tid);
+    store_v<D, KT>(kvn, smem + TA_VS, tid);
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
     if (tid == 0) {
       tc_fence_after();
-      const uint32_t idesc_pv = umma_idesc_bf16(128, 16);
-      const uint32_t pbase = sbase + TA_PS + pb * 32768, vbase = sbase + TA_VS + (t % 3) * 4096;
+      umma_bf16_ss(tmem, qdesc, umma_smem_desc_ns(sbase + TA_KS, 128, 256), idesc_s, 0u);
+      umma_commit(&bar_s[0]);
+    }
+    kvn = load_kv<D, KT>(p, row, KT, N, quad, tid);
+    for (int t = 0; t < T; ++t) {
+      const int pb = t & 1;
+      mbar_wait(&bar_s[0], ns[0] & 1); ++ns[0];
+      tc_fence_after();
+      uint32_t s[64];
+      __syncwarp();
+      {
+        uint32_t lo[32], hi[32];
+        tmem_ld_x32(my_taddr + half * 64, lo);
+        tmem_ld_x32(my_taddr + half * 64 + 32, hi);
+        tmem_ld_wait();
 #pragma unroll
-      for (int h = 0; h < HPQ; ++h) {
-#pragma unroll
-        for (int kk = 0; kk < KT2 / 16; ++kk) {
-          umma_bf16_ss(tmem + TA_O_COL + 16 * h, umma_smem_desc_ns(pbase + h * P_HEAD + kk * 256, 128, P_SBO),
-                       umma_smem_desc_ns(vbase + h * V_HEAD + kk * 256, 128, P_SBO), idesc_pv, (t | kk) ? 1u : 0u);
-        }
+        for (int i = 0; i < 32; ++i) { s[i] = lo[i]; s[32 + i] = hi[i]; }
       }
-      umma_commit(&bar_pv[pb]);
-      if (t + 1 < T2) {
-        umma_bf16_ss(tmem, qdesc, umma_smem_desc_ns(sbase + TA_KS + ((t + 1) & 1) * 8192, 128, 256), umma_idesc_bf16(128, 128), 0u);
-        umma_commit(&bar_s);
+      if (t >= 2) { mbar_wait(&bar_pv[pb], npv[pb] & 1); ++npv[pb]; }   // PV(t-2) done: Ps[pb], Vs[(t+1)%3] free
+      if (t + 1 < T) {
+        store_k<D, KT>(kvn, smem + TA_KS + ((t + 1) & 1) * 8192, tid);
+        store_v<D, KT>(kvn, smem + TA_VS + ((t + 1) % 3) * 4096, tid);
+      }
+      fence_async_smem();
+      tc_fence_before();
+      __syncthreads();                                                   // everyone holds S(t) in registers
+      if (tid == 0 && t + 1 < T) {
+        tc_fence_after();
+        umma_bf16_ss(tmem, qdesc, umma_smem_desc_ns(sbase + TA_KS + ((t + 1) & 1) * 8192, 128, 256), idesc_s, 0u);
+        umma_commit(&bar_s[0]);
+      }
+      kvn = load_kv<D, KT>(p, row, (t + 2) * KT, N, quad, tid);          // global latency hides under the exponentials
+      const bool tail = (t + 1) * KT > N;            // only the last tile holds absent keys
+      uint8_t* ps = smem + TA_PS + pb * 32768;
+#pragma unroll
+      for (int ch = 0; ch < 2; ++ch) {
+        const int col = half * 64 + ch * 32;
+        const int head = col / KT, jbase = col % KT; // head within the quad, first key of this chunk
+        const float mcc = mc[(ch * 32) / KT];
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float x0 = fmaf(__uint_as_float(s[ch * 32 + 2 * i]), c, -mcc);
+          float x1 = fmaf(__uint_as_float(s[ch * 32 + 2 * i + 1]), c, -mcc);
+          if (tail) { x0 = fminf(x0, 0.f); x1 = fminf(x1, 0.f); }   // absent keys score 0, which may exceed the bound
+          pk[i] = pack_bf16x2(ex2_f32(x0), ex2_f32(x1));
+        }
+        uint8_t* dst = ps + head * P_HEAD + (r >> 3) * P_SBO + (r & 7) * 16 + (jbase >> 3) * 128;
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4)
+          *reinterpret_cast<uint4*>(dst + q4 * 128) = make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]);
+      }
+      fence_async_smem();
+      __syncthreads();                                                   // P(t) staged
+      if (tid == 0) {
+        tc_fence_after();
+        const uint32_t idesc_pv = umma_idesc_bf16(128, 16);
+        const uint32_t pbase = sbase + TA_PS + pb * 32768, vbase = sbase + TA_VS + (t % 3) * 4096;
+#pragma unroll
+        for (int h = 0; h < HPQ; ++h) {
+#pragma unroll
+          for (int kk = 0; kk < KT / 16; ++kk) {
+            umma_bf16_ss(tmem + TA_O_COL + 16 * h, umma_smem_desc_ns(pbase + h * P_HEAD + kk * 256, 128, P_SBO),
+                         umma_smem_desc_ns(vbase + h * V_HEAD + kk * 256, 128, P_SBO), idesc_pv, (t | kk) ? 1u : 0u);
+          }
+        }
+        umma_commit(&bar_pv[pb]);
       }
     }
-  }
-  // ---- epilogue: O / l ----
-  {
-    const int last = T2 - 1;
-    mbar_wait(&bar_pv[last & 1], (last >> 1) & 1);   // commits are ordered: the last PV implies all earlier ones
+    // ---- drain: exactly one un-consumed PV completion per barrier that was used ----
+    if (T > 1) { const int ob = (T & 1); mbar_wait(&bar_pv[ob], npv[ob] & 1); ++npv[ob]; }    // tile T-2
+    { const int lb = (T - 1) & 1; mbar_wait(&bar_pv[lb], npv[lb] & 1); ++npv[lb]; }            // tile T-1
     tc_fence_after();
+    // ---- epilogue: O / l ----
     uint32_t o[16 * HPT];
     __syncwarp();
     if (HPT == 2) {
@@ -291,6 +395,14 @@ __global__ void __launch_bounds__(TA_THREADS, 2) tc_attn_axial_kernel(const Attn
 #pragma unroll
       for (int i = 0; i < 16; ++i) o[i] = t16[i];
     }
+    // the bound keeps every exponent <= 0; if it was so loose that a whole row underflowed (denominator ~ 0) the CTA
+    // repeats the computation with the exact maximum
+    bool bad = false;
+#pragma unroll
+    for (int hh = 0; hh < HPT; ++hh) bad = bad || (q_valid && !(__uint_as_float(o[hh * 16 + D]) > 1e-30f));
+    tc_fence_before();
+    const bool redo = attempt == 0 && !p.force_exact && __syncthreads_or(bad);
+    if (redo) { kvn = load_kv<D, KT>(p, row, 0, N, quad, tid); continue; }
     if (q_valid) {
 #pragma unroll
       for (int hh = 0; hh < HPT; ++hh) {
@@ -312,6 +424,7 @@ __global__ void __launch_bounds__(TA_THREADS, 2) tc_attn_axial_kernel(const Attn
         if (p.lse) p.lse[q_tok * p.heads + quad * HPQ + head] = mc[hh] + log2f(l);
       }
     }
+    break;
   }
   tc_fence_before();
   __syncthreads();
@@ -334,6 +447,7 @@ extern "C" int tfswa_attn_tc_fwd(const tfswa_attn_args* a, void* stream) {
   p.qkv = a->qkv; p.ldq = a->ldq; p.out = a->out; p.ldo = a->ldo; p.lse = a->lse;
   p.B = a->B; p.H = a->H; p.W = a->W; p.C = a->C; p.heads = a->heads; p.geom = a->geom;
   p.qscale = (float)(1.4426950408889634 / sqrt((double)D));
+  p.force_exact = a->use_shift_mask;      // (the mask flag has no meaning for axial geometries) test hook: exact two-pass path
   const int N = a->geom == TFSWA_GEOM_TSA ? a->H : a->W;
   const int rows = a->geom == TFSWA_GEOM_TSA ? a->B * a->W : a->B * a->H;
   dim3 grid(rows, (N + TA_QT - 1) / TA_QT, a->C / 16);

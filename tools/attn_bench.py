@@ -1,0 +1,30 @@
+"""Micro-benchmark of the attention kernels at the C3 stage shapes (development helper)."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from tfswa_unet_b200 import ops
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 1
+stage = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+geoms = [int(g) for g in sys.argv[3].split(",")] if len(sys.argv) > 3 else [0, 1]
+H, W, C = {1: (1025, 517, 32), 2: (512, 258, 64), 3: (256, 129, 128), 4: (128, 64, 256)}[stage]
+M = B * H * W
+torch.manual_seed(0)
+qkv = torch.randn(M, 3 * C, device="cuda").to(torch.bfloat16)
+out = torch.empty(M, C, device="cuda", dtype=torch.bfloat16)
+for tc in (True, False):
+    ops.USE_TC_ATTENTION = tc
+    for geom in geoms:
+        for _ in range(2):
+            ops.attention(qkv, out, B, H, W, C, 8, geom)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            ops.attention(qkv, out, B, H, W, C, 8, geom)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 3
+        N = H if geom == 0 else W
+        exps = M * N * 8
+        print(f"stage {stage} B={B} geom={geom} tc={tc}: {ms:.3f} ms  {exps/ms/1e9:.2f} Gexp/ms... = {exps/(ms*1e-3)/1e12:.2f} Texp/s")
