@@ -284,7 +284,7 @@ def main():
     if os.path.exists(prof_path):
         with open(prof_path) as f:
             prof = json.load(f)
-    if dom["flops"] > 0 and dom_name in ("tfswa_linear_fwd", "linear", "attn", "tfswa_attn_fwd", "tfswa_conv_fwd", "fused"):
+    if dom["flops"] > 0 and dom_name in ("linear", "linear_tc", "attn", "attn_tc", "tfswa_conv_fwd"):
         achieved = dom["flops"] / (dom["ms"] / 1e3) / 1e12
         peak = peaks["bf16_tflops_sustained"]
         roof = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak}
@@ -301,6 +301,10 @@ def main():
                        "tflops": (c["flops"] / (c["ms"] / 1e3) / 1e12) if c["ms"] > 0 and c["flops"] else None}
                  for cls, c in sorted(classes.items(), key=lambda kv: -kv[1]["ms"])}
 
+    top = sorted(kern.items(), key=lambda kv: -kv[1]["ms"])[:12]
+    top_kernels = {tag: {"ms_per_step": k["ms"] / args.steps, "launches_per_step": k["launches"] / args.steps,
+                         "tflops": (k["flops"] / (k["ms"] / 1e3) / 1e12) if k["flops"] else None,
+                         "gbs": (k["bytes"] / (k["ms"] / 1e3) / 1e9) if k["bytes"] else None} for tag, k in top}
     from oracle.tfswa_oracle import count_model_flops
     flops = count_model_flops(B, 2, 2, H_BINS, W_FRAMES)
     line = {
@@ -313,7 +317,7 @@ def main():
                    "l2": "working set >> 126 MB L2 (stage-1 token tensor alone is 271 MB bf16); no explicit flush needed",
                    "parallelism": f"dp{world} (independent segments, no data-path collective)"},
         "model_tflop_per_step": flops / 1e12 * world, "achieved_model_tflops": flops / 1e12 * world / (step_ms / 1e3),
-        "roofline": roof, "kernel_breakdown": breakdown,
+        "roofline": roof, "kernel_breakdown": breakdown, "top_kernels": top_kernels,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": x_host.numel() * 4 * world,
                 "d2h_bytes_per_step": out_host.numel() * 4 * world, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches, "clocks": clocks,

@@ -67,19 +67,21 @@ struct TcLinearParams {
   int BN, BK, KB, stages;
   int epilogue, ln;
   uint32_t tmem_cols;
+  int OB;                    // columns per output TMA box (64 / 32 / 16): BN/OB boxes of 128 rows x OB*2 bytes, swizzled
 };
 
 constexpr int TC_BM = 128;
-constexpr int TC_THREADS = 192;     // warp 0: TMA + TMEM alloc, warp 1: MMA issue, warps 2-5: epilogue
+constexpr int TC_THREADS = 320;     // warp 0: TMA + TMEM alloc, warp 1: MMA issue, warps 2-9: epilogue (2 per TMEM lane quadrant)
 constexpr int TC_MAX_STAGES = 4;
 
 __global__ void __launch_bounds__(TC_THREADS) tc_linear_kernel(const __grid_constant__ CUtensorMap tmx,
                                                                const __grid_constant__ CUtensorMap tmw,
+                                                               const __grid_constant__ CUtensorMap tmy,
                                                                const TcLinearParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_full[TC_MAX_STAGES], bar_empty[TC_MAX_STAGES], bar_acc;
   __shared__ uint32_t s_tmem;
-  __shared__ float s_bias[256], s_wsum[256];
+  __shared__ __align__(16) float s_bias[256], s_wsum[256];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t m0 = (int64_t)blockIdx.x * TC_BM;
@@ -93,6 +95,7 @@ __global__ void __launch_bounds__(TC_THREADS) tc_linear_kernel(const __grid_cons
     if (lane == 0) {
       prefetch_tmap(&tmx);
       prefetch_tmap(&tmw);
+      prefetch_tmap(&tmy);
       for (int s = 0; s < p.stages; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
       mbar_init(&bar_acc, 1);
       fence_barrier_init();
@@ -139,41 +142,64 @@ __global__ void __launch_bounds__(TC_THREADS) tc_linear_kernel(const __grid_cons
     }
   } else {
     // ---------------- epilogue: TMEM -> registers -> bias / LN algebra / GELU / residuals -> global ----------------
-    const int et = threadIdx.x - 64;         // 0..127
-    for (int i = et; i < p.BN; i += 128) {
+    const int et = threadIdx.x - 64;         // 0..255
+    for (int i = et; i < p.BN; i += 256) {
       s_bias[i] = p.bias ? p.bias[(int64_t)z * p.bias_bs + n0 + i] : 0.f;
       s_wsum[i] = p.ln ? p.wsum[(int64_t)z * p.wsum_bs + n0 + i] : 0.f;
     }
-    asm volatile("bar.sync 1, 128;" ::: "memory");
+    asm volatile("bar.sync 1, 256;" ::: "memory");
     const int quad = warp & 3;               // TMEM lane quadrant this warp may access
+    const int nch = p.BN / 16;               // 16-column chunks; the two warps of a quadrant split them
+    const int c_begin = ((warp - 2) >> 2) ? (nch / 2) * 16 : 0;
+    const int c_end = ((warp - 2) >> 2) ? p.BN : (nch / 2) * 16;
     const int64_t m = m0 + quad * 32 + lane;
     const bool row_ok = m < p.M;
-    float mean = 0.f, rstd = 1.f;
+    float rstd = 1.f, nrm = 0.f;                  // nrm = -rstd*mean
     if (p.ln && row_ok) {
       const float2 st = *reinterpret_cast<const float2*>(p.row_stats + (int64_t)z * p.rs_bs + m * 2);
-      mean = st.x; rstd = st.y;
+      rstd = st.y; nrm = -st.x * st.y;
     }
-    bf16* yrow = p.y + (int64_t)z * p.y_bs + m * p.ldy + n0;
+    // Output staging: once the accumulator is complete every smem pipeline stage is dead, so the tile is staged in
+    // the same memory as BN/OB boxes of [128 rows x OB columns] in the TMA swizzle pattern (bank-conflict-free 16-byte
+    // row-per-thread writes) and leaves the SM as coalesced bulk-tensor stores; rows beyond M are clipped by the TMA.
+    const int row_in_tile = quad * 32 + lane;
+    const uint32_t ob_bytes = p.OB * 2, box_bytes = 128u * ob_bytes, swz_mask = (ob_bytes >> 4) - 1u;
+    const uint32_t ob_shift = p.OB == 64 ? 6u : (p.OB == 32 ? 5u : 4u);
     const bf16* r1row = p.r1 ? p.r1 + (int64_t)z * p.r1_bs + m * p.ldr1 + n0 : nullptr;
     const bf16* r2row = p.r2 ? p.r2 + (int64_t)z * p.r2_bs + m * p.ldr2 + n0 : nullptr;
 
     mbar_wait(&bar_acc, 0);
     tc_fence_after();
-    for (int c = 0; c < p.BN; c += 16) {
+    for (int c = c_begin; c < c_end; c += 16) {
       uint32_t raw[16];
       __syncwarp();                                      // tcgen05.ld is .sync.aligned: keep the warp converged
       tmem_ld_x16(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)c, raw);
       tmem_ld_wait();
-      if (row_ok) {
       float v[16];
+      {
+        float bs[16];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        float a = __uint_as_float(raw[j]);
-        if (p.ln) a = rstd * (a - mean * s_wsum[c + j]);
-        a += s_bias[c + j];
-        if (p.epilogue == TFSWA_EPI_GELU) a = gelu_erf(a);
-        v[j] = a;
+        for (int q4 = 0; q4 < 4; ++q4) {
+          const float4 b4 = *reinterpret_cast<const float4*>(&s_bias[c + 4 * q4]);
+          bs[4 * q4] = b4.x; bs[4 * q4 + 1] = b4.y; bs[4 * q4 + 2] = b4.z; bs[4 * q4 + 3] = b4.w;
+        }
+        if (p.ln) {                                  // y = rstd*acc - (rstd*mean)*wsum + bias
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            const float4 w4 = *reinterpret_cast<const float4*>(&s_wsum[c + 4 * q4]);
+            bs[4 * q4] = fmaf(nrm, w4.x, bs[4 * q4]); bs[4 * q4 + 1] = fmaf(nrm, w4.y, bs[4 * q4 + 1]);
+            bs[4 * q4 + 2] = fmaf(nrm, w4.z, bs[4 * q4 + 2]); bs[4 * q4 + 3] = fmaf(nrm, w4.w, bs[4 * q4 + 3]);
+          }
+        }
+        if (p.epilogue == TFSWA_EPI_GELU) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = gelu_erf_fast(fmaf(rstd, __uint_as_float(raw[j]), bs[j]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = fmaf(rstd, __uint_as_float(raw[j]), bs[j]);
+        }
       }
+      if (row_ok) {
       if (r1row) {
         float t[8];
         load8(r1row + c, t);
@@ -192,12 +218,26 @@ __global__ void __launch_bounds__(TC_THREADS) tc_linear_kernel(const __grid_cons
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[8 + j] += t[j];
       }
-      float lo[8], hi[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) { lo[j] = v[j]; hi[j] = v[8 + j]; }
-      store8(yrow + c, lo);
-      store8(yrow + c + 8, hi);
       }
+      {
+        float lo[8], hi[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { lo[j] = v[j]; hi[j] = v[8 + j]; }
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          const int cc = c + hf * 8;                                   // first column of this 16-byte chunk
+          const uint32_t blk = (uint32_t)cc >> ob_shift, chunk = ((uint32_t)cc & (p.OB - 1)) >> 3;
+          uint32_t off = row_in_tile * ob_bytes + chunk * 16u;
+          off ^= ((off >> 7) & swz_mask) << 4;                         // Swizzle<log2(span/16),4,3>, as the TMA expects
+          store8(reinterpret_cast<bf16*>(tiles + blk * box_bytes + off), hf ? hi : lo);
+        }
+      }
+    }
+    fence_async_smem();
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (threadIdx.x == 64) {
+      for (int b = 0; b < p.BN / p.OB; ++b) tma_store_3d(&tmy, tiles + b * box_bytes, n0 + b * p.OB, (int)m0, z);
+      tma_store_commit_wait();
     }
   }
   tc_fence_before();
@@ -206,6 +246,11 @@ __global__ void __launch_bounds__(TC_THREADS) tc_linear_kernel(const __grid_cons
 }
 
 static int pick_bn(int N) {
+  // <= 128 accumulator columns keeps 4 CTAs resident per SM (TMEM) so the epilogue of one tile overlaps the loads and
+  // MMAs of others; prefer tiles whose output box is 64 (then 32) columns wide
+  for (int step = 64; step >= 16; step >>= 1)
+    for (int bn = 128; bn >= step; bn -= step)
+      if (bn % step == 0 && N % bn == 0) return bn;
   for (int bn = 256; bn >= 16; bn -= 16)
     if (N % bn == 0) return bn;
   return 0;
@@ -240,12 +285,17 @@ extern "C" int tfswa_linear_tc_fwd(const tfswa_linear_args* a, const void* w_bf1
   p.r1 = (const bf16*)a->r1; p.ldr1 = a->ldr1; p.r1_bs = a->r1_bs; p.r2 = (const bf16*)a->r2; p.ldr2 = a->ldr2; p.r2_bs = a->r2_bs;
   p.y = (bf16*)a->y; p.ldy = a->ldy; p.y_bs = a->y_bs;
   p.M = a->M; p.N = a->N; p.K = a->K; p.epilogue = a->epilogue; p.ln = a->prologue == TFSWA_PRO_LNHAT;
-  CUtensorMap tmx, tmw;
+  p.OB = (p.BN % 64 == 0) ? 64 : ((p.BN % 32 == 0) ? 32 : 16);
+  CUtensorMap tmx, tmw, tmy;
   int rc = make_tmap_bf16_3d(&tmx, a->x, a->K, a->M, a->batch, a->ldx, a->x_bs, p.BK, TC_BM);
   if (rc) return rc;
   rc = make_tmap_bf16_3d(&tmw, w_bf16, a->K, a->N, a->batch, a->K, (uint64_t)a->N * a->K, p.BK, p.BN);
   if (rc) return rc;
-  const size_t smem = (size_t)p.stages * stage_bytes + 1024;
+  rc = make_tmap_bf16_3d(&tmy, a->y, a->N, a->M, a->batch, a->ldy, a->y_bs, p.OB, TC_BM);
+  if (rc) return rc;
+  size_t smem = (size_t)p.stages * stage_bytes;
+  if (smem < (size_t)TC_BM * p.BN * 2) smem = (size_t)TC_BM * p.BN * 2;     // the output tile is staged in the same memory
+  smem += 1024;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(tc_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -253,6 +303,6 @@ extern "C" int tfswa_linear_tc_fwd(const tfswa_linear_args* a, const void* w_bf1
     attr_set = true;
   }
   dim3 grid((unsigned)ceil_div64(a->M, TC_BM), a->N / p.BN, a->batch);
-  tc_linear_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(tmx, tmw, p);
+  tc_linear_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(tmx, tmw, tmy, p);
   return check_launch("linear_tc");
 }
