@@ -124,8 +124,31 @@ __device__ __forceinline__ float ex2_f32(float x) {
   return y;
 }
 
+// 2^x for x <= 0 on the FMA/ALU pipes (no MUFU): round-to-nearest split x = n + r with the 1.5*2^23 trick, degree-3
+// polynomial for 2^r on [-0.5, 0.5] (max rel. error 7.5e-5, far below the bf16 resolution of P), exponent patched in
+// with an integer add.  Used for a fixed fraction of the elements so the MUFU and FMA pipes share the exponentials
+// (the kernel is otherwise bound by MUFU.EX2 at 16 results/clk/SM).
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -125.0f);
+  const float t = x + 12582912.0f;                  // low mantissa bits of t = round(x) (two's complement)
+  const float r = x - (t - 12582912.0f);
+  float p = fmaf(0.0551716685f, r, 0.2426111251f);  // minimax (relative) fit of 2^r on [-0.5, 0.5]: 7.5e-5
+  p = fmaf(p, r, 0.6932609677f);
+  p = fmaf(p, r, 0.9999280572f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+constexpr int TA_POLY_EVERY = 4;                    // every TA_POLY_EVERY-th exponential goes to ex2_poly (0 = never)
+
+// Roles: warps 0-7 ("softmax", 256 threads) own one query row per thread pair, stage the K / V' operands of the next
+// tile cooperatively and turn S into P; warp 8 ("issuer") does nothing but wait on mbarriers and issue tcgen05.mma,
+// so the serial descriptor/MMA issue work never sits on the critical path of a softmax warp.  There is no CTA-wide
+// barrier in the key loop:
+//   bar_s   (1)  S(t) complete in TMEM                          issuer commit  -> softmax
+//   bar_a   (8)  S(t-1) pulled into registers + operands(t) staged   softmax  -> issuer (may issue S(t))
+//   bar_b[2](8)  P(t) staged                                          softmax  -> issuer (may issue PV(t))
+//   bar_pv[2](1) PV(t) complete: P buffer t&1 and V' buffer t%3 free  issuer commit -> softmax
 template <int D>
-__global__ void __launch_bounds__(TA_THREADS, 2) tc_attn_axial_kernel(const AttnParams p) {
+__global__ void __launch_bounds__(TA_THREADS + 32, 2) tc_attn_axial_kernel(const AttnParams p) {
   constexpr int HPQ = 16 / D;            // heads per CTA
   constexpr int KT = 128 / HPQ;          // keys per tile: one S tile = 128 TMEM columns = HPQ heads x KT keys
   constexpr int HPT = HPQ / 2;           // heads per thread
@@ -133,23 +156,26 @@ __global__ void __launch_bounds__(TA_THREADS, 2) tc_attn_axial_kernel(const Attn
   constexpr int P_HEAD = 128 * KT * 2;   // bytes of one head's P tile
   constexpr int V_HEAD = 16 * KT * 2;
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ __align__(8) uint64_t bar_s[2], bar_pv[2];
+  __shared__ __align__(8) uint64_t bar_s, bar_a, bar_b[2], bar_pv[2], bar_sx[2], bar_ax[2];
   __shared__ uint32_t s_tmem;
   __shared__ float s_kext[2][16];        // per channel of the quad: min / max of k over the whole sequence
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool issuer = warp == 8;
   const int row = blockIdx.x, q0 = blockIdx.y * TA_QT, quad = blockIdx.z;
   const int N = p.geom == TFSWA_GEOM_TSA ? p.H : p.W;
-  const int quarter = warp & 3, half = warp >> 2;
+  const int quarter = warp & 3, half = (warp >> 2) & 1;
   const int r = quarter * 32 + lane;                 // my query row == my TMEM lane
   const float c = p.qscale;                          // head_dim^-0.5 * log2(e)
   const int T = (N + KT - 1) / KT;
 
   // ---- setup: zero the operand buffers (their zero patterns are permanent), barriers, TMEM ----
-  for (int i = tid; i < (TA_PS - TA_KS) / 16; i += TA_THREADS) reinterpret_cast<uint4*>(smem + TA_KS)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < (TA_PS - TA_KS) / 16; i += TA_THREADS + 32) reinterpret_cast<uint4*>(smem + TA_KS)[i] = make_uint4(0, 0, 0, 0);
   if (warp == 0) {
     if (lane == 0) {
-      mbar_init(&bar_s[0], 1); mbar_init(&bar_s[1], 1); mbar_init(&bar_pv[0], 1); mbar_init(&bar_pv[1], 1);
+      mbar_init(&bar_s, 1); mbar_init(&bar_a, 8);
+#pragma unroll
+      for (int i = 0; i < 2; ++i) { mbar_init(&bar_b[i], 8); mbar_init(&bar_pv[i], 1); mbar_init(&bar_sx[i], 1); mbar_init(&bar_ax[i], 8); }
       fence_barrier_init();
     }
     __syncwarp();
@@ -157,18 +183,18 @@ __global__ void __launch_bounds__(TA_THREADS, 2) tc_attn_axial_kernel(const Attn
   }
   bool q_valid = false;
   int64_t q_tok = 0;
-  if (q0 + r < N) q_tok = token_of<false>(p, row, q0 + r, q_valid);
   uint4 qa = make_uint4(0, 0, 0, 0), qb = qa;        // my row's 16 q channels
-  if (q_valid) {
-    const uint4* src = reinterpret_cast<const uint4*>((const bf16*)p.qkv + q_tok * p.ldq + quad * 16);
-    qa = src[0]; qb = src[1];
-  }
-  if (tid < TA_QT) {                                 // Q operand: row r, 16 channels = 2 chunks of 16 B
-    *reinterpret_cast<uint4*>(smem + TA_QS + (r >> 3) * 256 + (r & 7) * 16) = qa;
-    *reinterpret_cast<uint4*>(smem + TA_QS + (r >> 3) * 256 + 128 + (r & 7) * 16) = qb;
-  }
-  // ---- per-channel extrema of k over the sequence (for the row-max upper bound) ----
-  {
+  if (!issuer) {
+    if (q0 + r < N) q_tok = token_of<false>(p, row, q0 + r, q_valid);
+    if (q_valid) {
+      const uint4* src = reinterpret_cast<const uint4*>((const bf16*)p.qkv + q_tok * p.ldq + quad * 16);
+      qa = src[0]; qb = src[1];
+    }
+    if (tid < TA_QT) {                               // Q operand: row r, 16 channels = 2 chunks of 16 B
+      *reinterpret_cast<uint4*>(smem + TA_QS + (r >> 3) * 256 + (r & 7) * 16) = qa;
+      *reinterpret_cast<uint4*>(smem + TA_QS + (r >> 3) * 256 + 128 + (r & 7) * 16) = qb;
+    }
+    // ---- per-channel extrema of k over the sequence (for the row-max upper bound) ----
     float kmn[16], kmx[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) { kmn[i] = CUDART_INF_F; kmx[i] = -CUDART_INF_F; }
@@ -187,10 +213,12 @@ __global__ void __launch_bounds__(TA_THREADS, 2) tc_attn_axial_kernel(const Attn
     float* red = reinterpret_cast<float*>(smem + TA_PS);          // [256][33] floats, P region is idle here
 #pragma unroll
     for (int i = 0; i < 16; ++i) { red[tid * 33 + i] = kmn[i]; red[tid * 33 + 16 + i] = kmx[i]; }
-    __syncthreads();                                              // also: zero fill done before any operand store
-    // warp w reduces columns 4w..4w+3 over the 256 rows
+  }
+  __syncthreads();                                                // zero fill + partial extrema visible
+  if (!issuer) {
+    const float* red = reinterpret_cast<const float*>(smem + TA_PS);
 #pragma unroll
-    for (int cidx = 0; cidx < 4; ++cidx) {
+    for (int cidx = 0; cidx < 4; ++cidx) {                        // warp w reduces columns 4w..4w+3 over the 256 rows
       const int col = warp * 4 + cidx;
       float v = red[lane * 33 + col];
 #pragma unroll
@@ -206,16 +234,22 @@ __global__ void __launch_bounds__(TA_THREADS, 2) tc_attn_axial_kernel(const Attn
       if (lane == 0) s_kext[col >> 4][col & 15] = v;
     }
   }
-  KvRegs kvn = load_kv<D, KT>(p, row, 0, N, quad, tid);
+  tc_fence_before();
   __syncthreads();
+  tc_fence_after();
   const uint32_t sbase = smem_u32(smem);
   const uint64_t qdesc = umma_smem_desc_ns(sbase + TA_QS, 128, 256);
   const uint32_t idesc_s = umma_idesc_bf16(128, 128);
-  uint32_t ns[2] = {0u, 0u}, npv[2] = {0u, 0u};      // barrier completions consumed (wait parity = count & 1)
+  const uint32_t tmem = s_tmem;
+  const uint32_t my_taddr = tmem + ((uint32_t)(quarter * 32) << 16);
+  // barrier completions consumed so far by this thread (wait parity = count & 1)
+  uint32_t n_s = 0, n_a = 0, n_b[2] = {0u, 0u}, n_pv[2] = {0u, 0u}, n_sx[2] = {0u, 0u}, n_ax[2] = {0u, 0u};
 
   // row-max upper bound per head: s_ij = sum_d q_d k_jd <= sum_d max(q_d kmax_d, q_d kmin_d)   (raw score units)
   float m[HPT];
-  {
+#pragma unroll
+  for (int hh = 0; hh < HPT; ++hh) m[hh] = 0.f;
+  if (!issuer) {
     uint4 raw[2] = {qa, qb};
     const __nv_bfloat16* qe = reinterpret_cast<const __nv_bfloat16*>(raw);
 #pragma unroll
@@ -230,180 +264,192 @@ __global__ void __launch_bounds__(TA_THREADS, 2) tc_attn_axial_kernel(const Attn
       m[hh] = b;
     }
   }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = s_tmem;
-  const uint32_t my_taddr = tmem + ((uint32_t)(quarter * 32) << 16);
 
   for (int attempt = 0; attempt < 2; ++attempt) {
     if (attempt == 1 || p.force_exact) {
       // ================= exact row maxima (fallback): stream all S tiles once, double-buffered in TMEM =================
-      KvRegs kv0 = load_kv<D, KT>(p, row, 0, N, quad, tid);
-      KvRegs kv1 = load_kv<D, KT>(p, row, KT, N, quad, tid);
-      store_k<D, KT>(kv0, smem + TA_KS, tid);
-      store_k<D, KT>(kv1, smem + TA_KS + 8192, tid);
-      fence_async_smem();
-      tc_fence_before();
-      __syncthreads();
-      if (tid == 0) {
-        tc_fence_after();
-        umma_bf16_ss(tmem, qdesc, umma_smem_desc_ns(sbase + TA_KS, 128, 256), idesc_s, 0u);
-        umma_commit(&bar_s[0]);
-        if (T > 1) {
-          umma_bf16_ss(tmem + 128, qdesc, umma_smem_desc_ns(sbase + TA_KS + 8192, 128, 256), idesc_s, 0u);
-          umma_commit(&bar_s[1]);
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < HPT; ++i) m[i] = -CUDART_INF_F;
-      for (int t = 0; t < T; ++t) {
-        const int b = t & 1;
-        KvRegs kv2 = load_kv<D, KT>(p, row, (t + 2) * KT, N, quad, tid);
-        mbar_wait(&bar_s[b], ns[b] & 1); ++ns[b];
-        tc_fence_after();
-        const int kcount = min(KT, N - t * KT);
-#pragma unroll
-        for (int ch = 0; ch < 2; ++ch) {             // my 64 of the 128 columns
-          uint32_t s[32];
-          __syncwarp();
-          tmem_ld_x32(my_taddr + b * 128 + half * 64 + ch * 32, s);
-          tmem_ld_wait();
-          const int jbase = (half * 64 + ch * 32) % KT;
-          float mx = m[(ch * 32) / KT];
-          if (jbase + 32 <= kcount) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(s[i]));
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) if (jbase + i < kcount) mx = fmaxf(mx, __uint_as_float(s[i]));
+      //   bar_ax[b] (8): K(t) staged in Ks[b] and TMEM buffer b drained  -> issuer issues S(t);   bar_sx[b] (1): S(t) complete
+      if (issuer) {
+        for (int t = 0; t < T; ++t) {
+          const int b = t & 1;
+          mbar_wait(&bar_ax[b], n_ax[b] & 1); ++n_ax[b];
+          if (lane == 0) {
+            tc_fence_after();
+            umma_bf16_ss(tmem + b * 128, qdesc, umma_smem_desc_ns(sbase + TA_KS + b * 8192, 128, 256), idesc_s, 0u);
+            umma_commit(&bar_sx[b]);
           }
-          m[(ch * 32) / KT] = mx;
+          __syncwarp();
         }
-        if (t + 2 < T) store_k<D, KT>(kv2, smem + TA_KS + b * 8192, tid);
-        fence_async_smem();
-        tc_fence_before();
-        __syncthreads();
-        if (tid == 0 && t + 2 < T) {
+      } else {
+#pragma unroll
+        for (int i = 0; i < HPT; ++i) m[i] = -CUDART_INF_F;
+        // stage K(0), K(1)
+        for (int t0 = 0; t0 < 2 && t0 < T; ++t0) {
+          KvRegs kv = load_kv<D, KT>(p, row, t0 * KT, N, quad, tid);
+          store_k<D, KT>(kv, smem + TA_KS + t0 * 8192, tid);
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bar_ax[t0]);
+        }
+        for (int t = 0; t < T; ++t) {
+          const int b = t & 1;
+          KvRegs kv2 = load_kv<D, KT>(p, row, (t + 2) * KT, N, quad, tid);
+          mbar_wait(&bar_sx[b], n_sx[b] & 1); ++n_sx[b];
           tc_fence_after();
-          umma_bf16_ss(tmem + b * 128, qdesc, umma_smem_desc_ns(sbase + TA_KS + b * 8192, 128, 256), idesc_s, 0u);
-          umma_commit(&bar_s[b]);
+          const int kcount = min(KT, N - t * KT);
+#pragma unroll
+          for (int ch = 0; ch < 2; ++ch) {             // my 64 of the 128 columns
+            uint32_t s[32];
+            __syncwarp();
+            tmem_ld_x32(my_taddr + b * 128 + half * 64 + ch * 32, s);
+            tmem_ld_wait();
+            const int jbase = (half * 64 + ch * 32) % KT;
+            float mx = m[(ch * 32) / KT];
+            if (jbase + 32 <= kcount) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(s[i]));
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) if (jbase + i < kcount) mx = fmaxf(mx, __uint_as_float(s[i]));
+            }
+            m[(ch * 32) / KT] = mx;
+          }
+          if (t + 2 < T) {
+            store_k<D, KT>(kv2, smem + TA_KS + b * 8192, tid);      // S(t) complete -> Ks[b] free
+            fence_async_smem();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_ax[b]);
+          }
         }
       }
-      kvn = load_kv<D, KT>(p, row, 0, N, quad, tid);
+      tc_fence_before();
+      __syncthreads();                                              // every S tile consumed before the buffers are reused
+      tc_fence_after();
     }
     float mc[HPT];
 #pragma unroll
     for (int i = 0; i < HPT; ++i) mc[i] = m[i] * c;
 
     // =========================== P = ex2(S*c - m*c), O += P V' ===========================
-    // Per tile: (a) wait S(t), pull my 64 scores into registers; sync; S(t+1) is issued at once and runs under (b);
-    // (b) exponentials -> bf16 P operand; sync; PV(t) is issued and runs under the next tile's (a)/(b).
-    store_k<D, KT>(kvn, smem + TA_KS, tid);
-    store_v<D, KT>(kvn, smem + TA_VS, tid);
-    fence_async_smem();
-    tc_fence_before();
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-      umma_bf16_ss(tmem, qdesc, umma_smem_desc_ns(sbase + TA_KS, 128, 256), idesc_s, 0u);
-      umma_commit(&bar_s[0]);
-    }
-    kvn = load_kv<D, KT>(p, row, KT, N, quad, tid);
-    for (int t = 0; t < T; ++t) {
-      const int pb = t & 1;
-      mbar_wait(&bar_s[0], ns[0] & 1); ++ns[0];
-      tc_fence_after();
-      uint32_t s[64];
-      __syncwarp();
-      {
-        uint32_t lo[32], hi[32];
-        tmem_ld_x32(my_taddr + half * 64, lo);
-        tmem_ld_x32(my_taddr + half * 64 + 32, hi);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) { s[i] = lo[i]; s[32 + i] = hi[i]; }
-      }
-      if (t >= 2) { mbar_wait(&bar_pv[pb], npv[pb] & 1); ++npv[pb]; }   // PV(t-2) done: Ps[pb], Vs[(t+1)%3] free
-      if (t + 1 < T) {
-        store_k<D, KT>(kvn, smem + TA_KS + ((t + 1) & 1) * 8192, tid);
-        store_v<D, KT>(kvn, smem + TA_VS + ((t + 1) % 3) * 4096, tid);
-      }
-      fence_async_smem();
-      tc_fence_before();
-      __syncthreads();                                                   // everyone holds S(t) in registers
-      if (tid == 0 && t + 1 < T) {
-        tc_fence_after();
-        umma_bf16_ss(tmem, qdesc, umma_smem_desc_ns(sbase + TA_KS + ((t + 1) & 1) * 8192, 128, 256), idesc_s, 0u);
-        umma_commit(&bar_s[0]);
-      }
-      kvn = load_kv<D, KT>(p, row, (t + 2) * KT, N, quad, tid);          // global latency hides under the exponentials
-      const bool tail = (t + 1) * KT > N;            // only the last tile holds absent keys
-      uint8_t* ps = smem + TA_PS + pb * 32768;
-#pragma unroll
-      for (int ch = 0; ch < 2; ++ch) {
-        const int col = half * 64 + ch * 32;
-        const int head = col / KT, jbase = col % KT; // head within the quad, first key of this chunk
-        const float mcc = mc[(ch * 32) / KT];
-        uint32_t pk[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float x0 = fmaf(__uint_as_float(s[ch * 32 + 2 * i]), c, -mcc);
-          float x1 = fmaf(__uint_as_float(s[ch * 32 + 2 * i + 1]), c, -mcc);
-          if (tail) { x0 = fminf(x0, 0.f); x1 = fminf(x1, 0.f); }   // absent keys score 0, which may exceed the bound
-          pk[i] = pack_bf16x2(ex2_f32(x0), ex2_f32(x1));
+    if (issuer) {
+      const uint32_t idesc_pv = umma_idesc_bf16(128, 16);
+      for (int t = 0; t <= T; ++t) {
+        mbar_wait(&bar_a, n_a & 1); ++n_a;                            // S(t-1) consumed, operands(t) staged
+        if (t < T && lane == 0) {
+          tc_fence_after();
+          umma_bf16_ss(tmem, qdesc, umma_smem_desc_ns(sbase + TA_KS + (t & 1) * 8192, 128, 256), idesc_s, 0u);
+          umma_commit(&bar_s);
         }
-        uint8_t* dst = ps + head * P_HEAD + (r >> 3) * P_SBO + (r & 7) * 16 + (jbase >> 3) * 128;
+        if (t >= 1) {
+          const int u = t - 1, pb = u & 1;
+          mbar_wait(&bar_b[pb], n_b[pb] & 1); ++n_b[pb];              // P(u) staged
+          if (lane == 0) {
+            tc_fence_after();
+            const uint32_t pbase = sbase + TA_PS + pb * 32768, vbase = sbase + TA_VS + (u % 3) * 4096;
 #pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4)
-          *reinterpret_cast<uint4*>(dst + q4 * 128) = make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]);
-      }
-      fence_async_smem();
-      __syncthreads();                                                   // P(t) staged
-      if (tid == 0) {
-        tc_fence_after();
-        const uint32_t idesc_pv = umma_idesc_bf16(128, 16);
-        const uint32_t pbase = sbase + TA_PS + pb * 32768, vbase = sbase + TA_VS + (t % 3) * 4096;
+            for (int h = 0; h < HPQ; ++h) {
 #pragma unroll
-        for (int h = 0; h < HPQ; ++h) {
-#pragma unroll
-          for (int kk = 0; kk < KT / 16; ++kk) {
-            umma_bf16_ss(tmem + TA_O_COL + 16 * h, umma_smem_desc_ns(pbase + h * P_HEAD + kk * 256, 128, P_SBO),
-                         umma_smem_desc_ns(vbase + h * V_HEAD + kk * 256, 128, P_SBO), idesc_pv, (t | kk) ? 1u : 0u);
+              for (int kk = 0; kk < KT / 16; ++kk) {
+                umma_bf16_ss(tmem + TA_O_COL + 16 * h, umma_smem_desc_ns(pbase + h * P_HEAD + kk * 256, 128, P_SBO),
+                             umma_smem_desc_ns(vbase + h * V_HEAD + kk * 256, 128, P_SBO), idesc_pv, (u | kk) ? 1u : 0u);
+              }
+            }
+            umma_commit(&bar_pv[pb]);
           }
         }
-        umma_commit(&bar_pv[pb]);
+        __syncwarp();
       }
+    } else {
+      KvRegs kvn = load_kv<D, KT>(p, row, 0, N, quad, tid);
+      store_k<D, KT>(kvn, smem + TA_KS, tid);
+      store_v<D, KT>(kvn, smem + TA_VS, tid);
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_a);                             // operands(0) staged
+      kvn = load_kv<D, KT>(p, row, KT, N, quad, tid);
+      for (int t = 0; t < T; ++t) {
+        const int pb = t & 1;
+        mbar_wait(&bar_s, n_s & 1); ++n_s;
+        tc_fence_after();
+        uint32_t s[64];
+        __syncwarp();
+        {
+          uint32_t lo[32], hi[32];
+          tmem_ld_x32(my_taddr + half * 64, lo);
+          tmem_ld_x32(my_taddr + half * 64 + 32, hi);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) { s[i] = lo[i]; s[32 + i] = hi[i]; }
+        }
+        tc_fence_before();
+        if (t >= 2) { mbar_wait(&bar_pv[pb], n_pv[pb] & 1); ++n_pv[pb]; }   // PV(t-2) done: Ps[pb], Vs[(t+1)%3] free
+        if (t + 1 < T) {
+          store_k<D, KT>(kvn, smem + TA_KS + ((t + 1) & 1) * 8192, tid);
+          store_v<D, KT>(kvn, smem + TA_VS + ((t + 1) % 3) * 4096, tid);
+          fence_async_smem();
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_a);                           // S(t) consumed + operands(t+1) staged
+        kvn = load_kv<D, KT>(p, row, (t + 2) * KT, N, quad, tid);     // global latency hides under the exponentials
+        const bool tail = (t + 1) * KT > N;          // only the last tile holds absent keys
+        uint8_t* ps = smem + TA_PS + pb * 32768;
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+          const int col = half * 64 + ch * 32;
+          const int head = col / KT, jbase = col % KT; // head within the quad, first key of this chunk
+          const float mcc = mc[(ch * 32) / KT];
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float x0 = fmaf(__uint_as_float(s[ch * 32 + 2 * i]), c, -mcc);
+            float x1 = fmaf(__uint_as_float(s[ch * 32 + 2 * i + 1]), c, -mcc);
+            if (tail) { x0 = fminf(x0, 0.f); x1 = fminf(x1, 0.f); }   // absent keys score 0, which may exceed the bound
+            const float e0 = ex2_f32(x0);
+            const float e1 = (TA_POLY_EVERY > 0 && ((2 * i + 1) % TA_POLY_EVERY) == TA_POLY_EVERY - 1) ? ex2_poly(x1) : ex2_f32(x1);
+            pk[i] = pack_bf16x2(e0, e1);
+          }
+          uint8_t* dst = ps + head * P_HEAD + (r >> 3) * P_SBO + (r & 7) * 16 + (jbase >> 3) * 128;
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4)
+            *reinterpret_cast<uint4*>(dst + q4 * 128) = make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]);
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_b[pb]);                       // P(t) staged
+      }
+      // ---- drain: exactly one un-consumed PV completion per barrier that was used ----
+      if (T > 1) { const int ob = (T & 1); mbar_wait(&bar_pv[ob], n_pv[ob] & 1); ++n_pv[ob]; }    // tile T-2
+      { const int lb = (T - 1) & 1; mbar_wait(&bar_pv[lb], n_pv[lb] & 1); ++n_pv[lb]; }            // tile T-1
+      tc_fence_after();
     }
-    // ---- drain: exactly one un-consumed PV completion per barrier that was used ----
-    if (T > 1) { const int ob = (T & 1); mbar_wait(&bar_pv[ob], npv[ob] & 1); ++npv[ob]; }    // tile T-2
-    { const int lb = (T - 1) & 1; mbar_wait(&bar_pv[lb], npv[lb] & 1); ++npv[lb]; }            // tile T-1
-    tc_fence_after();
     // ---- epilogue: O / l ----
     uint32_t o[16 * HPT];
-    __syncwarp();
-    if (HPT == 2) {
-      uint32_t t32[32];
-      tmem_ld_x32(my_taddr + TA_O_COL + 32 * half, t32);
-      tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < 32; ++i) o[i % (16 * HPT)] = t32[i];
-    } else {
-      uint32_t t16[16];
-      tmem_ld_x16(my_taddr + TA_O_COL + 16 * half, t16);
-      tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < 16; ++i) o[i] = t16[i];
-    }
-    // the bound keeps every exponent <= 0; if it was so loose that a whole row underflowed (denominator ~ 0) the CTA
-    // repeats the computation with the exact maximum
     bool bad = false;
+    if (!issuer) {
+      __syncwarp();
+      if (HPT == 2) {
+        uint32_t t32[32];
+        tmem_ld_x32(my_taddr + TA_O_COL + 32 * half, t32);
+        tmem_ld_wait();
 #pragma unroll
-    for (int hh = 0; hh < HPT; ++hh) bad = bad || (q_valid && !(__uint_as_float(o[hh * 16 + D]) > 1e-30f));
+        for (int i = 0; i < 32; ++i) o[i % (16 * HPT)] = t32[i];
+      } else {
+        uint32_t t16[16];
+        tmem_ld_x16(my_taddr + TA_O_COL + 16 * half, t16);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) o[i] = t16[i];
+      }
+      // the bound keeps every exponent <= 0; if it was so loose that a whole row underflowed (denominator ~ 0) the CTA
+      // repeats the computation with the exact maximum
+#pragma unroll
+      for (int hh = 0; hh < HPT; ++hh) bad = bad || (q_valid && !(__uint_as_float(o[hh * 16 + D]) > 1e-30f));
+    }
     tc_fence_before();
     const bool redo = attempt == 0 && !p.force_exact && __syncthreads_or(bad);
-    if (redo) { kvn = load_kv<D, KT>(p, row, 0, N, quad, tid); continue; }
-    if (q_valid) {
+    if (redo) continue;
+    if (!issuer && q_valid) {
 #pragma unroll
       for (int hh = 0; hh < HPT; ++hh) {
         const int head = half * HPT + hh;            // head within the quad
@@ -460,7 +506,7 @@ extern "C" int tfswa_attn_tc_fwd(const tfswa_attn_args* a, void* stream) {
     if (e1 != cudaSuccess || e2 != cudaSuccess) { set_error("attn_tc: cudaFuncSetAttribute failed"); return TFSWA_ECUDA; }
     attr_set = true;
   }
-  if (D == 4) tc_attn_axial_kernel<4><<<grid, TA_THREADS, TA_SMEM, st>>>(p);
-  else tc_attn_axial_kernel<8><<<grid, TA_THREADS, TA_SMEM, st>>>(p);
+  if (D == 4) tc_attn_axial_kernel<4><<<grid, TA_THREADS + 32, TA_SMEM, st>>>(p);
+  else tc_attn_axial_kernel<8><<<grid, TA_THREADS + 32, TA_SMEM, st>>>(p);
   return check_launch("attn_tc");
 }
