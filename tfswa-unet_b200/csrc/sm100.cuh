@@ -29,19 +29,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)     // suspend-time hint: sleep in hardware instead of spinning
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug must surface as a trapped kernel (launch error), never as a hung GPU.
+// Bounded wait: a protocol bug must surface as a trapped kernel (launch error), never as a hung GPU.  try_wait sleeps
+// in hardware up to the suspend hint, so the retry count stays small; the bound is on retries, not on a clock read.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
+  uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) __trap();   // ~2 s at 1.9 GHz
+    if (++spins > (1u << 24)) __trap();
   }
 }
 

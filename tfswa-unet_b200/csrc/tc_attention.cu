@@ -58,19 +58,20 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 // (key, head) slice of v (2*D bytes). ----
 struct KvRegs { uint4 a, b; bool present; };
 
+// token(n) = tok_base + n * tok_stride for the axial geometries (no division in the key loop)
 template <int D, int KT>
-__device__ __forceinline__ KvRegs load_kv(const AttnParams& p, int row, int k0, int N, int quad, int tid) {
+__device__ __forceinline__ KvRegs load_kv(const AttnParams& p, int64_t tok_base, int64_t tok_stride, int k0, int N, int quad, int tid) {
   KvRegs r; r.a = make_uint4(0, 0, 0, 0); r.b = r.a; r.present = false;
   if (tid < KT) {
     if (k0 + tid < N) {
-      bool valid; const int64_t tok = token_of<false>(p, row, k0 + tid, valid);
+      const int64_t tok = tok_base + (int64_t)(k0 + tid) * tok_stride;
       const uint4* src = reinterpret_cast<const uint4*>((const bf16*)p.qkv + tok * p.ldq + p.C + quad * 16);
       r.a = src[0]; r.b = src[1]; r.present = true;
     }
   } else if (tid >= 128) {
     const int idx = tid - 128, j = idx % KT, h = idx / KT;
     if (k0 + j < N) {
-      bool valid; const int64_t tok = token_of<false>(p, row, k0 + j, valid);
+      const int64_t tok = tok_base + (int64_t)(k0 + j) * tok_stride;
       const bf16* src = (const bf16*)p.qkv + tok * p.ldq + 2 * p.C + quad * 16 + h * D;
       if (D == 4) { const uint2 t = *reinterpret_cast<const uint2*>(src); r.a.x = t.x; r.a.y = t.y; }
       else r.a = *reinterpret_cast<const uint4*>(src);
@@ -137,7 +138,7 @@ __device__ __forceinline__ float ex2_poly(float x) {
   p = fmaf(p, r, 0.9999280572f);
   return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
 }
-constexpr int TA_POLY_EVERY = 4;                    // every TA_POLY_EVERY-th exponential goes to ex2_poly (0 = never)
+constexpr int TA_POLY_EVERY = 0;                    // every TA_POLY_EVERY-th exponential goes to ex2_poly (0 = never)
 
 // Roles: warps 0-7 ("softmax", 256 threads) own one query row per thread pair, stage the K / V' operands of the next
 // tile cooperatively and turn S into P; warp 8 ("issuer") does nothing but wait on mbarriers and issue tcgen05.mma,
@@ -168,6 +169,9 @@ __global__ void __launch_bounds__(TA_THREADS + 32, 2) tc_attn_axial_kernel(const
   const int r = quarter * 32 + lane;                 // my query row == my TMEM lane
   const float c = p.qscale;                          // head_dim^-0.5 * log2(e)
   const int T = (N + KT - 1) / KT;
+  int64_t tok_base, tok_stride;
+  if (p.geom == TFSWA_GEOM_TSA) { const int b = row / p.W; tok_base = (int64_t)b * p.H * p.W + (row - b * p.W); tok_stride = p.W; }
+  else { tok_base = (int64_t)row * p.W; tok_stride = 1; }
 
   // ---- setup: zero the operand buffers (their zero patterns are permanent), barriers, TMEM ----
   for (int i = tid; i < (TA_PS - TA_KS) / 16; i += TA_THREADS + 32) reinterpret_cast<uint4*>(smem + TA_KS)[i] = make_uint4(0, 0, 0, 0);
@@ -185,7 +189,7 @@ __global__ void __launch_bounds__(TA_THREADS + 32, 2) tc_attn_axial_kernel(const
   int64_t q_tok = 0;
   uint4 qa = make_uint4(0, 0, 0, 0), qb = qa;        // my row's 16 q channels
   if (!issuer) {
-    if (q0 + r < N) q_tok = token_of<false>(p, row, q0 + r, q_valid);
+    if (q0 + r < N) { q_tok = tok_base + (int64_t)(q0 + r) * tok_stride; q_valid = true; }
     if (q_valid) {
       const uint4* src = reinterpret_cast<const uint4*>((const bf16*)p.qkv + q_tok * p.ldq + quad * 16);
       qa = src[0]; qb = src[1];
@@ -199,7 +203,7 @@ __global__ void __launch_bounds__(TA_THREADS + 32, 2) tc_attn_axial_kernel(const
 #pragma unroll
     for (int i = 0; i < 16; ++i) { kmn[i] = CUDART_INF_F; kmx[i] = -CUDART_INF_F; }
     for (int j = tid; j < N; j += TA_THREADS) {
-      bool valid; const int64_t tok = token_of<false>(p, row, j, valid);
+      const int64_t tok = tok_base + (int64_t)j * tok_stride;
       const uint4* src = reinterpret_cast<const uint4*>((const bf16*)p.qkv + tok * p.ldq + p.C + quad * 16);
       uint4 raw[2] = {src[0], src[1]};
       const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(raw);
@@ -285,7 +289,7 @@ __global__ void __launch_bounds__(TA_THREADS + 32, 2) tc_attn_axial_kernel(const
         for (int i = 0; i < HPT; ++i) m[i] = -CUDART_INF_F;
         // stage K(0), K(1)
         for (int t0 = 0; t0 < 2 && t0 < T; ++t0) {
-          KvRegs kv = load_kv<D, KT>(p, row, t0 * KT, N, quad, tid);
+          KvRegs kv = load_kv<D, KT>(p, tok_base, tok_stride, t0 * KT, N, quad, tid);
           store_k<D, KT>(kv, smem + TA_KS + t0 * 8192, tid);
           fence_async_smem();
           __syncwarp();
@@ -293,7 +297,7 @@ __global__ void __launch_bounds__(TA_THREADS + 32, 2) tc_attn_axial_kernel(const
         }
         for (int t = 0; t < T; ++t) {
           const int b = t & 1;
-          KvRegs kv2 = load_kv<D, KT>(p, row, (t + 2) * KT, N, quad, tid);
+          KvRegs kv2 = load_kv<D, KT>(p, tok_base, tok_stride, (t + 2) * KT, N, quad, tid);
           mbar_wait(&bar_sx[b], n_sx[b] & 1); ++n_sx[b];
           tc_fence_after();
           const int kcount = min(KT, N - t * KT);
@@ -361,13 +365,13 @@ __global__ void __launch_bounds__(TA_THREADS + 32, 2) tc_attn_axial_kernel(const
         __syncwarp();
       }
     } else {
-      KvRegs kvn = load_kv<D, KT>(p, row, 0, N, quad, tid);
+      KvRegs kvn = load_kv<D, KT>(p, tok_base, tok_stride, 0, N, quad, tid);
       store_k<D, KT>(kvn, smem + TA_KS, tid);
       store_v<D, KT>(kvn, smem + TA_VS, tid);
       fence_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_a);                             // operands(0) staged
-      kvn = load_kv<D, KT>(p, row, KT, N, quad, tid);
+      kvn = load_kv<D, KT>(p, tok_base, tok_stride, KT, N, quad, tid);
       for (int t = 0; t < T; ++t) {
         const int pb = t & 1;
         mbar_wait(&bar_s, n_s & 1); ++n_s;
@@ -391,9 +395,12 @@ __global__ void __launch_bounds__(TA_THREADS + 32, 2) tc_attn_axial_kernel(const
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar_a);                           // S(t) consumed + operands(t+1) staged
-        kvn = load_kv<D, KT>(p, row, (t + 2) * KT, N, quad, tid);     // global latency hides under the exponentials
-        const bool tail = (t + 1) * KT > N;          // only the last tile holds absent keys
+        kvn = load_kv<D, KT>(p, tok_base, tok_stride, (t + 2) * KT, N, quad, tid);     // global latency hides under the exponentials
         uint8_t* ps = smem + TA_PS + pb * 32768;
+        if ((t + 1) * KT > N) {                      // only the last tile holds absent keys: their score 0 may exceed the bound
+#pragma unroll
+          for (int i = 0; i < 64; ++i) s[i] = __float_as_uint(fminf(__uint_as_float(s[i]), m[(i / 32 * 32) / KT]));
+        }
 #pragma unroll
         for (int ch = 0; ch < 2; ++ch) {
           const int col = half * 64 + ch * 32;
@@ -402,9 +409,8 @@ __global__ void __launch_bounds__(TA_THREADS + 32, 2) tc_attn_axial_kernel(const
           uint32_t pk[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            float x0 = fmaf(__uint_as_float(s[ch * 32 + 2 * i]), c, -mcc);
-            float x1 = fmaf(__uint_as_float(s[ch * 32 + 2 * i + 1]), c, -mcc);
-            if (tail) { x0 = fminf(x0, 0.f); x1 = fminf(x1, 0.f); }   // absent keys score 0, which may exceed the bound
+            const float x0 = fmaf(__uint_as_float(s[ch * 32 + 2 * i]), c, -mcc);
+            const float x1 = fmaf(__uint_as_float(s[ch * 32 + 2 * i + 1]), c, -mcc);
             const float e0 = ex2_f32(x0);
             const float e1 = (TA_POLY_EVERY > 0 && ((2 * i + 1) % TA_POLY_EVERY) == TA_POLY_EVERY - 1) ? ex2_poly(x1) : ex2_f32(x1);
             pk[i] = pack_bf16x2(e0, e1);
