@@ -28,7 +28,7 @@ __global__ void __launch_bounds__(QT * (32 / D)) attn_fwd_kernel(const AttnParam
   const int head_local = warp % HG;
   const int qsub = warp / HG;
   const int row = blockIdx.x;
-  const int q0 = blockIdx.y * QT;
+  const int q0 = (WINDOW ? 0 : p.q_begin) + blockIdx.y * QT;
   const int hg = blockIdx.z;
   const int N = WINDOW ? p.ws * p.ws : (p.geom == TFSWA_GEOM_TSA ? p.H : p.W);
   const int ch0 = hg * 32;                 // first channel of this CTA's slab
@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(QT * (32 / D)) attn_fwd_kernel(const AttnParam
 
   // ---- my query ----
   const int qn = q0 + qsub * 32 + lane;
-  bool q_valid = qn < N;
+  bool q_valid = qn < (WINDOW || p.q_end == 0 ? N : p.q_end);
   int64_t q_tok = 0;
   if (q_valid) { bool v; q_tok = token_of<WINDOW>(p, row, qn, v); q_valid = v; }
   float q[D];
@@ -171,10 +171,107 @@ static int launch_attn(const AttnParams& p, cudaStream_t st) {
   } else {
     const int N = p.geom == TFSWA_GEOM_TSA ? p.H : p.W;
     const int rows = p.geom == TFSWA_GEOM_TSA ? p.B * p.W : p.B * p.H;
-    dim3 grid(rows, (N + QT - 1) / QT, hgs);
+    const int nq = (p.q_end ? p.q_end : N) - p.q_begin;
+    dim3 grid(rows, (nq + QT - 1) / QT, hgs);
     attn_fwd_kernel<T, D, false, false><<<grid, QT * HG, 0, st>>>(p);
   }
   return check_launch("attn_fwd");
+}
+
+// Ragged-remainder kernel for the tensor-core path: a handful of queries per sequence (N mod 128 < 32).  One warp per
+// (sequence, query, head); the 32 lanes split the KEYS (lane l takes keys l, l+32, ...), each keeps its own online
+// softmax state and the warp merges them with shuffles - so even a single leftover query is spread over 32 lanes
+// instead of running a 1000-step dependent chain in one thread.
+template <int D>
+__global__ void __launch_bounds__(256) attn_rem_kernel(const AttnParams p) {
+  const int row = blockIdx.x, qn = p.q_begin + blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  const int head = blockIdx.z * 8 + (threadIdx.x >> 5);
+  const int N = p.geom == TFSWA_GEOM_TSA ? p.H : p.W;
+  if (head >= p.heads) return;
+  const bf16* qkv = (const bf16*)p.qkv;
+  bool v; const int64_t q_tok = token_of<false>(p, row, qn, v);
+  float q[D];
+  {
+    const bf16* qp = qkv + q_tok * p.ldq + head * D;
+    if (D == 4) { float t[4]; load4(qp, t);
+#pragma unroll
+      for (int d = 0; d < 4; ++d) q[d] = t[d] * p.qscale;
+    } else {
+#pragma unroll
+      for (int d8 = 0; d8 < D / 8; ++d8) { float t[8]; load8(qp + d8 * 8, t);
+#pragma unroll
+        for (int d = 0; d < 8; ++d) q[d8 * 8 + d] = t[d] * p.qscale; }
+    }
+  }
+  float m = -CUDART_INF_F, l = 0.f, acc[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) acc[d] = 0.f;
+  for (int j = lane; j < N; j += 32) {
+    const int64_t tok = token_of<false>(p, row, j, v);
+    float kk[D], vv[D];
+    const bf16* kp = qkv + tok * p.ldq + p.C + head * D;
+    const bf16* vp = qkv + tok * p.ldq + 2 * p.C + head * D;
+    if (D == 4) { load4(kp, *reinterpret_cast<float(*)[4]>(kk)); load4(vp, *reinterpret_cast<float(*)[4]>(vv)); }
+    else {
+#pragma unroll
+      for (int d8 = 0; d8 < D / 8; ++d8) {
+        load8(kp + d8 * 8, *reinterpret_cast<float(*)[8]>(kk + d8 * 8));
+        load8(vp + d8 * 8, *reinterpret_cast<float(*)[8]>(vv + d8 * 8));
+      }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int d = 0; d < D; ++d) s = fmaf(q[d], kk[d], s);
+    if (s > m) {
+      const float c = fast_exp2(m - s);
+      l *= c;
+#pragma unroll
+      for (int d = 0; d < D; ++d) acc[d] *= c;
+      m = s;
+    }
+    const float pw = fast_exp2(s - m);
+    l += pw;
+#pragma unroll
+    for (int d = 0; d < D; ++d) acc[d] = fmaf(pw, vv[d], acc[d]);
+  }
+  // merge the 32 partial softmax states
+  float mg = m;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mg = fmaxf(mg, __shfl_xor_sync(0xffffffffu, mg, o));
+  const float sc = (m == -CUDART_INF_F) ? 0.f : fast_exp2(m - mg);
+  l *= sc;
+#pragma unroll
+  for (int d = 0; d < D; ++d) acc[d] *= sc;
+  l = warp_sum(l);
+#pragma unroll
+  for (int d = 0; d < D; ++d) acc[d] = warp_sum(acc[d]);
+  if (lane == 0) {
+    const float inv = 1.0f / l;
+    bf16* op = (bf16*)p.out + q_tok * p.ldo + head * D;
+    if (D == 4) { float t[4] = {acc[0] * inv, acc[1] * inv, acc[2] * inv, acc[3] * inv}; store4(op, t); }
+    else {
+#pragma unroll
+      for (int d8 = 0; d8 < D / 8; ++d8) { float t[8];
+#pragma unroll
+        for (int d = 0; d < 8; ++d) t[d] = acc[d8 * 8 + d] * inv;
+        store8(op + d8 * 8, t); }
+    }
+    if (p.lse) p.lse[q_tok * p.heads + head] = mg + log2f(l);
+  }
+}
+
+int attn_simt_axial_bf16(const AttnParams& p, cudaStream_t st) {
+  const int D = p.C / p.heads;
+  const int N = p.geom == TFSWA_GEOM_TSA ? p.H : p.W;
+  const int rows = p.geom == TFSWA_GEOM_TSA ? p.B * p.W : p.B * p.H;
+  const int nq = (p.q_end ? p.q_end : N) - p.q_begin;
+  dim3 grid(rows, nq, (p.heads + 7) / 8);
+  if (D == 4) attn_rem_kernel<4><<<grid, 256, 0, st>>>(p);
+  else if (D == 8) attn_rem_kernel<8><<<grid, 256, 0, st>>>(p);
+  else if (D == 16) attn_rem_kernel<16><<<grid, 256, 0, st>>>(p);
+  else attn_rem_kernel<32><<<grid, 256, 0, st>>>(p);
+  return check_launch("attn_rem");
 }
 
 }  // namespace tfswa

@@ -24,6 +24,7 @@ struct AttnParams {
   int B, H, W, C, heads;
   int geom, ws, shift, use_shift_mask;
   int Hp, Wp, nWh, nWw;
+  int q_begin, q_end;   // axial kernels: queries [q_begin, q_end) of every sequence (q_end = 0 means the whole sequence)
   float qscale;   // head_dim^-0.5 * log2(e)
   int force_exact; // tc attention: skip the row-max bound and run the exact two-pass path (tests)
   // backward
@@ -31,6 +32,9 @@ struct AttnParams {
 };
 
 // fill the geometry-derived fields shared by forward and backward launchers
+// SIMT flash kernel on a query range (attention.cu); used by the tensor-core launcher for ragged remainders
+int attn_simt_axial_bf16(const AttnParams& p, cudaStream_t st);
+
 inline void attn_fill_geometry(AttnParams& p) {
   if (p.geom == TFSWA_GEOM_SWA) {
     p.Hp = (p.H + p.ws - 1) / p.ws * p.ws; p.Wp = (p.W + p.ws - 1) / p.ws * p.ws;

@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(TA_THREADS + 32, 2) tc_attn_axial_kernel(const
   int64_t q_tok = 0;
   uint4 qa = make_uint4(0, 0, 0, 0), qb = qa;        // my row's 16 q channels
   if (!issuer) {
-    if (q0 + r < N) { q_tok = tok_base + (int64_t)(q0 + r) * tok_stride; q_valid = true; }
+    if (q0 + r < (p.q_end ? p.q_end : N)) { q_tok = tok_base + (int64_t)(q0 + r) * tok_stride; q_valid = true; }
     if (q_valid) {
       const uint4* src = reinterpret_cast<const uint4*>((const bf16*)p.qkv + q_tok * p.ldq + quad * 16);
       qa = src[0]; qb = src[1];
@@ -502,7 +502,12 @@ extern "C" int tfswa_attn_tc_fwd(const tfswa_attn_args* a, void* stream) {
   p.force_exact = a->use_shift_mask;      // (the mask flag has no meaning for axial geometries) test hook: exact two-pass path
   const int N = a->geom == TFSWA_GEOM_TSA ? a->H : a->W;
   const int rows = a->geom == TFSWA_GEOM_TSA ? a->B * a->W : a->B * a->H;
-  dim3 grid(rows, (N + TA_QT - 1) / TA_QT, a->C / 16);
+  // Ragged remainder: the MMA needs 128-query tiles; when the last tile would hold only a few queries (1025 = 8*128 + 1,
+  // 517 = 4*128 + 5) those queries go to the SIMT flash kernel instead of a 128-row tile that is >75 % padding.
+  const int rem = N % TA_QT;
+  const int q_tc = (N >= TA_QT && rem > 0 && rem < 32) ? N - rem : N;
+  p.q_begin = 0; p.q_end = q_tc;
+  dim3 grid(rows, (q_tc + TA_QT - 1) / TA_QT, a->C / 16);
   TFSWA_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "attn_tc: sequence too long");
   cudaStream_t st = (cudaStream_t)stream;
   static bool attr_set = false;
@@ -514,5 +519,12 @@ extern "C" int tfswa_attn_tc_fwd(const tfswa_attn_args* a, void* stream) {
   }
   if (D == 4) tc_attn_axial_kernel<4><<<grid, TA_THREADS + 32, TA_SMEM, st>>>(p);
   else tc_attn_axial_kernel<8><<<grid, TA_THREADS + 32, TA_SMEM, st>>>(p);
+  if (q_tc < N) {
+    int rc = check_launch("attn_tc");
+    if (rc) return rc;
+    AttnParams ps = p;
+    ps.q_begin = q_tc; ps.q_end = 0;
+    return attn_simt_axial_bf16(ps, st);
+  }
   return check_launch("attn_tc");
 }
