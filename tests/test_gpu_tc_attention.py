@@ -31,6 +31,7 @@ def _ref(qkv, B, H, W, C, heads, geom):
     (1, 1025, 2, 32, 0), (1, 2, 517, 32, 1),         # the C3 stage-1 sequence lengths
     (1, 64, 4, 64, 0), (2, 4, 258, 64, 1),           # head_dim 8
     (1, 512, 2, 64, 0), (1, 128, 3, 32, 0), (1, 2, 33, 64, 1),
+    (1, 256, 3, 128, 0), (2, 3, 200, 128, 1), (1, 140, 2, 128, 0), (1, 2, 300, 128, 1),   # head_dim 16 (one head per CTA)
 ])
 def test_tc_attention_matches_simt_and_reference(B, H, W, C, geom):
     from tfswa_unet_b200 import ops
@@ -60,7 +61,7 @@ def test_tc_attention_matches_simt_and_reference(B, H, W, C, geom):
     assert float((lse_tc - lse_s).abs().max()) <= 3e-2, "log-sum-exp mismatch"
 
 
-@pytest.mark.parametrize("B,H,W,C,geom", [(1, 300, 2, 32, 0), (1, 2, 517, 32, 1), (1, 3, 200, 64, 1)])
+@pytest.mark.parametrize("B,H,W,C,geom", [(1, 300, 2, 32, 0), (1, 2, 517, 32, 1), (1, 3, 200, 64, 1), (1, 2, 260, 128, 1)])
 def test_tc_attention_exact_two_pass_path(B, H, W, C, geom):
     """the in-kernel fallback (exact row maxima) selected explicitly must agree with the bounded fast path"""
     from tfswa_unet_b200 import ops

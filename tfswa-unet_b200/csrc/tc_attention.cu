@@ -38,9 +38,10 @@ constexpr uint32_t TA_O_COL = 128;         // O accumulators live in columns [12
 
 constexpr int TA_QS = 0;                   // Q operand, 128 rows x 32 B
 constexpr int TA_KS = 4096;                // 2 x 8 KB expanded-K operand (pass 1: 256 rows, pass 2: 128 rows)
-constexpr int TA_VS = TA_KS + 2 * 8192;    // 3 x 4 KB V' operands
-constexpr int TA_PS = TA_VS + 3 * 4096;    // 2 x 32 KB P operands
-constexpr int TA_SMEM = TA_PS + 2 * 32768; // 98304
+constexpr int TA_VS = TA_KS + 2 * 8192;    // 3 V' operand buffers of vs_bytes<D>() each, then 2 x 32 KB P operands
+template <int D> __host__ __device__ constexpr int vs_bytes() { return D == 16 ? 8192 : 4096; }
+template <int D> __host__ __device__ constexpr int ps_off() { return TA_VS + 3 * vs_bytes<D>(); }
+template <int D> __host__ __device__ constexpr int smem_bytes() { return ps_off<D>() + 2 * 32768; }   // 96 KB (d=4,8) / 108 KB (d=16)
 
 __device__ __forceinline__ uint32_t ex2_bf16x2(uint32_t x) {
   uint32_t y;
@@ -74,7 +75,8 @@ __device__ __forceinline__ KvRegs load_kv(const AttnParams& p, int64_t tok_base,
       const int64_t tok = tok_base + (int64_t)(k0 + j) * tok_stride;
       const bf16* src = (const bf16*)p.qkv + tok * p.ldq + 2 * p.C + quad * 16 + h * D;
       if (D == 4) { const uint2 t = *reinterpret_cast<const uint2*>(src); r.a.x = t.x; r.a.y = t.y; }
-      else r.a = *reinterpret_cast<const uint4*>(src);
+      else if (D == 8) r.a = *reinterpret_cast<const uint4*>(src);
+      else { r.a = reinterpret_cast<const uint4*>(src)[0]; r.b = reinterpret_cast<const uint4*>(src)[1]; }
       r.present = true;
     }
   }
@@ -94,12 +96,15 @@ __device__ __forceinline__ void store_k(const KvRegs& kv, uint8_t* ks, int tid) 
       const int n = h * KT + j;
       *reinterpret_cast<uint2*>(ks + (n >> 3) * 256 + (h >> 1) * 128 + (n & 7) * 16 + (h & 1) * 8) = parts[h];
     }
-  } else {
+  } else if (D == 8) {
 #pragma unroll
     for (int h = 0; h < HPQ; ++h) {
       const int n = h * KT + j;
       *reinterpret_cast<uint4*>(ks + (n >> 3) * 256 + h * 128 + (n & 7) * 16) = h ? kv.b : kv.a;
     }
+  } else {                                           // d = 16: one head fills the 16 K-slots, no expansion
+    *reinterpret_cast<uint4*>(ks + (j >> 3) * 256 + (j & 7) * 16) = kv.a;
+    *reinterpret_cast<uint4*>(ks + (j >> 3) * 256 + 128 + (j & 7) * 16) = kv.b;
   }
 }
 
@@ -108,15 +113,16 @@ __device__ __forceinline__ void store_k(const KvRegs& kv, uint8_t* ks, int tid) 
 template <int D, int KT>
 __device__ __forceinline__ void store_v(const KvRegs& kv, uint8_t* vs, int tid) {
   if (tid < 128) return;
+  constexpr int NV = D == 16 ? 32 : 16;
   const int idx = tid - 128, j = idx % KT, h = idx / KT;
-  const uint16_t* e = reinterpret_cast<const uint16_t*>(&kv.a);
-  constexpr int head_bytes = 16 * KT * 2, sbo = (KT / 8) * 128;
+  uint4 raw[2] = {kv.a, kv.b};
+  const uint16_t* e = reinterpret_cast<const uint16_t*>(raw);
+  constexpr int head_bytes = NV * KT * 2, sbo = (KT / 8) * 128;
   uint8_t* base = vs + h * head_bytes + (j >> 3) * 128 + (j & 7) * 2;
 #pragma unroll
-  for (int d = 0; d < D; ++d) *reinterpret_cast<uint16_t*>(base + d * 16) = e[d];
+  for (int d = 0; d < D; ++d) *reinterpret_cast<uint16_t*>(base + (d >> 3) * sbo + (d & 7) * 16) = e[d];
   const uint16_t one = kv.present ? (uint16_t)0x3F80 : (uint16_t)0;       // bf16 1.0
-  if (D == 4) *reinterpret_cast<uint16_t*>(base + 4 * 16) = one;
-  else *reinterpret_cast<uint16_t*>(base + sbo) = one;
+  *reinterpret_cast<uint16_t*>(base + (D >> 3) * sbo + (D & 7) * 16) = one;
 }
 
 __device__ __forceinline__ float ex2_f32(float x) {
@@ -150,12 +156,15 @@ constexpr int TA_POLY_EVERY = 0;                    // every TA_POLY_EVERY-th ex
 //   bar_pv[2](1) PV(t) complete: P buffer t&1 and V' buffer t%3 free  issuer commit -> softmax
 template <int D>
 __global__ void __launch_bounds__(TA_THREADS + 32, 2) tc_attn_axial_kernel(const AttnParams p) {
-  constexpr int HPQ = 16 / D;            // heads per CTA
+  constexpr int HPQ = 16 / D;            // heads per CTA (4, 2, 1)
   constexpr int KT = 128 / HPQ;          // keys per tile: one S tile = 128 TMEM columns = HPQ heads x KT keys
-  constexpr int HPT = HPQ / 2;           // heads per thread
+  constexpr int HPT = HPQ >= 2 ? HPQ / 2 : 1;   // head slots per thread (d = 16: both threads of a row share the head)
+  constexpr int NV = D == 16 ? 32 : 16;  // PV MMA N: v dims + ones column (+ zero padding)
   constexpr int P_SBO = (KT / 8) * 128;  // 8-row group stride of the P / V' operands
   constexpr int P_HEAD = 128 * KT * 2;   // bytes of one head's P tile
-  constexpr int V_HEAD = 16 * KT * 2;
+  constexpr int V_HEAD = NV * KT * 2;
+  constexpr int TA_PS = ps_off<D>();
+  constexpr int VSB = vs_bytes<D>();
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t bar_s, bar_a, bar_b[2], bar_pv[2], bar_sx[2], bar_ax[2];
   __shared__ uint32_t s_tmem;
@@ -258,7 +267,7 @@ __global__ void __launch_bounds__(TA_THREADS + 32, 2) tc_attn_axial_kernel(const
     const __nv_bfloat16* qe = reinterpret_cast<const __nv_bfloat16*>(raw);
 #pragma unroll
     for (int hh = 0; hh < HPT; ++hh) {
-      const int head = half * HPT + hh;
+      const int head = HPQ >= 2 ? half * HPT + hh : 0;
       float b = 0.f;
 #pragma unroll
       for (int d = 0; d < D; ++d) {
@@ -327,9 +336,14 @@ __global__ void __launch_bounds__(TA_THREADS + 32, 2) tc_attn_axial_kernel(const
           }
         }
       }
+      if (HPQ == 1 && !issuer) reinterpret_cast<float*>(smem + TA_PS)[half * 128 + r] = m[0];
       tc_fence_before();
       __syncthreads();                                              // every S tile consumed before the buffers are reused
       tc_fence_after();
+      if (HPQ == 1) {                                               // the two threads of a row each saw half of the keys
+        if (!issuer) { const float* ex = reinterpret_cast<const float*>(smem + TA_PS); m[0] = fmaxf(ex[r], ex[128 + r]); }
+        __syncthreads();
+      }
     }
     float mc[HPT];
 #pragma unroll
@@ -337,7 +351,7 @@ __global__ void __launch_bounds__(TA_THREADS + 32, 2) tc_attn_axial_kernel(const
 
     // =========================== P = ex2(S*c - m*c), O += P V' ===========================
     if (issuer) {
-      const uint32_t idesc_pv = umma_idesc_bf16(128, 16);
+      const uint32_t idesc_pv = umma_idesc_bf16(128, NV);
       for (int t = 0; t <= T; ++t) {
         mbar_wait(&bar_a, n_a & 1); ++n_a;                            // S(t-1) consumed, operands(t) staged
         if (t < T && lane == 0) {
@@ -350,12 +364,12 @@ __global__ void __launch_bounds__(TA_THREADS + 32, 2) tc_attn_axial_kernel(const
           mbar_wait(&bar_b[pb], n_b[pb] & 1); ++n_b[pb];              // P(u) staged
           if (lane == 0) {
             tc_fence_after();
-            const uint32_t pbase = sbase + TA_PS + pb * 32768, vbase = sbase + TA_VS + (u % 3) * 4096;
+            const uint32_t pbase = sbase + TA_PS + pb * 32768, vbase = sbase + TA_VS + (u % 3) * VSB;
 #pragma unroll
             for (int h = 0; h < HPQ; ++h) {
 #pragma unroll
               for (int kk = 0; kk < KT / 16; ++kk) {
-                umma_bf16_ss(tmem + TA_O_COL + 16 * h, umma_smem_desc_ns(pbase + h * P_HEAD + kk * 256, 128, P_SBO),
+                umma_bf16_ss(tmem + TA_O_COL + NV * h, umma_smem_desc_ns(pbase + h * P_HEAD + kk * 256, 128, P_SBO),
                              umma_smem_desc_ns(vbase + h * V_HEAD + kk * 256, 128, P_SBO), idesc_pv, (u | kk) ? 1u : 0u);
               }
             }
@@ -390,7 +404,7 @@ __global__ void __launch_bounds__(TA_THREADS + 32, 2) tc_attn_axial_kernel(const
         if (t >= 2) { mbar_wait(&bar_pv[pb], n_pv[pb] & 1); ++n_pv[pb]; }   // PV(t-2) done: Ps[pb], Vs[(t+1)%3] free
         if (t + 1 < T) {
           store_k<D, KT>(kvn, smem + TA_KS + ((t + 1) & 1) * 8192, tid);
-          store_v<D, KT>(kvn, smem + TA_VS + ((t + 1) % 3) * 4096, tid);
+          store_v<D, KT>(kvn, smem + TA_VS + ((t + 1) % 3) * VSB, tid);
           fence_async_smem();
         }
         __syncwarp();
@@ -430,50 +444,60 @@ __global__ void __launch_bounds__(TA_THREADS + 32, 2) tc_attn_axial_kernel(const
       tc_fence_after();
     }
     // ---- epilogue: O / l ----
-    uint32_t o[16 * HPT];
+    uint32_t o[32];
     bool bad = false;
     if (!issuer) {
       __syncwarp();
-      if (HPT == 2) {
-        uint32_t t32[32];
-        tmem_ld_x32(my_taddr + TA_O_COL + 32 * half, t32);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o[i % (16 * HPT)] = t32[i];
-      } else {
+      if (D == 8) {
         uint32_t t16[16];
         tmem_ld_x16(my_taddr + TA_O_COL + 16 * half, t16);
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 16; ++i) o[i] = t16[i];
+      } else {
+        tmem_ld_x32(my_taddr + TA_O_COL + (D == 4 ? 32 * half : 0), o);
+        tmem_ld_wait();
       }
       // the bound keeps every exponent <= 0; if it was so loose that a whole row underflowed (denominator ~ 0) the CTA
       // repeats the computation with the exact maximum
+      if (D == 16) bad = q_valid && !(__uint_as_float(o[16]) > 1e-30f);
+      else {
 #pragma unroll
-      for (int hh = 0; hh < HPT; ++hh) bad = bad || (q_valid && !(__uint_as_float(o[hh * 16 + D]) > 1e-30f));
+        for (int hh = 0; hh < HPT; ++hh) bad = bad || (q_valid && !(__uint_as_float(o[hh * 16 + D]) > 1e-30f));
+      }
     }
     tc_fence_before();
     const bool redo = attempt == 0 && !p.force_exact && __syncthreads_or(bad);
     if (redo) continue;
     if (!issuer && q_valid) {
-#pragma unroll
-      for (int hh = 0; hh < HPT; ++hh) {
-        const int head = half * HPT + hh;            // head within the quad
-        const float l = __uint_as_float(o[hh * 16 + D]);
+      if (D == 16) {                                 // both threads of the row hold the same 32 columns: split the 16 dims
+        const float l = __uint_as_float(o[16]);
         const float inv = 1.0f / l;
-        bf16* op = (bf16*)p.out + q_tok * p.ldo + quad * 16 + head * D;
-        if (D == 4) {
-          float v[4];
+        float v[8];
 #pragma unroll
-          for (int d = 0; d < 4; ++d) v[d] = __uint_as_float(o[hh * 16 + d]) * inv;
-          store4(op, v);
-        } else {
-          float v[8];
+        for (int d = 0; d < 8; ++d) v[d] = __uint_as_float(half ? o[8 + d] : o[d]) * inv;
+        store8((bf16*)p.out + q_tok * p.ldo + quad * 16 + half * 8, v);
+        if (p.lse && half == 0) p.lse[q_tok * p.heads + quad] = mc[0] + log2f(l);
+      } else {
 #pragma unroll
-          for (int d = 0; d < 8; ++d) v[d] = __uint_as_float(o[hh * 16 + d]) * inv;
-          store8(op, v);
+        for (int hh = 0; hh < HPT; ++hh) {
+          const int head = half * HPT + hh;          // head within the quad
+          const float l = __uint_as_float(o[hh * 16 + D]);
+          const float inv = 1.0f / l;
+          bf16* op = (bf16*)p.out + q_tok * p.ldo + quad * 16 + head * D;
+          if (D == 4) {
+            float v[4];
+#pragma unroll
+            for (int d = 0; d < 4; ++d) v[d] = __uint_as_float(o[hh * 16 + d]) * inv;
+            store4(op, v);
+          } else {
+            float v[8];
+#pragma unroll
+            for (int d = 0; d < 8; ++d) v[d] = __uint_as_float(o[hh * 16 + d]) * inv;
+            store8(op, v);
+          }
+          if (p.lse) p.lse[q_tok * p.heads + quad * HPQ + head] = mc[hh] + log2f(l);
         }
-        if (p.lse) p.lse[q_tok * p.heads + quad * HPQ + head] = mc[hh] + log2f(l);
       }
     }
     break;
@@ -493,7 +517,7 @@ extern "C" int tfswa_attn_tc_fwd(const tfswa_attn_args* a, void* stream) {
   TFSWA_REQUIRE(a->geom == TFSWA_GEOM_TSA || a->geom == TFSWA_GEOM_FSA, "attn_tc: axial geometries only (windows use tfswa_attn_fwd)");
   TFSWA_REQUIRE(a->B > 0 && a->H > 0 && a->W > 0 && a->heads > 0 && a->C % a->heads == 0 && a->C % 16 == 0, "attn_tc: bad shape");
   const int D = a->C / a->heads;
-  TFSWA_REQUIRE(D == 4 || D == 8, "attn_tc: head_dim %d not in {4,8} (use tfswa_attn_fwd)", D);
+  TFSWA_REQUIRE(D == 4 || D == 8 || D == 16, "attn_tc: head_dim %d not in {4,8,16} (use tfswa_attn_fwd)", D);
   TFSWA_REQUIRE(a->ldq % 8 == 0 && a->ldo % 4 == 0 && (((uintptr_t)a->qkv) & 15) == 0, "attn_tc: alignment");
   AttnParams p = {};
   p.qkv = a->qkv; p.ldq = a->ldq; p.out = a->out; p.ldo = a->ldo; p.lse = a->lse;
@@ -512,13 +536,16 @@ extern "C" int tfswa_attn_tc_fwd(const tfswa_attn_args* a, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e1 = cudaFuncSetAttribute(tc_attn_axial_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TA_SMEM);
-    cudaError_t e2 = cudaFuncSetAttribute(tc_attn_axial_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, TA_SMEM);
+    cudaError_t e1 = cudaFuncSetAttribute(tc_attn_axial_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<4>());
+    cudaError_t e2 = cudaFuncSetAttribute(tc_attn_axial_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<8>());
+    if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(tc_attn_axial_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<16>());
+    cudaFuncSetAttribute(tc_attn_axial_kernel<16>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     if (e1 != cudaSuccess || e2 != cudaSuccess) { set_error("attn_tc: cudaFuncSetAttribute failed"); return TFSWA_ECUDA; }
     attr_set = true;
   }
-  if (D == 4) tc_attn_axial_kernel<4><<<grid, TA_THREADS + 32, TA_SMEM, st>>>(p);
-  else tc_attn_axial_kernel<8><<<grid, TA_THREADS + 32, TA_SMEM, st>>>(p);
+  if (D == 4) tc_attn_axial_kernel<4><<<grid, TA_THREADS + 32, smem_bytes<4>(), st>>>(p);
+  else if (D == 8) tc_attn_axial_kernel<8><<<grid, TA_THREADS + 32, smem_bytes<8>(), st>>>(p);
+  else tc_attn_axial_kernel<16><<<grid, TA_THREADS + 32, smem_bytes<16>(), st>>>(p);
   if (q_tc < N) {
     int rc = check_launch("attn_tc");
     if (rc) return rc;

@@ -192,13 +192,15 @@ def attention(qkv: Tensor, out: Tensor, B: int, H: int, W: int, C_: int, heads: 
     a.B, a.H, a.W, a.C, a.heads = B, H, W, C_, heads
     a.geom, a.ws, a.shift, a.use_shift_mask, a.dtype = geom, ws, shift, int(use_shift_mask), _dt(qkv)
     d = C_ // heads
-    tc = USE_TC_ATTENTION and qkv.dtype == torch.bfloat16 and geom != L.GEOM_SWA and d in (4, 8) and heads * d == C_
+    tc = USE_TC_ATTENTION and qkv.dtype == torch.bfloat16 and geom != L.GEOM_SWA and d in (4, 8, 16) and heads * d == C_
     if tc:
         # the tensor-core kernel works on 128-query x (128*d/16)-key tiles; short sequences that fill them badly
         # (e.g. 129 tokens -> 25 % useful work) stay on the SIMT kernel, which has no padding
         n = H if geom == L.GEOM_TSA else W
         kt = 128 * d // 16
-        fill = (n / (-(-n // 128) * 128)) * (n / (-(-n // kt) * kt))
+        rem = n % 128
+        nq = n - rem if (n >= 128 and 0 < rem < 32) else n       # a short remainder goes to the key-split warp kernel
+        fill = (nq / (-(-nq // 128) * 128)) * (n / (-(-n // kt) * kt))
         tc = fill >= 0.4
     _call("tfswa_attn_tc_fwd" if tc else "tfswa_attn_fwd", C.byref(a), _stream(),
           tag=f"{'attn_tc' if tc else 'attn'}[{('tsa', 'fsa', 'swa')[geom]},d={d}]",
