@@ -144,7 +144,7 @@ __device__ __forceinline__ float ex2_poly(float x) {
   p = fmaf(p, r, 0.9999280572f);
   return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
 }
-constexpr int TA_POLY_EVERY = 0;                    // every TA_POLY_EVERY-th exponential goes to ex2_poly (0 = never)
+constexpr int TA_POLY_EVERY = 4;                    // every TA_POLY_EVERY-th exponential goes to ex2_poly (0 = never)
 
 // Roles: warps 0-7 ("softmax", 256 threads) own one query row per thread pair, stage the K / V' operands of the next
 // tile cooperatively and turn S into P; warp 8 ("issuer") does nothing but wait on mbarriers and issue tcgen05.mma,
@@ -425,7 +425,7 @@ __global__ void __launch_bounds__(TA_THREADS + 32, 2) tc_attn_axial_kernel(const
           for (int i = 0; i < 16; ++i) {
             const float x0 = fmaf(__uint_as_float(s[ch * 32 + 2 * i]), c, -mcc);
             const float x1 = fmaf(__uint_as_float(s[ch * 32 + 2 * i + 1]), c, -mcc);
-            const float e0 = ex2_f32(x0);
+            const float e0 = (TA_POLY_EVERY > 0 && ((2 * i) % TA_POLY_EVERY) == TA_POLY_EVERY - 1) ? ex2_poly(x0) : ex2_f32(x0);
             const float e1 = (TA_POLY_EVERY > 0 && ((2 * i + 1) % TA_POLY_EVERY) == TA_POLY_EVERY - 1) ? ex2_poly(x1) : ex2_f32(x1);
             pk[i] = pack_bf16x2(e0, e1);
           }
