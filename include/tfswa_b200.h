@@ -117,6 +117,11 @@ typedef struct {
 } tfswa_conv_args;
 int tfswa_conv_fwd(const tfswa_conv_args* a, void* stream);
 
+/* Same contract on the tcgen05 tensor cores (bf16, eval-mode epilogues only: no pre / col_stats): the A operand is
+ * gathered by producer warps into the UMMA swizzle pattern, the weight tiles come by TMA.  w_bf16: the weights of
+ * tfswa_conv_args.w cast to bf16 (same layout). */
+int tfswa_conv_tc_fwd(const tfswa_conv_args* a, const void* w_bf16, void* stream);
+
 /* stem: Conv2d(Cin,Cout,7,p=3) on the NCHW fp32 network input -> NHWC act (tfswa_unet.py:58-62).
  * w: (Cout, Cin, 7, 7) fp32 in nn.Conv2d layout. */
 int tfswa_stem_fwd(const float* x_nchw, const float* w, const float* bias, void* y, void* pre, float* col_stats,

@@ -1,0 +1,42 @@
+"""GPU (-m gpu): tcgen05 implicit-GEMM convolutions against the fp32-accumulate SIMT kernel on the same bf16 inputs and
+against torch fp32 conv2d / conv_transpose2d."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import seeded
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("kind,B,Cin,Cout,H,W,gelu", [
+    ("conv3", 2, 32, 32, 37, 21, True), ("conv3", 1, 32, 32, 130, 65, False),
+    ("down", 2, 32, 64, 37, 21, True), ("down", 1, 64, 128, 66, 34, True), ("down", 1, 128, 256, 32, 17, True),
+    ("up", 2, 64, 32, 18, 10, True), ("up", 1, 128, 64, 33, 16, True), ("up", 1, 256, 128, 16, 8, False),
+])
+def test_tc_conv_matches_reference(kind, B, Cin, Cout, H, W, gelu):
+    from tfswa_unet_b200 import ops, _lib as L
+    from tfswa_unet_b200.autograd import conv_layout
+    x = seeded((B, Cin, H, W), 1).cuda().to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    k = 3 if kind == "conv3" else 4
+    w = (seeded((Cout, Cin, k, k), 2) / (Cin * k * k) ** 0.5).cuda().to(torch.bfloat16).float()      # Cout-first OIHW
+    b = seeded((Cout,), 3, 0.1).cuda()
+    if kind == "conv3":
+        ref, out_hw = F.conv2d(x.float(), w, b, padding=1), (H, W)
+    elif kind == "down":
+        ref = F.conv2d(x.float(), w, b, stride=2, padding=1)
+        out_hw = tuple(ref.shape[2:])
+    else:
+        ref = F.conv_transpose2d(x.float(), w.permute(1, 0, 2, 3), b, stride=2, padding=1)
+        out_hw = tuple(ref.shape[2:])
+    if gelu:
+        ref = F.gelu(ref)
+    wl = conv_layout(w, kind)
+    kid = {"conv3": 0, "down": 1, "up": 2}[kind]
+    y = ops.conv_tc(x, wl.to(torch.bfloat16).contiguous(), b, kid, out_hw, epilogue=L.EPI_GELU if gelu else 0)
+    y2 = ops.conv(x, wl, b, kid, out_hw, epilogue=L.EPI_GELU if gelu else 0)
+    torch.cuda.synchronize()
+    scale = float(ref.abs().max())
+    assert y.shape == ref.shape
+    assert float((y.float() - ref).abs().max()) <= 1e-2 * scale + 1e-3
+    assert float((y.float() - y2.float()).abs().max()) <= 1e-2 * scale + 1e-3

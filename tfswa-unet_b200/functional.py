@@ -52,6 +52,20 @@ class LinW:
         return self._tc
 
 
+_BF16_CACHE = {}
+
+
+def _bf16_of(w: Tensor) -> Tensor:
+    """bf16 copy of a prepared (cached, immutable) weight tensor, keyed by storage + version"""
+    key = (w.data_ptr(), w._version, tuple(w.shape))
+    hit = _BF16_CACHE.get(key)
+    if hit is None:
+        if len(_BF16_CACHE) > 256:
+            _BF16_CACHE.clear()
+        hit = _BF16_CACHE[key] = w.detach().to(torch.bfloat16).contiguous()
+    return hit
+
+
 USE_TC = True   # tcgen05 path for bf16 activations (set False to force the SIMT engine, e.g. for A/B tests)
 
 
@@ -141,6 +155,9 @@ def conv(x: Tensor, w_oihw: Tensor, wl: Tensor, b: Tensor, kind: str, out_hw, dt
     if _needs_grad(x, w_oihw, b):
         from .autograd import ConvFn
         return ConvFn.apply(x, w_oihw, b, kind, tuple(out_hw), dtype, epilogue, want_col_stats)
+    if (USE_TC and kind != "stem" and not want_col_stats and x.dtype == torch.bfloat16 and x.shape[1] % 32 == 0
+            and b.shape[0] % 16 == 0 and b.shape[0] <= 256):
+        return ops.conv_tc(x, _bf16_of(wl), b, _KIND[kind], out_hw, epilogue=epilogue)
     stats = torch.zeros((2, b.shape[0]), dtype=torch.float32, device=x.device) if want_col_stats else None
     if kind == "stem":
         y = ops.stem(x, wl, b, dtype, epilogue=epilogue, col_stats=stats)

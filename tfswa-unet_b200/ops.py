@@ -236,6 +236,27 @@ def conv(x: Tensor, w: Tensor, bias: Tensor, kind: int, out_hw: Tuple[int, int],
     return (y, pre) if save_pre else y
 
 
+def conv_tc(x: Tensor, w_bf16: Tensor, bias: Tensor, kind: int, out_hw: Tuple[int, int], *, epilogue: int = 0) -> Tensor:
+    """tcgen05 version of :func:`conv` (bf16, no pre / col_stats); w_bf16 = kernel-layout weights cast to bf16."""
+    _cuda(x, w_bf16)
+    B, Cin, Hin, Win = x.shape
+    Hout, Wout = out_hw
+    Cout = bias.shape[0]
+    if x.dtype != torch.bfloat16 or w_bf16.dtype != torch.bfloat16 or not w_bf16.is_contiguous():
+        raise TypeError("conv_tc: bf16 activations and contiguous bf16 weights required")
+    _f32c(bias)
+    y = torch.empty((B, Cout, Hout, Wout), dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
+    a = L.ConvArgs()
+    a.x, a.y, a.bias = x.data_ptr(), y.data_ptr(), bias.data_ptr()
+    a.B, a.Hin, a.Win, a.Cin, a.Hout, a.Wout, a.Cout = B, Hin, Win, Cin, Hout, Wout, Cout
+    a.kind, a.epilogue, a.dtype = kind, epilogue, L.BF16
+    taps = (9, 16, 16)[kind]
+    _call("tfswa_conv_tc_fwd", C.byref(a), w_bf16.data_ptr(), _stream(), tag=f"conv_tc[kind={kind},Cin={Cin},Cout={Cout}]",
+          work={"flops": 2 * B * Hout * Wout * Cout * Cin * (taps if kind != 2 else 4),
+                "bytes": 2 * (x.numel() + y.numel())})
+    return y
+
+
 def stem(x_nchw: Tensor, w: Tensor, bias: Tensor, dtype: torch.dtype, *, epilogue: int = 0, save_pre: bool = False,
          col_stats: Optional[Tensor] = None):
     _cuda(x_nchw, w)
