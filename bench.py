@@ -292,6 +292,15 @@ def main():
         achieved = dom["bytes"] / (dom["ms"] / 1e3) / 1e9
         peak = peaks["hbm_gbs"]
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak}
+    if dom_name in ("attn", "attn_tc"):
+        # attention at head_dim 4..16 is bound by exponentials, not by MMA issue or HBM: report the
+        # exponential rate against MUFU.EX2 at 16 results/clk/SM next to the (honestly tiny) tensor fraction
+        exps = sum(k["exps"] for t, k in kern.items() if t.split("[")[0] == dom_name)
+        mufu_peak = 16 * 148 * (clocks["sm_mhz"] or 1965.0) * 1e6 if clocks else 16 * 148 * 1.965e9
+        roof["exp_rate"] = {"achieved_exps_per_s": exps / (dom["ms"] / 1e3), "mufu_peak_exps_per_s": mufu_peak,
+                            "frac": exps / (dom["ms"] / 1e3) / mufu_peak,
+                            "note": "algorithmic exps (no tile padding); a fraction of the exponentials is evaluated "
+                                    "by a polynomial on the FMA pipe, so frac may exceed the MUFU share"}
     roof.update({"traffic": prof.get(dom_name, {}).get("dram_bytes_per_launch"), "kernel": dom_name,
                  "launches_per_step": dom["launches"] / args.steps, "avg_launch_ms": dom["ms"] / max(1, dom["launches"]),
                  "share_of_step": dom["ms"] / total_kernel_ms, "peak_source": peaks["source"],

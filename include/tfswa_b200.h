@@ -102,7 +102,10 @@ int tfswa_attn_fwd(const tfswa_attn_args* a, void* stream);
 /* Same contract for the axial geometries (TSA / FSA) at head_dim 4 and 8, bf16, on the tcgen05 tensor cores:
  * QK^T and PV as tcgen05.mma with TMEM accumulators, heads packed along the MMA K dimension, exact two-pass softmax
  * with ex2.approx.ftz.bf16x2, the denominator accumulated by the tensor core through a ones column appended to V. */
-int tfswa_attn_tc_fwd(const tfswa_attn_args* a, void* stream);
+/* scratch: caller-owned device buffer of tfswa_attn_tc_scratch_bytes(a) bytes (per-sequence k extrema for the softmax
+ * shift bound); contents are dead after the call. */
+int64_t tfswa_attn_tc_scratch_bytes(const tfswa_attn_args* a);
+int tfswa_attn_tc_fwd(const tfswa_attn_args* a, void* scratch, int64_t scratch_bytes, void* stream);
 
 /* ---- convolutions (implicit GEMM over NHWC) ---------------------------------------------------
  * kind: 0 = 3x3 s1 p1 (output_head.0, tfswa_unet.py:140), 1 = 4x4 s2 p1 (DownsampleBlock, blocks.py:157),

@@ -179,11 +179,82 @@ static int launch_attn(const AttnParams& p, cudaStream_t st) {
 }
 
 // Ragged-remainder kernel for the tensor-core path: a handful of queries per sequence (N mod 128 < 32).  One warp per
-// (sequence, query, head); the 32 lanes split the KEYS (lane l takes keys l, l+32, ...), each keeps its own online
-// softmax state and the warp merges them with shuffles - so even a single leftover query is spread over 32 lanes
-// instead of running a 1000-step dependent chain in one thread.
+// (sequence, query, 32-channel slab); the 32 lanes split the KEYS (lane l takes keys l, l+32, ...) and each lane
+// handles all 32/D heads of the slab from one 64-byte k row and one 64-byte v row (full-sector loads), keeps its own
+// online-softmax state per head, and the warp merges the 32 partial states with shuffles.
 template <int D>
 __global__ void __launch_bounds__(256) attn_rem_kernel(const AttnParams p) {
+  constexpr int HG = 32 / D;
+  const int row = blockIdx.x, lane = threadIdx.x & 31;
+  const int N = p.geom == TFSWA_GEOM_TSA ? p.H : p.W;
+  const int qn = p.q_begin + blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (qn >= (p.q_end ? p.q_end : N)) return;
+  const int ch0 = blockIdx.z * 32;
+  const bf16* qkv = (const bf16*)p.qkv;
+  bool vld; const int64_t q_tok = token_of<false>(p, row, qn, vld);
+  float q[32];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { float t[8]; load8(qkv + q_tok * p.ldq + ch0 + i * 8, t);
+#pragma unroll
+    for (int d = 0; d < 8; ++d) q[i * 8 + d] = t[d] * p.qscale; }
+  float m[HG], l[HG], acc[32];
+#pragma unroll
+  for (int h = 0; h < HG; ++h) { m[h] = -CUDART_INF_F; l[h] = 0.f; }
+#pragma unroll
+  for (int d = 0; d < 32; ++d) acc[d] = 0.f;
+  for (int j = lane; j < N; j += 32) {
+    const int64_t tok = token_of<false>(p, row, j, vld);
+    float kk[32], vv[32];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      load8(qkv + tok * p.ldq + p.C + ch0 + i * 8, *reinterpret_cast<float(*)[8]>(kk + i * 8));
+      load8(qkv + tok * p.ldq + 2 * p.C + ch0 + i * 8, *reinterpret_cast<float(*)[8]>(vv + i * 8));
+    }
+#pragma unroll
+    for (int h = 0; h < HG; ++h) {
+      float s = 0.f;
+#pragma unroll
+      for (int d = 0; d < D; ++d) s = fmaf(q[h * D + d], kk[h * D + d], s);
+      if (s > m[h]) {
+        const float c = fast_exp2(m[h] - s);
+        l[h] *= c;
+#pragma unroll
+        for (int d = 0; d < D; ++d) acc[h * D + d] *= c;
+        m[h] = s;
+      }
+      const float pw = fast_exp2(s - m[h]);
+      l[h] += pw;
+#pragma unroll
+      for (int d = 0; d < D; ++d) acc[h * D + d] = fmaf(pw, vv[h * D + d], acc[h * D + d]);
+    }
+  }
+  // merge the 32 partial softmax states of every head
+  float out[32], lse[HG];
+#pragma unroll
+  for (int h = 0; h < HG; ++h) {
+    float mg = m[h];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mg = fmaxf(mg, __shfl_xor_sync(0xffffffffu, mg, o));
+    const float sc = (m[h] == -CUDART_INF_F) ? 0.f : fast_exp2(m[h] - mg);
+    const float lt = warp_sum(l[h] * sc);
+    const float inv = 1.0f / lt;
+#pragma unroll
+    for (int d = 0; d < D; ++d) out[h * D + d] = warp_sum(acc[h * D + d] * sc) * inv;
+    lse[h] = mg + log2f(lt);
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) store8((bf16*)p.out + q_tok * p.ldo + ch0 + i * 8, *reinterpret_cast<float(*)[8]>(out + i * 8));
+    if (p.lse) {
+#pragma unroll
+      for (int h = 0; h < HG; ++h) p.lse[q_tok * p.heads + blockIdx.z * HG + h] = lse[h];
+    }
+  }
+}
+
+// variant with one warp per (sequence, query, head): more warps in flight when only one or two queries are left over
+template <int D>
+__global__ void __launch_bounds__(256) attn_rem_head_kernel(const AttnParams p) {
   const int row = blockIdx.x, qn = p.q_begin + blockIdx.y;
   const int lane = threadIdx.x & 31;
   const int head = blockIdx.z * 8 + (threadIdx.x >> 5);
@@ -266,7 +337,15 @@ int attn_simt_axial_bf16(const AttnParams& p, cudaStream_t st) {
   const int N = p.geom == TFSWA_GEOM_TSA ? p.H : p.W;
   const int rows = p.geom == TFSWA_GEOM_TSA ? p.B * p.W : p.B * p.H;
   const int nq = (p.q_end ? p.q_end : N) - p.q_begin;
-  dim3 grid(rows, nq, (p.heads + 7) / 8);
+  if (nq <= 2) {
+    dim3 gridh(rows, nq, (p.heads + 7) / 8);
+    if (D == 4) attn_rem_head_kernel<4><<<gridh, 256, 0, st>>>(p);
+    else if (D == 8) attn_rem_head_kernel<8><<<gridh, 256, 0, st>>>(p);
+    else if (D == 16) attn_rem_head_kernel<16><<<gridh, 256, 0, st>>>(p);
+    else attn_rem_head_kernel<32><<<gridh, 256, 0, st>>>(p);
+    return check_launch("attn_rem");
+  }
+  dim3 grid(rows, (nq + 7) / 8, p.C / 32);
   if (D == 4) attn_rem_kernel<4><<<grid, 256, 0, st>>>(p);
   else if (D == 8) attn_rem_kernel<8><<<grid, 256, 0, st>>>(p);
   else if (D == 16) attn_rem_kernel<16><<<grid, 256, 0, st>>>(p);

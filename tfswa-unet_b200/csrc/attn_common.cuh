@@ -26,6 +26,7 @@ struct AttnParams {
   int Hp, Wp, nWh, nWw;
   int q_begin, q_end;   // axial kernels: queries [q_begin, q_end) of every sequence (q_end = 0 means the whole sequence)
   float qscale;   // head_dim^-0.5 * log2(e)
+  float* kext;     // tc attention: per-sequence per-channel min/max of k (scratch, (rows, 2, C) fp32)
   int force_exact; // tc attention: skip the row-max bound and run the exact two-pass path (tests)
   // backward
   const void* dout; const void* o; void* dqkv; float* dsum; float* dpad; float scale;

@@ -146,6 +146,41 @@ __device__ __forceinline__ float ex2_poly(float x) {
 }
 constexpr int TA_POLY_EVERY = 4;                    // every TA_POLY_EVERY-th exponential goes to ex2_poly (0 = never)
 
+// Per-channel extrema of k over every sequence: kext[row][0][c] = min_j k[j][c], kext[row][1][c] = max_j k[j][c].
+// One CTA per sequence; thread t owns 8 channels (one 16-byte load per key) of key lane t / (C/8).
+__global__ void __launch_bounds__(256) attn_kext_kernel(const AttnParams p) {
+  __shared__ float red[2][256][9];
+  const int row = blockIdx.x, tid = threadIdx.x;
+  const int groups = p.C / 8, g = tid % groups, kl = tid / groups, KL = 256 / groups;
+  const int N = p.geom == TFSWA_GEOM_TSA ? p.H : p.W;
+  int64_t tok_base, tok_stride;
+  if (p.geom == TFSWA_GEOM_TSA) { const int b = row / p.W; tok_base = (int64_t)b * p.H * p.W + (row - b * p.W); tok_stride = p.W; }
+  else { tok_base = (int64_t)row * p.W; tok_stride = 1; }
+  float mn[8], mx[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { mn[i] = CUDART_INF_F; mx[i] = -CUDART_INF_F; }
+  if (kl < KL) {
+    for (int j = kl; j < N; j += KL) {
+      float v[8];
+      load8((const bf16*)p.qkv + (tok_base + (int64_t)j * tok_stride) * p.ldq + p.C + g * 8, v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { mn[i] = fminf(mn[i], v[i]); mx[i] = fmaxf(mx[i], v[i]); }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { red[0][tid][i] = mn[i]; red[1][tid][i] = mx[i]; }
+  __syncthreads();
+  if (tid < 2 * p.C) {                              // thread -> (min|max, channel): reduce over the key lanes
+    const int which = tid / p.C, c = tid % p.C, gg = c / 8, i = c % 8;
+    float v = which ? -CUDART_INF_F : CUDART_INF_F;
+    for (int k = 0; k < KL; ++k) {
+      const float o = red[which][k * groups + gg][i];
+      v = which ? fmaxf(v, o) : fminf(v, o);
+    }
+    p.kext[((int64_t)row * 2 + which) * p.C + c] = v;
+  }
+}
+
 // Roles: warps 0-7 ("softmax", 256 threads) own one query row per thread pair, stage the K / V' operands of the next
 // tile cooperatively and turn S into P; warp 8 ("issuer") does nothing but wait on mbarriers and issue tcgen05.mma,
 // so the serial descriptor/MMA issue work never sits on the critical path of a softmax warp.  There is no CTA-wide
@@ -207,45 +242,17 @@ __global__ void __launch_bounds__(TA_THREADS + 32, 2) tc_attn_axial_kernel(const
       *reinterpret_cast<uint4*>(smem + TA_QS + (r >> 3) * 256 + (r & 7) * 16) = qa;
       *reinterpret_cast<uint4*>(smem + TA_QS + (r >> 3) * 256 + 128 + (r & 7) * 16) = qb;
     }
-    // ---- per-channel extrema of k over the sequence (for the row-max upper bound) ----
-    float kmn[16], kmx[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) { kmn[i] = CUDART_INF_F; kmx[i] = -CUDART_INF_F; }
-    for (int j = tid; j < N; j += TA_THREADS) {
-      const int64_t tok = tok_base + (int64_t)j * tok_stride;
-      const uint4* src = reinterpret_cast<const uint4*>((const bf16*)p.qkv + tok * p.ldq + p.C + quad * 16);
-      uint4 raw[2] = {src[0], src[1]};
-      const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(raw);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float lo = __low2float(h2[i]), hi = __high2float(h2[i]);
-        kmn[2 * i] = fminf(kmn[2 * i], lo); kmx[2 * i] = fmaxf(kmx[2 * i], lo);
-        kmn[2 * i + 1] = fminf(kmn[2 * i + 1], hi); kmx[2 * i + 1] = fmaxf(kmx[2 * i + 1], hi);
-      }
-    }
-    float* red = reinterpret_cast<float*>(smem + TA_PS);          // [256][33] floats, P region is idle here
-#pragma unroll
-    for (int i = 0; i < 16; ++i) { red[tid * 33 + i] = kmn[i]; red[tid * 33 + 16 + i] = kmx[i]; }
   }
-  __syncthreads();                                                // zero fill + partial extrema visible
-  if (!issuer) {
-    const float* red = reinterpret_cast<const float*>(smem + TA_PS);
-#pragma unroll
-    for (int cidx = 0; cidx < 4; ++cidx) {                        // warp w reduces columns 4w..4w+3 over the 256 rows
-      const int col = warp * 4 + cidx;
-      float v = red[lane * 33 + col];
-#pragma unroll
-      for (int k = 1; k < 8; ++k) {
-        const float o = red[(lane + 32 * k) * 33 + col];
-        v = col < 16 ? fminf(v, o) : fmaxf(v, o);
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const float w = __shfl_xor_sync(0xffffffffu, v, o);
-        v = col < 16 ? fminf(v, w) : fmaxf(v, w);
-      }
-      if (lane == 0) s_kext[col >> 4][col & 15] = v;
-    }
+  // Pull this sequence's k|v rows (32 B each per quad) towards L2 now: the key loop only prefetches one tile ahead
+  // into registers, which hides an L2 hit but not an HBM miss.
+  for (int j = tid; j < 2 * N; j += TA_THREADS + 32) {
+    const int key = j >> 1;
+    const bf16* ptr = (const bf16*)p.qkv + (tok_base + (int64_t)key * tok_stride) * p.ldq + ((j & 1) ? 2 * p.C : p.C) + quad * 16;
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+  }
+  if (tid < 32) {   // per-channel extrema of k over the sequence, computed once per (sequence, channel) by attn_kext_kernel
+    const float* ke = p.kext + ((int64_t)row * 2 + (tid >> 4)) * p.C + quad * 16 + (tid & 15);
+    s_kext[tid >> 4][tid & 15] = *ke;
   }
   tc_fence_before();
   __syncthreads();
@@ -390,30 +397,27 @@ __global__ void __launch_bounds__(TA_THREADS + 32, 2) tc_attn_axial_kernel(const
         const int pb = t & 1;
         mbar_wait(&bar_s, n_s & 1); ++n_s;
         tc_fence_after();
-        uint32_t s[64];
+        uint32_t sc[2][32];                                            // my 64 scores
         __syncwarp();
-        {
-          uint32_t lo[32], hi[32];
-          tmem_ld_x32(my_taddr + half * 64, lo);
-          tmem_ld_x32(my_taddr + half * 64 + 32, hi);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) { s[i] = lo[i]; s[32 + i] = hi[i]; }
-        }
-        tc_fence_before();
+        tmem_ld_x32(my_taddr + half * 64, sc[0]);
+        tmem_ld_x32(my_taddr + half * 64 + 32, sc[1]);
+        tmem_ld_wait();
         if (t >= 2) { mbar_wait(&bar_pv[pb], n_pv[pb] & 1); ++n_pv[pb]; }   // PV(t-2) done: Ps[pb], Vs[(t+1)%3] free
         if (t + 1 < T) {
           store_k<D, KT>(kvn, smem + TA_KS + ((t + 1) & 1) * 8192, tid);
           store_v<D, KT>(kvn, smem + TA_VS + ((t + 1) % 3) * VSB, tid);
           fence_async_smem();
         }
+        tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar_a);                           // S(t) consumed + operands(t+1) staged
         kvn = load_kv<D, KT>(p, tok_base, tok_stride, (t + 2) * KT, N, quad, tid);     // global latency hides under the exponentials
         uint8_t* ps = smem + TA_PS + pb * 32768;
         if ((t + 1) * KT > N) {                      // only the last tile holds absent keys: their score 0 may exceed the bound
 #pragma unroll
-          for (int i = 0; i < 64; ++i) s[i] = __float_as_uint(fminf(__uint_as_float(s[i]), m[(i / 32 * 32) / KT]));
+          for (int ch = 0; ch < 2; ++ch)
+#pragma unroll
+            for (int i = 0; i < 32; ++i) sc[ch][i] = __float_as_uint(fminf(__uint_as_float(sc[ch][i]), m[(ch * 32) / KT]));
         }
 #pragma unroll
         for (int ch = 0; ch < 2; ++ch) {
@@ -423,8 +427,8 @@ __global__ void __launch_bounds__(TA_THREADS + 32, 2) tc_attn_axial_kernel(const
           uint32_t pk[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            const float x0 = fmaf(__uint_as_float(s[ch * 32 + 2 * i]), c, -mcc);
-            const float x1 = fmaf(__uint_as_float(s[ch * 32 + 2 * i + 1]), c, -mcc);
+            const float x0 = fmaf(__uint_as_float(sc[ch][2 * i]), c, -mcc);
+            const float x1 = fmaf(__uint_as_float(sc[ch][2 * i + 1]), c, -mcc);
             const float e0 = (TA_POLY_EVERY > 0 && ((2 * i) % TA_POLY_EVERY) == TA_POLY_EVERY - 1) ? ex2_poly(x0) : ex2_f32(x0);
             const float e1 = (TA_POLY_EVERY > 0 && ((2 * i + 1) % TA_POLY_EVERY) == TA_POLY_EVERY - 1) ? ex2_poly(x1) : ex2_f32(x1);
             pk[i] = pack_bf16x2(e0, e1);
@@ -511,7 +515,13 @@ __global__ void __launch_bounds__(TA_THREADS + 32, 2) tc_attn_axial_kernel(const
 
 using namespace tfswa;
 
-extern "C" int tfswa_attn_tc_fwd(const tfswa_attn_args* a, void* stream) {
+extern "C" int64_t tfswa_attn_tc_scratch_bytes(const tfswa_attn_args* a) {
+  if (!a) return 0;
+  const int64_t rows = a->geom == TFSWA_GEOM_TSA ? (int64_t)a->B * a->W : (int64_t)a->B * a->H;
+  return rows * 2 * a->C * (int64_t)sizeof(float);
+}
+
+extern "C" int tfswa_attn_tc_fwd(const tfswa_attn_args* a, void* scratch, int64_t scratch_bytes, void* stream) {
   TFSWA_REQUIRE(a && a->qkv && a->out, "attn_tc: null pointer");
   TFSWA_REQUIRE(a->dtype == TFSWA_BF16, "attn_tc: bf16 activations only");
   TFSWA_REQUIRE(a->geom == TFSWA_GEOM_TSA || a->geom == TFSWA_GEOM_FSA, "attn_tc: axial geometries only (windows use tfswa_attn_fwd)");
@@ -523,6 +533,9 @@ extern "C" int tfswa_attn_tc_fwd(const tfswa_attn_args* a, void* stream) {
   p.qkv = a->qkv; p.ldq = a->ldq; p.out = a->out; p.ldo = a->ldo; p.lse = a->lse;
   p.B = a->B; p.H = a->H; p.W = a->W; p.C = a->C; p.heads = a->heads; p.geom = a->geom;
   p.qscale = (float)(1.4426950408889634 / sqrt((double)D));
+  TFSWA_REQUIRE(scratch && scratch_bytes >= tfswa_attn_tc_scratch_bytes(a), "attn_tc: scratch buffer too small");
+  TFSWA_REQUIRE(a->C <= 128, "attn_tc: C=%d > 128 unsupported", a->C);
+  p.kext = (float*)scratch;
   p.force_exact = a->use_shift_mask;      // (the mask flag has no meaning for axial geometries) test hook: exact two-pass path
   const int N = a->geom == TFSWA_GEOM_TSA ? a->H : a->W;
   const int rows = a->geom == TFSWA_GEOM_TSA ? a->B * a->W : a->B * a->H;
@@ -534,6 +547,7 @@ extern "C" int tfswa_attn_tc_fwd(const tfswa_attn_args* a, void* stream) {
   dim3 grid(rows, (q_tc + TA_QT - 1) / TA_QT, a->C / 16);
   TFSWA_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "attn_tc: sequence too long");
   cudaStream_t st = (cudaStream_t)stream;
+  attn_kext_kernel<<<rows, 256, 0, st>>>(p);
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e1 = cudaFuncSetAttribute(tc_attn_axial_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<4>());

@@ -47,7 +47,7 @@ def collect_timing():
     for tag, recs in (_TIMING or {}).items():
         ms = sum(s.elapsed_time(e) for s, e, _ in recs)
         out[tag] = {"launches": len(recs), "ms": ms, "flops": sum(w.get("flops", 0) for _, _, w in recs),
-                    "bytes": sum(w.get("bytes", 0) for _, _, w in recs)}
+                    "bytes": sum(w.get("bytes", 0) for _, _, w in recs), "exps": sum(w.get("exps", 0) for _, _, w in recs)}
     return out
 
 
@@ -192,7 +192,7 @@ def attention(qkv: Tensor, out: Tensor, B: int, H: int, W: int, C_: int, heads: 
     a.B, a.H, a.W, a.C, a.heads = B, H, W, C_, heads
     a.geom, a.ws, a.shift, a.use_shift_mask, a.dtype = geom, ws, shift, int(use_shift_mask), _dt(qkv)
     d = C_ // heads
-    tc = USE_TC_ATTENTION and qkv.dtype == torch.bfloat16 and geom != L.GEOM_SWA and d in (4, 8, 16) and heads * d == C_
+    tc = USE_TC_ATTENTION and qkv.dtype == torch.bfloat16 and geom != L.GEOM_SWA and d in (4, 8, 16) and heads * d == C_ and C_ <= 128
     if tc:
         # the tensor-core kernel works on 128-query x (128*d/16)-key tiles; short sequences that fill them badly
         # (e.g. 129 tokens -> 25 % useful work) stay on the SIMT kernel, which has no padding
@@ -202,20 +202,25 @@ def attention(qkv: Tensor, out: Tensor, B: int, H: int, W: int, C_: int, heads: 
         nq = n - rem if (n >= 128 and 0 < rem < 32) else n       # a short remainder goes to the key-split warp kernel
         fill = (nq / (-(-nq // 128) * 128)) * (n / (-(-n // kt) * kt))
         tc = fill >= 0.4
-    _call("tfswa_attn_tc_fwd" if tc else "tfswa_attn_fwd", C.byref(a), _stream(),
-          tag=f"{'attn_tc' if tc else 'attn'}[{('tsa', 'fsa', 'swa')[geom]},d={d}]",
-          work=_attn_work(B, H, W, C_, geom, ws, qkv.element_size()))
+    tag = f"{'attn_tc' if tc else 'attn'}[{('tsa', 'fsa', 'swa')[geom]},d={d}]"
+    work = _attn_work(B, H, W, C_, geom, ws, qkv.element_size(), heads)
+    if tc:
+        nbytes = L.lib().tfswa_attn_tc_scratch_bytes(C.byref(a))
+        scratch = torch.empty((nbytes,), dtype=torch.uint8, device=qkv.device)
+        _call("tfswa_attn_tc_fwd", C.byref(a), scratch.data_ptr(), nbytes, _stream(), tag=tag, work=work)
+    else:
+        _call("tfswa_attn_fwd", C.byref(a), _stream(), tag=tag, work=work)
     return out
 
 
-def _attn_work(B, H, W, C_, geom, ws, esize):
+def _attn_work(B, H, W, C_, geom, ws, esize, heads=8):
     """algorithmic work of one attention launch: 4*tokens*N*C FLOPs (QK^T + PV), one exp per score element per head"""
     if geom == L.GEOM_SWA:
         Hp, Wp = -(-H // ws) * ws, -(-W // ws) * ws
         toks, N = B * Hp * Wp, ws * ws
     else:
         toks, N = B * H * W, (H if geom == L.GEOM_TSA else W)
-    return {"flops": 4 * toks * N * C_, "bytes": esize * B * H * W * 4 * C_, "exps": toks * N}
+    return {"flops": 4 * toks * N * C_, "bytes": esize * B * H * W * 4 * C_, "exps": toks * N * heads}
 
 
 def conv(x: Tensor, w: Tensor, bias: Tensor, kind: int, out_hw: Tuple[int, int], *, epilogue: int = 0,
