@@ -397,38 +397,41 @@ __global__ void __launch_bounds__(TA_THREADS + 32, 2) tc_attn_axial_kernel(const
         const int pb = t & 1;
         mbar_wait(&bar_s, n_s & 1); ++n_s;
         tc_fence_after();
-        uint32_t sc[2][32];                                            // my 64 scores
-        __syncwarp();
-        tmem_ld_x32(my_taddr + half * 64, sc[0]);
-        tmem_ld_x32(my_taddr + half * 64 + 32, sc[1]);
-        tmem_ld_wait();
+        // buffer-reuse wait and operand staging for tile t+1 first (independent of S(t))
         if (t >= 2) { mbar_wait(&bar_pv[pb], n_pv[pb] & 1); ++n_pv[pb]; }   // PV(t-2) done: Ps[pb], Vs[(t+1)%3] free
         if (t + 1 < T) {
           store_k<D, KT>(kvn, smem + TA_KS + ((t + 1) & 1) * 8192, tid);
           store_v<D, KT>(kvn, smem + TA_VS + ((t + 1) % 3) * VSB, tid);
           fence_async_smem();
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bar_a);                           // S(t) consumed + operands(t+1) staged
-        kvn = load_kv<D, KT>(p, tok_base, tok_stride, (t + 2) * KT, N, quad, tid);     // global latency hides under the exponentials
         uint8_t* ps = smem + TA_PS + pb * 32768;
-        if ((t + 1) * KT > N) {                      // only the last tile holds absent keys: their score 0 may exceed the bound
-#pragma unroll
-          for (int ch = 0; ch < 2; ++ch)
-#pragma unroll
-            for (int i = 0; i < 32; ++i) sc[ch][i] = __float_as_uint(fminf(__uint_as_float(sc[ch][i]), m[(ch * 32) / KT]));
-        }
+        const bool tail = (t + 1) * KT > N;          // only the last tile holds absent keys: their score 0 may exceed the bound
+        // my 64 scores in two halves of 32 (keeps only 32 score registers live): exp of the first half runs while
+        // nothing else of S(t) is needed; S is released to the issuer after the second TMEM load
 #pragma unroll
         for (int ch = 0; ch < 2; ++ch) {
+          uint32_t sc[32];
+          __syncwarp();
+          tmem_ld_x32(my_taddr + half * 64 + ch * 32, sc);
+          tmem_ld_wait();
+          if (ch == 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_a);                       // S(t) consumed + operands(t+1) staged
+            kvn = load_kv<D, KT>(p, tok_base, tok_stride, (t + 2) * KT, N, quad, tid);   // latency hides under the exponentials
+          }
           const int col = half * 64 + ch * 32;
           const int head = col / KT, jbase = col % KT; // head within the quad, first key of this chunk
           const float mcc = mc[(ch * 32) / KT];
+          if (tail) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) sc[i] = __float_as_uint(fminf(__uint_as_float(sc[i]), m[(ch * 32) / KT]));
+          }
           uint32_t pk[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            const float x0 = fmaf(__uint_as_float(sc[ch][2 * i]), c, -mcc);
-            const float x1 = fmaf(__uint_as_float(sc[ch][2 * i + 1]), c, -mcc);
+            const float x0 = fmaf(__uint_as_float(sc[2 * i]), c, -mcc);
+            const float x1 = fmaf(__uint_as_float(sc[2 * i + 1]), c, -mcc);
             const float e0 = (TA_POLY_EVERY > 0 && ((2 * i) % TA_POLY_EVERY) == TA_POLY_EVERY - 1) ? ex2_poly(x0) : ex2_f32(x0);
             const float e1 = (TA_POLY_EVERY > 0 && ((2 * i + 1) % TA_POLY_EVERY) == TA_POLY_EVERY - 1) ? ex2_poly(x1) : ex2_f32(x1);
             pk[i] = pack_bf16x2(e0, e1);
