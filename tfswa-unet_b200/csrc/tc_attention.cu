@@ -207,7 +207,10 @@ __global__ void __launch_bounds__(TA_THREADS + 32, 2) tc_attn_axial_kernel(const
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool issuer = warp == 8;
-  const int row = blockIdx.x, q0 = blockIdx.y * TA_QT, quad = blockIdx.z;
+  // grid.x enumerates the (query tile, quad) pairs of one sequence, grid.y the sequences: CTAs that share a
+  // sequence's k|v rows are scheduled together, so those rows come from HBM once and from L2 afterwards
+  const int nquads = p.C / 16;
+  const int row = blockIdx.y, q0 = (blockIdx.x / nquads) * TA_QT, quad = blockIdx.x % nquads;
   const int N = p.geom == TFSWA_GEOM_TSA ? p.H : p.W;
   const int quarter = warp & 3, half = (warp >> 2) & 1;
   const int r = quarter * 32 + lane;                 // my query row == my TMEM lane
@@ -547,8 +550,8 @@ extern "C" int tfswa_attn_tc_fwd(const tfswa_attn_args* a, void* scratch, int64_
   const int rem = N % TA_QT;
   const int q_tc = (N >= TA_QT && rem > 0 && rem < 32) ? N - rem : N;
   p.q_begin = 0; p.q_end = q_tc;
-  dim3 grid(rows, (q_tc + TA_QT - 1) / TA_QT, a->C / 16);
-  TFSWA_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "attn_tc: sequence too long");
+  dim3 grid(((q_tc + TA_QT - 1) / TA_QT) * (a->C / 16), rows, 1);
+  TFSWA_REQUIRE(rows <= 65535, "attn_tc: more than 65535 sequences in one launch (split the batch)");
   cudaStream_t st = (cudaStream_t)stream;
   attn_kext_kernel<<<rows, 256, 0, st>>>(p);
   static bool attr_set = false;
