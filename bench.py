@@ -270,7 +270,8 @@ def main():
     value = audio_s / (step_ms / 1e3)
     e2e_value = audio_s / (ms_e2e / args.steps / 1e3)
 
-    # ---- roofline of the dominant kernel class (largest share of the timed region) ----
+    # ---- kernel classes (C-ABI entry point) and the dominant kernel: the single (entry point, shape) tag with the
+    # largest share of the timed region; all launches of one tag have identical shapes, so "per launch" is exact ----
     total_kernel_ms = sum(k["ms"] for k in kern.values()) or 1.0
     classes = {}
     for tag, k in kern.items():
@@ -278,33 +279,35 @@ def main():
         c = classes.setdefault(cls, {"ms": 0.0, "launches": 0, "flops": 0, "bytes": 0})
         for f in c:
             c[f] += k[f]
-    dom_name, dom = max(classes.items(), key=lambda kv: kv[1]["ms"])
+    dom_name, dom = max(kern.items(), key=lambda kv: kv[1]["ms"])
+    dom_cls = dom_name.split("[")[0]
     prof = {}
     prof_path = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(prof_path):
         with open(prof_path) as f:
             prof = json.load(f)
-    if dom["flops"] > 0 and dom_name in ("linear", "linear_tc", "attn", "attn_tc", "tfswa_conv_fwd"):
-        achieved = dom["flops"] / (dom["ms"] / 1e3) / 1e12
+    avg_s = dom["ms"] / max(1, dom["launches"]) / 1e3
+    if dom["flops"] > 0 and dom_cls in ("linear", "linear_tc", "attn", "attn_tc", "conv_tc", "tfswa_conv_fwd"):
+        achieved = dom["flops"] / dom["launches"] / avg_s / 1e12
         peak = peaks["bf16_tflops_sustained"]
         roof = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak}
     else:
-        achieved = dom["bytes"] / (dom["ms"] / 1e3) / 1e9
+        achieved = dom["bytes"] / dom["launches"] / avg_s / 1e9
         peak = peaks["hbm_gbs"]
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak}
-    if dom_name in ("attn", "attn_tc"):
-        # attention at head_dim 4..16 is bound by exponentials, not by MMA issue or HBM (SURVEY 7.3.1): report the
+    if dom_cls in ("attn", "attn_tc"):
+        # attention at head_dim 4..16 is bound by exponentials, not by MMA issue or HBM (DESIGN.md 4.3): report the
         # exponential rate against MUFU.EX2 at 16 results/clk/SM next to the (honestly tiny) tensor fraction
-        exps = sum(k["exps"] for t, k in kern.items() if t.split("[")[0] == dom_name)
-        mufu_peak = 16 * 148 * (clocks["sm_mhz"] or 1965.0) * 1e6 if clocks else 16 * 148 * 1.965e9
-        roof["exp_rate"] = {"achieved_exps_per_s": exps / (dom["ms"] / 1e3), "mufu_peak_exps_per_s": mufu_peak,
-                            "frac": exps / (dom["ms"] / 1e3) / mufu_peak,
-                            "note": "algorithmic exps (no tile padding); a fraction of the exponentials is evaluated "
-                                    "by a polynomial on the FMA pipe, so frac may exceed the MUFU share"}
+        mufu_peak = 16 * 148 * ((clocks or {}).get("sm_mhz") or 1965.0) * 1e6
+        rate = dom["exps"] / dom["launches"] / avg_s
+        roof["exp_rate"] = {"achieved_exps_per_s": rate, "mufu_peak_exps_per_s": mufu_peak, "frac": rate / mufu_peak,
+                            "hbm_gbs": dom["bytes"] / dom["launches"] / avg_s / 1e9,
+                            "note": "algorithmic exps (no tile padding); one exponential in four is evaluated by a "
+                                    "polynomial on the FMA pipe, so frac is not the MUFU pipe utilisation"}
     roof.update({"traffic": prof.get(dom_name, {}).get("dram_bytes_per_launch"), "kernel": dom_name,
-                 "launches_per_step": dom["launches"] / args.steps, "avg_launch_ms": dom["ms"] / max(1, dom["launches"]),
+                 "launches_per_step": dom["launches"] / args.steps, "avg_launch_ms": avg_s * 1e3,
                  "share_of_step": dom["ms"] / total_kernel_ms, "peak_source": peaks["source"],
-                 "algorithmic_per_step": {"flops": dom["flops"] / args.steps, "bytes": dom["bytes"] / args.steps}})
+                 "algorithmic_per_launch": {"flops": dom["flops"] / dom["launches"], "bytes": dom["bytes"] / dom["launches"]}})
     breakdown = {cls: {"ms_per_step": c["ms"] / args.steps, "share": c["ms"] / total_kernel_ms,
                        "launches_per_step": c["launches"] / args.steps,
                        "tflops": (c["flops"] / (c["ms"] / 1e3) / 1e12) if c["ms"] > 0 and c["flops"] else None}

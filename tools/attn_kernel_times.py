@@ -1,3 +1,4 @@
+"""Per-kernel device times (torch profiler) of one TSA and one FSA attention call at stage-1 size, B=1."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
