@@ -313,7 +313,7 @@ def main():
                        "tflops": (c["flops"] / (c["ms"] / 1e3) / 1e12) if c["ms"] > 0 and c["flops"] else None}
                  for cls, c in sorted(classes.items(), key=lambda kv: -kv[1]["ms"])}
 
-    top = sorted(kern.items(), key=lambda kv: -kv[1]["ms"])[:12]
+    top = sorted(kern.items(), key=lambda kv: -kv[1]["ms"])[:40]
     top_kernels = {tag: {"ms_per_step": k["ms"] / args.steps, "launches_per_step": k["launches"] / args.steps,
                          "tflops": (k["flops"] / (k["ms"] / 1e3) / 1e12) if k["flops"] else None,
                          "gbs": (k["bytes"] / (k["ms"] / 1e3) / 1e9) if k["bytes"] else None} for tag, k in top}

@@ -77,6 +77,23 @@ int tfswa_linear_fwd(const tfswa_linear_args* a, void* stream);
  * TFSWA_EINVAL for pre / col_stats / AFFINE / GELU-prologue requests (use tfswa_linear_fwd for those). */
 int tfswa_linear_tc_fwd(const tfswa_linear_args* a, const void* w_bf16, const float* wsum, void* stream);
 
+/* Fused tail of a pre-LN transformer branch (attention.py:86 + :121-128 with the residuals of :146,:159 / :220,:233 /
+ * :378,:387), bf16, tcgen05:    y = att Wp^T + bp + res;   out = y + W2 gelu(W1' LN_hat(y) + b1') + b2
+ * with the LayerNorm affine folded into W1'/b1' by the host.  One launch replaces tfswa_linear_tc_fwd (proj) +
+ * tfswa_row_stats + tfswa_linear_tc_fwd (fc1, GELU) + tfswa_linear_tc_fwd (fc2); y, its statistics and the 4C-wide
+ * hidden activations never leave the SM.  C in {32, 64}, hidden == 4*C; other widths return TFSWA_EINVAL (callers use
+ * the unfused sequence).  `batch` independent branches: att/out (M, batch, C) addressed by element strides; res is
+ * (M, C), shared by all branches when res_bs == 0.  Weights bf16 row-major (nn.Linear layout), biases fp32. */
+typedef struct {
+  const void* att; int64_t lda; int64_t att_bs;
+  const void* res; int64_t ldr; int64_t res_bs;
+  const void* wp;  const void* w1; const void* w2;      /* (batch,C,C), (batch,hidden,C), (batch,C,hidden) bf16 */
+  const float* bp; const float* b1; const float* b2;    /* (batch,C), (batch,hidden), (batch,C) */
+  void* out; int64_t ldo; int64_t out_bs;
+  int64_t M; int32_t C; int32_t hidden; int32_t batch; float eps;
+} tfswa_tail_args;
+int tfswa_branch_tail_tc_fwd(const tfswa_tail_args* a, void* stream);
+
 /* per-row LayerNorm statistics {mean, rstd} over K channels, eps 1e-5 (F.layer_norm, attention.py:146,159) */
 int tfswa_row_stats(const void* x, int64_t ldx, int64_t x_bs, float* stats, int64_t st_bs,
                     int64_t M, int32_t K, int32_t batch, int32_t dtype, void* stream);

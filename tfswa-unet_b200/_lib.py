@@ -34,6 +34,15 @@ class LinearArgs(C.Structure):
                 ("prologue", _i32), ("epilogue", _i32), ("batch", _i32), ("dtype", _i32)]
 
 
+class TailArgs(C.Structure):
+    _fields_ = [("att", _p), ("lda", _i64), ("att_bs", _i64),
+                ("res", _p), ("ldr", _i64), ("res_bs", _i64),
+                ("wp", _p), ("w1", _p), ("w2", _p),
+                ("bp", _p), ("b1", _p), ("b2", _p),
+                ("out", _p), ("ldo", _i64), ("out_bs", _i64),
+                ("M", _i64), ("C", _i32), ("hidden", _i32), ("batch", _i32), ("eps", C.c_float)]
+
+
 class AttnArgs(C.Structure):
     _fields_ = [("qkv", _p), ("ldq", _i64), ("out", _p), ("ldo", _i64), ("lse", _p),
                 ("pad_kv", _p), ("rel_bias", _p),
@@ -54,6 +63,7 @@ SIGNATURES = {
     "tfswa_device_supported": (C.c_int, []),
     "tfswa_linear_fwd": (C.c_int, [C.POINTER(LinearArgs), _p]),
     "tfswa_linear_tc_fwd": (C.c_int, [C.POINTER(LinearArgs), _p, _p, _p]),
+    "tfswa_branch_tail_tc_fwd": (C.c_int, [C.POINTER(TailArgs), _p]),
     "tfswa_row_stats": (C.c_int, [_p, _i64, _i64, _p, _i64, _i64, _i32, _i32, _i32, _p]),
     "tfswa_attn_fwd": (C.c_int, [C.POINTER(AttnArgs), _p]),
     "tfswa_attn_tc_scratch_bytes": (C.c_int64, [C.POINTER(AttnArgs)]),

@@ -135,6 +135,15 @@ def _mlp(y: Tensor, fc1, fc2) -> Tensor:
     return Fn.linear(h, fc2, r1=y)
 
 
+def _tail(att: Tensor, res: Tensor, p: dict) -> Tensor:
+    """res + proj(att), then the MLP with its residual (attention.py:86,146,159).  Narrow stages run it as one fused
+    tensor-core kernel at inference; otherwise (and under autograd) it is three linears + a statistics pass."""
+    if Fn.fused_tail_ok(att, res, p["proj"], p["fc1"], p["fc2"]):
+        return Fn.branch_tail(att, res, p["proj"], p["fc1"], p["fc2"])
+    y = Fn.linear(att, p["proj"], r1=res)
+    return _mlp(y, p["fc1"], p["fc2"])
+
+
 def _bn_train(count: int, stats: Tensor, bn: nn.BatchNorm2d):
     """Train-mode BatchNorm2d bookkeeping on accumulated column sums -> per-channel (scale, shift)."""
     return Fn.bn_finalize(stats, count, bn)
@@ -153,8 +162,7 @@ def branch_forward(x: Tensor, p: dict, geom: int, heads: int, ws: int = 8, shift
     qkv = Fn.linear(xt, p["qkv"], prologue=L.PRO_LNHAT, row_stats=st1)                  # (M,1,3C)
     att = Fn.attention(qkv[:, 0, :], B, H, W, C, heads, geom, ws=ws, shift=shift,
                        pad_kv=p["qkv"].b[0, C:], rel_bias=rel_bias, use_shift_mask=use_shift_mask)   # (M,C)
-    y = Fn.linear(att[:, None, :], p["proj"], r1=xt)
-    z = _mlp(y, p["fc1"], p["fc2"])
+    z = _tail(att[:, None, :], xt, p)
     return untokens(z[:, 0, :], B, H, W)
 
 
@@ -181,8 +189,7 @@ def block_forward(blk: nn.Module, x: Tensor, skip: Optional[Tensor], p: dict) ->
     att = Fn.attention3(qkv3, B, H, W, C, blk.num_heads, ws=blk.window_size, shift=blk.shift_size,
                         pad_kv=b9[2, C:], use_shift_mask=getattr(blk.swa, "use_shift_mask", False),
                         rel_bias=getattr(blk.swa, "rel_bias", None))                      # (M,3,C)
-    y = Fn.linear(att, p["proj"], r1=x1)                                                 # + residual  (M,3,C)
-    z = _mlp(y, p["fc1"], p["fc2"])                                                      # (M,3,C) == cat along C
+    z = _tail(att, x1, p)                                                                # (M,3,C) == cat along C
     zc = z.view(M, 1, 3 * C)
     skt = None if skip is None else tokens(skip)[:, None, :]
     # fusion: 1x1 conv (3C->C) + BN + GELU, + identity (+ skip)                    blocks.py:85-89,123-146

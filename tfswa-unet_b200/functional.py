@@ -87,6 +87,21 @@ def linear(x: Tensor, lw: LinW, *, prologue: int = 0, epilogue: int = 0,
     return ops.linear(x, w, bias, prologue=prologue, epilogue=epilogue, row_stats=row_stats, r1=r1, r2=r2)
 
 
+USE_FUSED_TAIL = True   # one kernel for proj + residual + LN + MLP + residual at C in {32, 64} (inference, bf16)
+
+
+def fused_tail_ok(att: Tensor, res: Tensor, proj: LinW, fc1: LinW, fc2: LinW) -> bool:
+    C_ = att.shape[2]
+    return (USE_TC and USE_FUSED_TAIL and att.dtype == torch.bfloat16 and C_ in (32, 64) and fc1.w.shape[1] == 4 * C_
+            and proj.b is not None and fc1.b is not None and fc2.b is not None
+            and not _needs_grad(att, res, proj.w, fc1.w, fc2.w))
+
+
+def branch_tail(att: Tensor, res: Tensor, proj: LinW, fc1: LinW, fc2: LinW) -> Tensor:
+    """res + proj(att) -> y;  y + fc2(GELU(fc1(LN_hat(y))))  in one kernel.  att (M,nb,C), res (M,1|nb,C)."""
+    return ops.branch_tail_tc(att, res, proj.tc()[0], fc1.tc()[0], fc2.tc()[0], proj.b, fc1.b, fc2.b)
+
+
 def attention(qkv: Tensor, B: int, H: int, W: int, C: int, heads: int, geom: int, *, ws: int = 8, shift: int = 0,
               pad_kv: Optional[Tensor] = None, rel_bias: Optional[Tensor] = None, use_shift_mask: bool = False) -> Tensor:
     """qkv (M, 3C) view -> (M, C)."""

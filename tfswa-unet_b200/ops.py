@@ -166,6 +166,38 @@ def linear_tc(x: Tensor, w_bf16: Tensor, wsum: Optional[Tensor], bias: Optional[
     return y
 
 
+def branch_tail_tc(att: Tensor, res: Tensor, wp: Tensor, w1: Tensor, w2: Tensor, bp: Tensor, b1: Tensor, b2: Tensor,
+                   eps: float = 1e-5) -> Tensor:
+    """Fused proj + residual + LN + fc1 + GELU + fc2 + residual of `nb` branches (see tfswa_branch_tail_tc_fwd).
+    att (M, nb, C) bf16, res (M, 1|nb, C) bf16, weights bf16 (nb,C,C) / (nb,4C,C) / (nb,C,4C), biases fp32."""
+    _cuda(att, res, wp, w1, w2)
+    M, nb, C_ = att.shape
+    hid = w1.shape[1]
+    if (att.dtype != torch.bfloat16 or res.dtype != torch.bfloat16 or res.shape[0] != M or res.shape[2] != C_
+            or res.shape[1] not in (1, nb)):
+        raise ValueError(f"branch_tail_tc: att {tuple(att.shape)}/{att.dtype} vs res {tuple(res.shape)}/{res.dtype}")
+    for name, w, shape in (("wp", wp, (nb, C_, C_)), ("w1", w1, (nb, hid, C_)), ("w2", w2, (nb, C_, hid))):
+        if tuple(w.shape) != shape or w.dtype != torch.bfloat16 or not w.is_contiguous():
+            raise ValueError(f"branch_tail_tc: {name} {tuple(w.shape)}/{w.dtype}, expected contiguous bf16 {shape}")
+    for name, b, n in (("bp", bp, C_), ("b1", b1, hid), ("b2", b2, C_)):
+        if tuple(b.shape) != (nb, n):
+            raise ValueError(f"branch_tail_tc: {name} {tuple(b.shape)}, expected {(nb, n)}")
+        _f32c(b)
+    out = torch.empty((M, nb, C_), dtype=att.dtype, device=att.device)
+    a = L.TailArgs()
+    a.att = att.data_ptr(); a.lda, a.att_bs = _tok3(att, "att")
+    a.res = res.data_ptr(); a.ldr, a.res_bs = _tok3(res, "res")
+    if res.shape[1] == 1:
+        a.res_bs = 0
+    a.wp, a.w1, a.w2 = wp.data_ptr(), w1.data_ptr(), w2.data_ptr()
+    a.bp, a.b1, a.b2 = bp.data_ptr(), b1.data_ptr(), b2.data_ptr()
+    a.out = out.data_ptr(); a.ldo, a.out_bs = _tok3(out, "out")
+    a.M, a.C, a.hidden, a.batch, a.eps = M, C_, hid, nb, eps
+    _call("tfswa_branch_tail_tc_fwd", C.byref(a), _stream(), tag=f"tail_tc[C={C_},nb={nb}]",
+          work={"flops": 2 * M * nb * (C_ * C_ + 2 * C_ * hid), "bytes": 2 * M * C_ * (2 * nb + res.shape[1])})
+    return out
+
+
 def row_stats(x: Tensor) -> Tensor:
     """(M, nb, K) -> (nb, M, 2) fp32 {mean, rstd} over K (LayerNorm statistics, eps 1e-5)."""
     _cuda(x)
