@@ -98,7 +98,8 @@ def lib() -> C.CDLL:
             raise RuntimeError(
                 f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                 "(nvcc, sm_100a). tfswa_unet_b200 has no CPU or PyTorch fallback.")
-        l = C.CDLL(LIB_PATH)
+        # TFSWA_B200_LIB: developer A/B switch (an alternative build of the SAME library, e.g. another tile constant)
+        l = C.CDLL(os.environ.get("TFSWA_B200_LIB") or LIB_PATH)
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(l, name)   # AttributeError here = header/library mismatch
             fn.restype = res

@@ -35,13 +35,14 @@ constexpr int TA_THREADS = 256;
 constexpr int TA_QT = 128;                 // queries per CTA
 constexpr uint32_t TA_TMEM_COLS = 256;
 constexpr uint32_t TA_O_COL = 128;         // O accumulators live in columns [128, 128+64)
+constexpr uint32_t TA_P_COL = 192;         // bf16 P (A operand of the PV MMA): 64 columns = 128 keys x 2 per 32-bit cell
 
 constexpr int TA_QS = 0;                   // Q operand, 128 rows x 32 B
 constexpr int TA_KS = 4096;                // 2 x 8 KB expanded-K operand (pass 1: 256 rows, pass 2: 128 rows)
-constexpr int TA_VS = TA_KS + 2 * 8192;    // 3 V' operand buffers of vs_bytes<D>() each, then 2 x 32 KB P operands
+constexpr int TA_VS = TA_KS + 2 * 8192;    // 3 V' operand buffers of vs_bytes<D>() each, then 1 KB exchange scratch
 template <int D> __host__ __device__ constexpr int vs_bytes() { return D == 16 ? 8192 : 4096; }
 template <int D> __host__ __device__ constexpr int ps_off() { return TA_VS + 3 * vs_bytes<D>(); }
-template <int D> __host__ __device__ constexpr int smem_bytes() { return ps_off<D>() + 2 * 32768; }   // 96 KB (d=4,8) / 108 KB (d=16)
+template <int D> __host__ __device__ constexpr int smem_bytes() { return ps_off<D>() + 1024; }        // 33 KB (d=4,8) / 45 KB (d=16)
 
 __device__ __forceinline__ uint32_t ex2_bf16x2(uint32_t x) {
   uint32_t y;
@@ -144,7 +145,10 @@ __device__ __forceinline__ float ex2_poly(float x) {
   p = fmaf(p, r, 0.9999280572f);
   return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
 }
-constexpr int TA_POLY_EVERY = 4;                    // every TA_POLY_EVERY-th exponential goes to ex2_poly (0 = never)
+#ifndef TFSWA_TA_POLY_EVERY
+#define TFSWA_TA_POLY_EVERY 4
+#endif
+constexpr int TA_POLY_EVERY = TFSWA_TA_POLY_EVERY;  // every TA_POLY_EVERY-th exponential goes to ex2_poly (0 = never); -D for A/B builds
 
 // Per-channel extrema of k over every sequence: kext[row][0][c] = min_j k[j][c], kext[row][1][c] = max_j k[j][c].
 // One CTA per sequence; thread t owns 8 channels (one 16-byte load per key) of key lane t / (C/8).
@@ -187,8 +191,10 @@ __global__ void __launch_bounds__(256) attn_kext_kernel(const AttnParams p) {
 // barrier in the key loop:
 //   bar_s   (1)  S(t) complete in TMEM                          issuer commit  -> softmax
 //   bar_a   (8)  S(t-1) pulled into registers + operands(t) staged   softmax  -> issuer (may issue S(t))
-//   bar_b[2](8)  P(t) staged                                          softmax  -> issuer (may issue PV(t))
-//   bar_pv[2](1) PV(t) complete: P buffer t&1 and V' buffer t%3 free  issuer commit -> softmax
+//   bar_b   (8)  P(t) written to TMEM                                 softmax  -> issuer (may issue PV(t))
+//   bar_pv  (1)  PV(t) complete: P columns and V' buffer t%3 free     issuer commit -> softmax
+// P never touches shared memory: the softmax threads write it to TMEM with tcgen05.st (their own lane = their query
+// row) and the PV MMA takes its A operand from TMEM, so the only generic->async proxy hand-off per tile is K / V'.
 template <int D>
 __global__ void __launch_bounds__(TA_THREADS + 32, 2) tc_attn_axial_kernel(const AttnParams p) {
   constexpr int HPQ = 16 / D;            // heads per CTA (4, 2, 1)
@@ -196,12 +202,11 @@ __global__ void __launch_bounds__(TA_THREADS + 32, 2) tc_attn_axial_kernel(const
   constexpr int HPT = HPQ >= 2 ? HPQ / 2 : 1;   // head slots per thread (d = 16: both threads of a row share the head)
   constexpr int NV = D == 16 ? 32 : 16;  // PV MMA N: v dims + ones column (+ zero padding)
   constexpr int P_SBO = (KT / 8) * 128;  // 8-row group stride of the P / V' operands
-  constexpr int P_HEAD = 128 * KT * 2;   // bytes of one head's P tile
   constexpr int V_HEAD = NV * KT * 2;
   constexpr int TA_PS = ps_off<D>();
   constexpr int VSB = vs_bytes<D>();
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ __align__(8) uint64_t bar_s, bar_a, bar_b[2], bar_pv[2], bar_sx[2], bar_ax[2];
+  __shared__ __align__(8) uint64_t bar_s, bar_a, bar_b, bar_pv, bar_sx[2], bar_ax[2];
   __shared__ uint32_t s_tmem;
   __shared__ float s_kext[2][16];        // per channel of the quad: min / max of k over the whole sequence
 
@@ -224,9 +229,9 @@ __global__ void __launch_bounds__(TA_THREADS + 32, 2) tc_attn_axial_kernel(const
   for (int i = tid; i < (TA_PS - TA_KS) / 16; i += TA_THREADS + 32) reinterpret_cast<uint4*>(smem + TA_KS)[i] = make_uint4(0, 0, 0, 0);
   if (warp == 0) {
     if (lane == 0) {
-      mbar_init(&bar_s, 1); mbar_init(&bar_a, 8);
+      mbar_init(&bar_s, 1); mbar_init(&bar_a, 8); mbar_init(&bar_b, 8); mbar_init(&bar_pv, 1);
 #pragma unroll
-      for (int i = 0; i < 2; ++i) { mbar_init(&bar_b[i], 8); mbar_init(&bar_pv[i], 1); mbar_init(&bar_sx[i], 1); mbar_init(&bar_ax[i], 8); }
+      for (int i = 0; i < 2; ++i) { mbar_init(&bar_sx[i], 1); mbar_init(&bar_ax[i], 8); }
       fence_barrier_init();
     }
     __syncwarp();
@@ -266,7 +271,7 @@ __global__ void __launch_bounds__(TA_THREADS + 32, 2) tc_attn_axial_kernel(const
   const uint32_t tmem = s_tmem;
   const uint32_t my_taddr = tmem + ((uint32_t)(quarter * 32) << 16);
   // barrier completions consumed so far by this thread (wait parity = count & 1)
-  uint32_t n_s = 0, n_a = 0, n_b[2] = {0u, 0u}, n_pv[2] = {0u, 0u}, n_sx[2] = {0u, 0u}, n_ax[2] = {0u, 0u};
+  uint32_t n_s = 0, n_a = 0, n_b = 0, n_pv = 0, n_sx[2] = {0u, 0u}, n_ax[2] = {0u, 0u};
 
   // row-max upper bound per head: s_ij = sum_d q_d k_jd <= sum_d max(q_d kmax_d, q_d kmin_d)   (raw score units)
   float m[HPT];
@@ -370,20 +375,20 @@ __global__ void __launch_bounds__(TA_THREADS + 32, 2) tc_attn_axial_kernel(const
           umma_commit(&bar_s);
         }
         if (t >= 1) {
-          const int u = t - 1, pb = u & 1;
-          mbar_wait(&bar_b[pb], n_b[pb] & 1); ++n_b[pb];              // P(u) staged
+          const int u = t - 1;
+          mbar_wait(&bar_b, n_b & 1); ++n_b;                          // P(u) in TMEM
           if (lane == 0) {
             tc_fence_after();
-            const uint32_t pbase = sbase + TA_PS + pb * 32768, vbase = sbase + TA_VS + (u % 3) * VSB;
+            const uint32_t vbase = sbase + TA_VS + (u % 3) * VSB;
 #pragma unroll
             for (int h = 0; h < HPQ; ++h) {
 #pragma unroll
-              for (int kk = 0; kk < KT / 16; ++kk) {
-                umma_bf16_ss(tmem + TA_O_COL + NV * h, umma_smem_desc_ns(pbase + h * P_HEAD + kk * 256, 128, P_SBO),
+              for (int kk = 0; kk < KT / 16; ++kk) {       // head h's keys occupy KT/2 columns; one K=16 step = 8 columns
+                umma_bf16_ts(tmem + TA_O_COL + NV * h, tmem + TA_P_COL + h * (KT / 2) + kk * 8,
                              umma_smem_desc_ns(vbase + h * V_HEAD + kk * 256, 128, P_SBO), idesc_pv, (u | kk) ? 1u : 0u);
               }
             }
-            umma_commit(&bar_pv[pb]);
+            umma_commit(&bar_pv);
           }
         }
         __syncwarp();
@@ -397,17 +402,15 @@ __global__ void __launch_bounds__(TA_THREADS + 32, 2) tc_attn_axial_kernel(const
       if (lane == 0) mbar_arrive(&bar_a);                             // operands(0) staged
       kvn = load_kv<D, KT>(p, tok_base, tok_stride, KT, N, quad, tid);
       for (int t = 0; t < T; ++t) {
-        const int pb = t & 1;
         mbar_wait(&bar_s, n_s & 1); ++n_s;
         tc_fence_after();
-        // buffer-reuse wait and operand staging for tile t+1 first (independent of S(t))
-        if (t >= 2) { mbar_wait(&bar_pv[pb], n_pv[pb] & 1); ++n_pv[pb]; }   // PV(t-2) done: Ps[pb], Vs[(t+1)%3] free
+        // operand staging for tile t+1 first (independent of S(t)); Ks[(t+1)&1] was read by S(t-1) (complete: S(t) is),
+        // Vs[(t+1)%3] by PV(t-2), whose completion was consumed during tile t-1
         if (t + 1 < T) {
           store_k<D, KT>(kvn, smem + TA_KS + ((t + 1) & 1) * 8192, tid);
           store_v<D, KT>(kvn, smem + TA_VS + ((t + 1) % 3) * VSB, tid);
           fence_async_smem();
         }
-        uint8_t* ps = smem + TA_PS + pb * 32768;
         const bool tail = (t + 1) * KT > N;          // only the last tile holds absent keys: their score 0 may exceed the bound
         // my 64 scores in two halves of 32 (keeps only 32 score registers live): exp of the first half runs while
         // nothing else of S(t) is needed; S is released to the issuer after the second TMEM load
@@ -421,10 +424,11 @@ __global__ void __launch_bounds__(TA_THREADS + 32, 2) tc_attn_axial_kernel(const
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_a);                       // S(t) consumed + operands(t+1) staged
+            // (measured: issuing this prefetch at the top of the tile, after the proxy fence, is 4 % slower - the
+            // nine registers it keeps live through the first half cost more than the fence's wait for it)
             kvn = load_kv<D, KT>(p, tok_base, tok_stride, (t + 2) * KT, N, quad, tid);   // latency hides under the exponentials
           }
           const int col = half * 64 + ch * 32;
-          const int head = col / KT, jbase = col % KT; // head within the quad, first key of this chunk
           const float mcc = mc[(ch * 32) / KT];
           if (tail) {
 #pragma unroll
@@ -439,18 +443,22 @@ __global__ void __launch_bounds__(TA_THREADS + 32, 2) tc_attn_axial_kernel(const
             const float e1 = (TA_POLY_EVERY > 0 && ((2 * i + 1) % TA_POLY_EVERY) == TA_POLY_EVERY - 1) ? ex2_poly(x1) : ex2_f32(x1);
             pk[i] = pack_bf16x2(e0, e1);
           }
-          uint8_t* dst = ps + head * P_HEAD + (r >> 3) * P_SBO + (r & 7) * 16 + (jbase >> 3) * 128;
-#pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4)
-            *reinterpret_cast<uint4*>(dst + q4 * 128) = make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]);
+          if (ch == 0 && t >= 1) {                   // PV(t-1) complete: the P columns (and Vs[(t-1)%3]) are free
+            mbar_wait(&bar_pv, n_pv & 1); ++n_pv;
+            tc_fence_after();
+          }
+          __syncwarp();
+          tmem_st_x16(my_taddr + TA_P_COL + (uint32_t)(col >> 1), pk);   // column pair (2c, 2c+1) -> 32-bit cell c
         }
-        fence_async_smem();
+        tmem_st_wait();
+        tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&bar_b[pb]);                       // P(t) staged
+        if (lane == 0) mbar_arrive(&bar_b);                           // P(t) in TMEM
       }
-      // ---- drain: exactly one un-consumed PV completion per barrier that was used ----
-      if (T > 1) { const int ob = (T & 1); mbar_wait(&bar_pv[ob], n_pv[ob] & 1); ++n_pv[ob]; }    // tile T-2
-      { const int lb = (T - 1) & 1; mbar_wait(&bar_pv[lb], n_pv[lb] & 1); ++n_pv[lb]; }            // tile T-1
+      // (measured: splitting P / PV per 32-column chunk with two barrier pairs, to give each chunk a whole tile of
+      // slack, is 11 % slower - the extra tcgen05.wait::st, arrives and issuer wake-ups cost more than the sleep they remove)
+      // ---- drain: PV(0..T-2) were consumed inside the loop, PV(T-1) is the one outstanding completion ----
+      mbar_wait(&bar_pv, n_pv & 1); ++n_pv;
       tc_fence_after();
     }
     // ---- epilogue: O / l ----
