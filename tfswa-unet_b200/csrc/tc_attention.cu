@@ -31,7 +31,8 @@ namespace tfswa {
 
 using namespace sm100;
 
-constexpr int TA_THREADS = 256;
+constexpr int TA_THREADS = 256;                // softmax threads (warps 0-7)
+constexpr int TA_NTHREADS = TA_THREADS + 64;   // + issuer warp (8) + producer warp (9)
 constexpr int TA_QT = 128;                 // queries per CTA
 constexpr uint32_t TA_TMEM_COLS = 256;
 constexpr uint32_t TA_O_COL = 128;         // O accumulators live in columns [128, 128+64)
@@ -126,6 +127,43 @@ __device__ __forceinline__ void store_v(const KvRegs& kv, uint8_t* vs, int tid) 
   *reinterpret_cast<uint16_t*>(base + (D >> 3) * sbo + (D & 7) * 16) = one;
 }
 
+// Producer-warp staging of one whole key tile: lane -> keys lane, lane+32, ...; per key the quad's 16 k channels go to
+// the expanded-K operand (store_k) and its 16 v channels to the per-head V' operands (v dims | 1 | 0...).
+template <int D, int KT>
+__device__ __forceinline__ void stage_tile(const AttnParams& p, int64_t tok_base, int64_t tok_stride, int k0, int N, int quad,
+                                           uint8_t* ks, uint8_t* vs, int lane) {
+  constexpr int HPQ = 16 / D;
+  constexpr int NV = D == 16 ? 32 : 16;
+  constexpr int head_bytes = NV * KT * 2, sbo = (KT / 8) * 128;
+  KvRegs kr[KT / 32];
+  uint4 vr[KT / 32][2];
+#pragma unroll
+  for (int i = 0; i < KT / 32; ++i) {                  // all loads first (independent, L2-resident after the prologue prefetch)
+    const int j = lane + 32 * i;
+    kr[i].a = make_uint4(0, 0, 0, 0); kr[i].b = kr[i].a; vr[i][0] = kr[i].a; vr[i][1] = kr[i].a;
+    kr[i].present = k0 + j < N;
+    if (kr[i].present) {
+      const bf16* src = (const bf16*)p.qkv + (tok_base + (int64_t)(k0 + j) * tok_stride) * p.ldq + p.C + quad * 16;
+      kr[i].a = reinterpret_cast<const uint4*>(src)[0]; kr[i].b = reinterpret_cast<const uint4*>(src)[1];
+      vr[i][0] = reinterpret_cast<const uint4*>(src + p.C)[0]; vr[i][1] = reinterpret_cast<const uint4*>(src + p.C)[1];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < KT / 32; ++i) {
+    const int j = lane + 32 * i;
+    store_k<D, KT>(kr[i], ks, j);
+    const uint16_t* e = reinterpret_cast<const uint16_t*>(vr[i]);
+    const uint16_t one = kr[i].present ? (uint16_t)0x3F80 : (uint16_t)0;       // bf16 1.0; absent keys are all-zero columns
+#pragma unroll
+    for (int h = 0; h < HPQ; ++h) {
+      uint8_t* base = vs + h * head_bytes + (j >> 3) * 128 + (j & 7) * 2;
+#pragma unroll
+      for (int d = 0; d < D; ++d) *reinterpret_cast<uint16_t*>(base + (d >> 3) * sbo + (d & 7) * 16) = e[h * D + d];
+      *reinterpret_cast<uint16_t*>(base + (D >> 3) * sbo + (D & 7) * 16) = one;
+    }
+  }
+}
+
 __device__ __forceinline__ float ex2_f32(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -185,18 +223,20 @@ __global__ void __launch_bounds__(256) attn_kext_kernel(const AttnParams p) {
   }
 }
 
-// Roles: warps 0-7 ("softmax", 256 threads) own one query row per thread pair, stage the K / V' operands of the next
-// tile cooperatively and turn S into P; warp 8 ("issuer") does nothing but wait on mbarriers and issue tcgen05.mma,
-// so the serial descriptor/MMA issue work never sits on the critical path of a softmax warp.  There is no CTA-wide
+// Roles: warps 0-7 ("softmax", 256 threads) own one query row per thread pair and turn S into P - in the key loop
+// they touch neither global nor shared memory (TMEM in, TMEM out); warp 9 ("producer") stages the K / V' operands of
+// tile t+2 in shared memory while tile t is being consumed (the generic->async proxy fence, a MEMBAR, stays off the
+// softmax warps); warp 8 ("issuer") does nothing but wait on mbarriers and issue tcgen05.mma.  There is no CTA-wide
 // barrier in the key loop:
 //   bar_s   (1)  S(t) complete in TMEM                          issuer commit  -> softmax
-//   bar_a   (8)  S(t-1) pulled into registers + operands(t) staged   softmax  -> issuer (may issue S(t))
+//   bar_a   (9)  S(t-1) pulled into registers (8 softmax warps) + operands(t) staged (producer) -> issuer (may issue S(t))
+//   bar_free(1)  S(t) and PV(t-1) complete: Ks[t&1], Vs[(t-1)%3] may be overwritten    softmax warp 0 -> producer
 //   bar_b   (8)  P(t) written to TMEM                                 softmax  -> issuer (may issue PV(t))
 //   bar_pv  (1)  PV(t) complete: P columns and V' buffer t%3 free     issuer commit -> softmax
 // P never touches shared memory: the softmax threads write it to TMEM with tcgen05.st (their own lane = their query
 // row) and the PV MMA takes its A operand from TMEM, so the only generic->async proxy hand-off per tile is K / V'.
 template <int D>
-__global__ void __launch_bounds__(TA_THREADS + 32, 2) tc_attn_axial_kernel(const AttnParams p) {
+__global__ void __launch_bounds__(TA_NTHREADS, 2) tc_attn_axial_kernel(const AttnParams p) {
   constexpr int HPQ = 16 / D;            // heads per CTA (4, 2, 1)
   constexpr int KT = 128 / HPQ;          // keys per tile: one S tile = 128 TMEM columns = HPQ heads x KT keys
   constexpr int HPT = HPQ >= 2 ? HPQ / 2 : 1;   // head slots per thread (d = 16: both threads of a row share the head)
@@ -206,12 +246,12 @@ __global__ void __launch_bounds__(TA_THREADS + 32, 2) tc_attn_axial_kernel(const
   constexpr int TA_PS = ps_off<D>();
   constexpr int VSB = vs_bytes<D>();
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ __align__(8) uint64_t bar_s, bar_a, bar_b, bar_pv, bar_sx[2], bar_ax[2];
+  __shared__ __align__(8) uint64_t bar_s, bar_a, bar_b, bar_pv, bar_free, bar_sx[2], bar_ax[2];
   __shared__ uint32_t s_tmem;
   __shared__ float s_kext[2][16];        // per channel of the quad: min / max of k over the whole sequence
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const bool issuer = warp == 8;
+  const bool softmax = warp < 8, issuer = warp == 8, producer = warp == 9;
   // grid.x enumerates the (query tile, quad) pairs of one sequence, grid.y the sequences: CTAs that share a
   // sequence's k|v rows are scheduled together, so those rows come from HBM once and from L2 afterwards
   const int nquads = p.C / 16;
@@ -226,10 +266,10 @@ __global__ void __launch_bounds__(TA_THREADS + 32, 2) tc_attn_axial_kernel(const
   else { tok_base = (int64_t)row * p.W; tok_stride = 1; }
 
   // ---- setup: zero the operand buffers (their zero patterns are permanent), barriers, TMEM ----
-  for (int i = tid; i < (TA_PS - TA_KS) / 16; i += TA_THREADS + 32) reinterpret_cast<uint4*>(smem + TA_KS)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < (TA_PS - TA_KS) / 16; i += TA_NTHREADS) reinterpret_cast<uint4*>(smem + TA_KS)[i] = make_uint4(0, 0, 0, 0);
   if (warp == 0) {
     if (lane == 0) {
-      mbar_init(&bar_s, 1); mbar_init(&bar_a, 8); mbar_init(&bar_b, 8); mbar_init(&bar_pv, 1);
+      mbar_init(&bar_s, 1); mbar_init(&bar_a, 9); mbar_init(&bar_b, 8); mbar_init(&bar_pv, 1); mbar_init(&bar_free, 1);
 #pragma unroll
       for (int i = 0; i < 2; ++i) { mbar_init(&bar_sx[i], 1); mbar_init(&bar_ax[i], 8); }
       fence_barrier_init();
@@ -240,7 +280,7 @@ __global__ void __launch_bounds__(TA_THREADS + 32, 2) tc_attn_axial_kernel(const
   bool q_valid = false;
   int64_t q_tok = 0;
   uint4 qa = make_uint4(0, 0, 0, 0), qb = qa;        // my row's 16 q channels
-  if (!issuer) {
+  if (softmax) {
     if (q0 + r < (p.q_end ? p.q_end : N)) { q_tok = tok_base + (int64_t)(q0 + r) * tok_stride; q_valid = true; }
     if (q_valid) {
       const uint4* src = reinterpret_cast<const uint4*>((const bf16*)p.qkv + q_tok * p.ldq + quad * 16);
@@ -253,7 +293,7 @@ __global__ void __launch_bounds__(TA_THREADS + 32, 2) tc_attn_axial_kernel(const
   }
   // Pull this sequence's k|v rows (32 B each per quad) towards L2 now: the key loop only prefetches one tile ahead
   // into registers, which hides an L2 hit but not an HBM miss.
-  for (int j = tid; j < 2 * N; j += TA_THREADS + 32) {
+  for (int j = tid; j < 2 * N; j += TA_NTHREADS) {
     const int key = j >> 1;
     const bf16* ptr = (const bf16*)p.qkv + (tok_base + (int64_t)key * tok_stride) * p.ldq + ((j & 1) ? 2 * p.C : p.C) + quad * 16;
     asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
@@ -271,13 +311,13 @@ __global__ void __launch_bounds__(TA_THREADS + 32, 2) tc_attn_axial_kernel(const
   const uint32_t tmem = s_tmem;
   const uint32_t my_taddr = tmem + ((uint32_t)(quarter * 32) << 16);
   // barrier completions consumed so far by this thread (wait parity = count & 1)
-  uint32_t n_s = 0, n_a = 0, n_b = 0, n_pv = 0, n_sx[2] = {0u, 0u}, n_ax[2] = {0u, 0u};
+  uint32_t n_s = 0, n_a = 0, n_b = 0, n_pv = 0, n_free = 0, n_sx[2] = {0u, 0u}, n_ax[2] = {0u, 0u};
 
   // row-max upper bound per head: s_ij = sum_d q_d k_jd <= sum_d max(q_d kmax_d, q_d kmin_d)   (raw score units)
   float m[HPT];
 #pragma unroll
   for (int hh = 0; hh < HPT; ++hh) m[hh] = 0.f;
-  if (!issuer) {
+  if (softmax) {
     uint4 raw[2] = {qa, qb};
     const __nv_bfloat16* qe = reinterpret_cast<const __nv_bfloat16*>(raw);
 #pragma unroll
@@ -308,7 +348,7 @@ __global__ void __launch_bounds__(TA_THREADS + 32, 2) tc_attn_axial_kernel(const
           }
           __syncwarp();
         }
-      } else {
+      } else if (softmax) {
 #pragma unroll
         for (int i = 0; i < HPT; ++i) m[i] = -CUDART_INF_F;
         // stage K(0), K(1)
@@ -351,12 +391,12 @@ __global__ void __launch_bounds__(TA_THREADS + 32, 2) tc_attn_axial_kernel(const
           }
         }
       }
-      if (HPQ == 1 && !issuer) reinterpret_cast<float*>(smem + TA_PS)[half * 128 + r] = m[0];
+      if (HPQ == 1 && softmax) reinterpret_cast<float*>(smem + TA_PS)[half * 128 + r] = m[0];
       tc_fence_before();
       __syncthreads();                                              // every S tile consumed before the buffers are reused
       tc_fence_after();
       if (HPQ == 1) {                                               // the two threads of a row each saw half of the keys
-        if (!issuer) { const float* ex = reinterpret_cast<const float*>(smem + TA_PS); m[0] = fmaxf(ex[r], ex[128 + r]); }
+        if (softmax) { const float* ex = reinterpret_cast<const float*>(smem + TA_PS); m[0] = fmaxf(ex[r], ex[128 + r]); }
         __syncthreads();
       }
     }
@@ -393,24 +433,23 @@ __global__ void __launch_bounds__(TA_THREADS + 32, 2) tc_attn_axial_kernel(const
         }
         __syncwarp();
       }
+    } else if (producer) {
+      // operands(k) for k = 0..T-1 (k >= 2 waits until tile k-2 released its buffers), then one arrival per bar_a phase
+      for (int k = 0; k <= T; ++k) {
+        if (k < T) {
+          if (k >= 2) { mbar_wait(&bar_free, n_free & 1); ++n_free; }
+          stage_tile<D, KT>(p, tok_base, tok_stride, k * KT, N, quad, smem + TA_KS + (k & 1) * 8192, smem + TA_VS + (k % 3) * VSB, lane);
+          fence_async_smem();
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_a);
+      }
     } else {
-      KvRegs kvn = load_kv<D, KT>(p, tok_base, tok_stride, 0, N, quad, tid);
-      store_k<D, KT>(kvn, smem + TA_KS, tid);
-      store_v<D, KT>(kvn, smem + TA_VS, tid);
-      fence_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bar_a);                             // operands(0) staged
-      kvn = load_kv<D, KT>(p, tok_base, tok_stride, KT, N, quad, tid);
+      if (lane == 0) mbar_arrive(&bar_a);                             // phase 0: nothing to consume yet
       for (int t = 0; t < T; ++t) {
         mbar_wait(&bar_s, n_s & 1); ++n_s;
         tc_fence_after();
-        // operand staging for tile t+1 first (independent of S(t)); Ks[(t+1)&1] was read by S(t-1) (complete: S(t) is),
-        // Vs[(t+1)%3] by PV(t-2), whose completion was consumed during tile t-1
-        if (t + 1 < T) {
-          store_k<D, KT>(kvn, smem + TA_KS + ((t + 1) & 1) * 8192, tid);
-          store_v<D, KT>(kvn, smem + TA_VS + ((t + 1) % 3) * VSB, tid);
-          fence_async_smem();
-        }
         const bool tail = (t + 1) * KT > N;          // only the last tile holds absent keys: their score 0 may exceed the bound
         // my 64 scores in two halves of 32 (keeps only 32 score registers live): exp of the first half runs while
         // nothing else of S(t) is needed; S is released to the issuer after the second TMEM load
@@ -423,10 +462,7 @@ __global__ void __launch_bounds__(TA_THREADS + 32, 2) tc_attn_axial_kernel(const
           if (ch == 1) {
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&bar_a);                       // S(t) consumed + operands(t+1) staged
-            // (measured: issuing this prefetch at the top of the tile, after the proxy fence, is 4 % slower - the
-            // nine registers it keeps live through the first half cost more than the fence's wait for it)
-            kvn = load_kv<D, KT>(p, tok_base, tok_stride, (t + 2) * KT, N, quad, tid);   // latency hides under the exponentials
+            if (lane == 0) mbar_arrive(&bar_a);                       // S(t) consumed
           }
           const int col = half * 64 + ch * 32;
           const float mcc = mc[(ch * 32) / KT];
@@ -443,9 +479,12 @@ __global__ void __launch_bounds__(TA_THREADS + 32, 2) tc_attn_axial_kernel(const
             const float e1 = (TA_POLY_EVERY > 0 && ((2 * i + 1) % TA_POLY_EVERY) == TA_POLY_EVERY - 1) ? ex2_poly(x1) : ex2_f32(x1);
             pk[i] = pack_bf16x2(e0, e1);
           }
-          if (ch == 0 && t >= 1) {                   // PV(t-1) complete: the P columns (and Vs[(t-1)%3]) are free
-            mbar_wait(&bar_pv, n_pv & 1); ++n_pv;
-            tc_fence_after();
+          if (ch == 0) {
+            if (t >= 1) {                            // PV(t-1) complete: the P columns (and Vs[(t-1)%3]) are free
+              mbar_wait(&bar_pv, n_pv & 1); ++n_pv;
+              tc_fence_after();
+            }
+            if (tid == 0 && t + 2 < T) mbar_arrive(&bar_free);       // S(t), PV(t-1) complete -> producer may stage tile t+2
           }
           __syncwarp();
           tmem_st_x16(my_taddr + TA_P_COL + (uint32_t)(col >> 1), pk);   // column pair (2c, 2c+1) -> 32-bit cell c
@@ -464,7 +503,7 @@ __global__ void __launch_bounds__(TA_THREADS + 32, 2) tc_attn_axial_kernel(const
     // ---- epilogue: O / l ----
     uint32_t o[32];
     bool bad = false;
-    if (!issuer) {
+    if (softmax) {
       __syncwarp();
       if (D == 8) {
         uint32_t t16[16];
@@ -487,7 +526,7 @@ __global__ void __launch_bounds__(TA_THREADS + 32, 2) tc_attn_axial_kernel(const
     tc_fence_before();
     const bool redo = attempt == 0 && !p.force_exact && __syncthreads_or(bad);
     if (redo) continue;
-    if (!issuer && q_valid) {
+    if (softmax && q_valid) {
       if (D == 16) {                                 // both threads of the row hold the same 32 columns: split the 16 dims
         const float l = __uint_as_float(o[16]);
         const float inv = 1.0f / l;
@@ -571,9 +610,9 @@ extern "C" int tfswa_attn_tc_fwd(const tfswa_attn_args* a, void* scratch, int64_
     if (e1 != cudaSuccess || e2 != cudaSuccess) { set_error("attn_tc: cudaFuncSetAttribute failed"); return TFSWA_ECUDA; }
     attr_set = true;
   }
-  if (D == 4) tc_attn_axial_kernel<4><<<grid, TA_THREADS + 32, smem_bytes<4>(), st>>>(p);
-  else if (D == 8) tc_attn_axial_kernel<8><<<grid, TA_THREADS + 32, smem_bytes<8>(), st>>>(p);
-  else tc_attn_axial_kernel<16><<<grid, TA_THREADS + 32, smem_bytes<16>(), st>>>(p);
+  if (D == 4) tc_attn_axial_kernel<4><<<grid, TA_NTHREADS, smem_bytes<4>(), st>>>(p);
+  else if (D == 8) tc_attn_axial_kernel<8><<<grid, TA_NTHREADS, smem_bytes<8>(), st>>>(p);
+  else tc_attn_axial_kernel<16><<<grid, TA_NTHREADS, smem_bytes<16>(), st>>>(p);
   if (q_tc < N) {
     int rc = check_launch("attn_tc");
     if (rc) return rc;
