@@ -124,6 +124,11 @@ int tfswa_attn_fwd(const tfswa_attn_args* a, void* stream);
 int64_t tfswa_attn_tc_scratch_bytes(const tfswa_attn_args* a);
 int tfswa_attn_tc_fwd(const tfswa_attn_args* a, void* scratch, int64_t scratch_bytes, void* stream);
 
+/* SW-MSA (8x8 windows, attention.py:347-403) with scores and probabilities held in registers: warp-level tensor-core
+ * MMAs (m16n8k16, bf16 in / fp32 accumulate), exact row maxima, no shared-memory round trip for S or P.  bf16 only;
+ * head_dim in {4,8,16,32}; the default-off mask / relative-bias features are served by tfswa_attn_fwd. */
+int tfswa_attn_win_tc_fwd(const tfswa_attn_args* a, void* stream);
+
 /* ---- convolutions (implicit GEMM over NHWC) ---------------------------------------------------
  * kind: 0 = 3x3 s1 p1 (output_head.0, tfswa_unet.py:140), 1 = 4x4 s2 p1 (DownsampleBlock, blocks.py:157),
  *       2 = transposed 4x4 s2 p1 (UpsampleBlock, blocks.py:172).

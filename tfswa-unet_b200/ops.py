@@ -234,9 +234,14 @@ def attention(qkv: Tensor, out: Tensor, B: int, H: int, W: int, C_: int, heads: 
         nq = n - rem if (n >= 128 and 0 < rem < 32) else n       # a short remainder goes to the key-split warp kernel
         fill = (nq / (-(-nq // 128) * 128)) * (n / (-(-n // kt) * kt))
         tc = fill >= 0.4
-    tag = f"{'attn_tc' if tc else 'attn'}[{('tsa', 'fsa', 'swa')[geom]},d={d}]"
+    win_tc = (USE_TC_ATTENTION and qkv.dtype == torch.bfloat16 and geom == L.GEOM_SWA and ws == 8 and rel_bias is None
+              and not (use_shift_mask and shift > 0) and d in (4, 8, 16, 32) and heads * d == C_
+              and (C_ == 32 or C_ % 64 == 0) and (d < 32 or C_ >= 64))
+    tag = f"{'attn_tc' if (tc or win_tc) else 'attn'}[{('tsa', 'fsa', 'swa')[geom]},d={d}]"
     work = _attn_work(B, H, W, C_, geom, ws, qkv.element_size(), heads)
-    if tc:
+    if win_tc:
+        _call("tfswa_attn_win_tc_fwd", C.byref(a), _stream(), tag=tag, work=work)
+    elif tc:
         nbytes = L.lib().tfswa_attn_tc_scratch_bytes(C.byref(a))
         scratch = torch.empty((nbytes,), dtype=torch.uint8, device=qkv.device)
         _call("tfswa_attn_tc_fwd", C.byref(a), scratch.data_ptr(), nbytes, _stream(), tag=tag, work=work)

@@ -12,19 +12,21 @@ M = B * H * W
 torch.manual_seed(0)
 qkv = torch.randn(M, 3 * C, device="cuda").to(torch.bfloat16)
 out = torch.empty(M, C, device="cuda", dtype=torch.bfloat16)
+pad_kv = torch.randn(2 * C, device="cuda")
+kw = lambda g: dict(ws=8, shift=4, pad_kv=pad_kv) if g == 2 else {}
 for tc in (True, False):
     ops.USE_TC_ATTENTION = tc
     for geom in geoms:
         for _ in range(2):
-            ops.attention(qkv, out, B, H, W, C, 8, geom)
+            ops.attention(qkv, out, B, H, W, C, 8, geom, **kw(geom))
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(3):
-            ops.attention(qkv, out, B, H, W, C, 8, geom)
+            ops.attention(qkv, out, B, H, W, C, 8, geom, **kw(geom))
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 3
-        N = H if geom == 0 else W
+        N = H if geom == 0 else (W if geom == 1 else 64)
         exps = M * N * 8
         print(f"stage {stage} B={B} geom={geom} tc={tc}: {ms:.3f} ms  {exps/ms/1e9:.2f} Gexp/ms... = {exps/(ms*1e-3)/1e12:.2f} Texp/s")
