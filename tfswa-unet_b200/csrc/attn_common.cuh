@@ -35,6 +35,8 @@ struct AttnParams {
 // fill the geometry-derived fields shared by forward and backward launchers
 // SIMT flash kernel on a query range (attention.cu); used by the tensor-core launcher for ragged remainders
 int attn_simt_axial_bf16(const AttnParams& p, cudaStream_t st);
+// register-resident warp-MMA flash kernel on queries [0, q_end) (attention_axial_mma.cu); needs p.kext
+int attn_axial_mma_bf16(const AttnParams& p, cudaStream_t st);
 
 inline void attn_fill_geometry(AttnParams& p) {
   if (p.geom == TFSWA_GEOM_SWA) {

@@ -26,6 +26,7 @@
 // Replaces attention.py:70-85 (+ permutes :143,:162,:217,:236) for head_dim 4 and 8, bf16 activations.
 #include "attn_common.cuh"
 #include "sm100.cuh"
+#include <stdlib.h>
 
 namespace tfswa {
 
@@ -601,6 +602,19 @@ extern "C" int tfswa_attn_tc_fwd(const tfswa_attn_args* a, void* scratch, int64_
   TFSWA_REQUIRE(rows <= 65535, "attn_tc: more than 65535 sequences in one launch (split the batch)");
   cudaStream_t st = (cudaStream_t)stream;
   attn_kext_kernel<<<rows, 256, 0, st>>>(p);
+  // TFSWA_AXIAL_KERNEL=umma|mma selects the main kernel (A/B): "umma" = tcgen05 + TMEM (this file), "mma" = register-
+  // resident warp-level MMAs (attention_axial_mma.cu)
+  // Measured on B200 (tools/attn_bench.py, C3 stage shapes): head_dim 4: umma 1.38 / 0.81 ms vs mma 1.42 / 0.86 ms
+  // (TSA / FSA); head_dim 8: 0.226 / 0.188 vs 0.211 / 0.160; head_dim 16: 0.077 / 0.078 vs 0.063 / 0.062 -> default below.
+  static int force = -1;                              // 0 = default choice, 1 = umma, 2 = mma
+  if (force < 0) { const char* e = getenv("TFSWA_AXIAL_KERNEL"); force = !e ? 0 : (e[0] == 'm' ? 2 : 1); }
+  const bool use_mma = force == 2 || (force == 0 && D >= 8);
+  if (use_mma && a->heads % 8 == 0) {
+    int rc = attn_axial_mma_bf16(p, st);
+    if (rc) return rc;
+    if (q_tc < N) { AttnParams ps = p; ps.q_begin = q_tc; ps.q_end = 0; return attn_simt_axial_bf16(ps, st); }
+    return TFSWA_OK;
+  }
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e1 = cudaFuncSetAttribute(tc_attn_axial_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<4>());
