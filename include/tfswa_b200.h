@@ -94,6 +94,20 @@ typedef struct {
 } tfswa_tail_args;
 int tfswa_branch_tail_tc_fwd(const tfswa_tail_args* a, void* stream);
 
+/* Fused head of a TFSWABlock (blocks.py:53-56,115 + attention.py:70 of the three branches), bf16, tcgen05, inference:
+ *   x1 = x Wi^T + bi  (input_proj with eval BatchNorm folded in);   qkv = LN_hat(x1) Wq^T + bq  (LN affine folded in)
+ * One launch replaces tfswa_linear_tc_fwd (input_proj) + tfswa_row_stats + tfswa_linear_tc_fwd (qkv).  C in {32, 64};
+ * wi (C,C), wq (9C,C) bf16 row-major; bi (C), bq (9C) fp32; x (M,C), x1 (M,C), qkv (M,9C) bf16 with row strides. */
+typedef struct {
+  const void* x;  int64_t ldx;
+  const void* wi; const void* wq;
+  const float* bi; const float* bq;
+  void* x1;  int64_t ld1;
+  void* qkv; int64_t ldq;
+  int64_t M; int32_t C; float eps;
+} tfswa_head_args;
+int tfswa_block_head_tc_fwd(const tfswa_head_args* a, void* stream);
+
 /* per-row LayerNorm statistics {mean, rstd} over K channels, eps 1e-5 (F.layer_norm, attention.py:146,159) */
 int tfswa_row_stats(const void* x, int64_t ldx, int64_t x_bs, float* stats, int64_t st_bs,
                     int64_t M, int32_t K, int32_t batch, int32_t dtype, void* stream);

@@ -43,6 +43,11 @@ class TailArgs(C.Structure):
                 ("M", _i64), ("C", _i32), ("hidden", _i32), ("batch", _i32), ("eps", C.c_float)]
 
 
+class HeadArgs(C.Structure):
+    _fields_ = [("x", _p), ("ldx", _i64), ("wi", _p), ("wq", _p), ("bi", _p), ("bq", _p),
+                ("x1", _p), ("ld1", _i64), ("qkv", _p), ("ldq", _i64), ("M", _i64), ("C", _i32), ("eps", C.c_float)]
+
+
 class AttnArgs(C.Structure):
     _fields_ = [("qkv", _p), ("ldq", _i64), ("out", _p), ("ldo", _i64), ("lse", _p),
                 ("pad_kv", _p), ("rel_bias", _p),
@@ -64,6 +69,7 @@ SIGNATURES = {
     "tfswa_linear_fwd": (C.c_int, [C.POINTER(LinearArgs), _p]),
     "tfswa_linear_tc_fwd": (C.c_int, [C.POINTER(LinearArgs), _p, _p, _p]),
     "tfswa_branch_tail_tc_fwd": (C.c_int, [C.POINTER(TailArgs), _p]),
+    "tfswa_block_head_tc_fwd": (C.c_int, [C.POINTER(HeadArgs), _p]),
     "tfswa_row_stats": (C.c_int, [_p, _i64, _i64, _p, _i64, _i64, _i32, _i32, _i32, _p]),
     "tfswa_attn_fwd": (C.c_int, [C.POINTER(AttnArgs), _p]),
     "tfswa_attn_tc_scratch_bytes": (C.c_int64, [C.POINTER(AttnArgs)]),

@@ -59,7 +59,7 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 #ifndef TFSWA_AX_POLY_EVERY
-#define TFSWA_AX_POLY_EVERY 4
+#define TFSWA_AX_POLY_EVERY 8
 #endif
 constexpr int AX_POLY_EVERY = TFSWA_AX_POLY_EVERY;
 constexpr int AX_KT = 64;                // keys per shared-memory tile

@@ -175,15 +175,18 @@ def block_forward(blk: nn.Module, x: Tensor, skip: Optional[Tensor], p: dict) ->
     training = blk.training
     xt = tokens(x)[:, None, :]
     # input_proj: 1x1 conv + BN (no activation)                                   blocks.py:53-56,115
-    if training:
-        pre, stats = Fn.linear(xt, p["in"], want_col_stats=True)
-        sc, sh = _bn_train(M, stats, blk.input_proj[1])
-        x1 = Fn.affine_act(pre, sc, sh)
+    if not training and Fn.fused_head_ok(xt, p["in"], p["qkv"]):
+        x1, qkv = Fn.block_head(xt, p["in"], p["qkv"])                                   # one kernel at C = 32 / 64
     else:
-        x1 = Fn.linear(xt, p["in"])
-    # LN statistics once, q|k|v of all three branches in one GEMM
-    st1 = Fn.row_stats(x1)
-    qkv = Fn.linear(x1, p["qkv"], prologue=L.PRO_LNHAT, row_stats=st1)                  # (M,1,9C)
+        if training:
+            pre, stats = Fn.linear(xt, p["in"], want_col_stats=True)
+            sc, sh = _bn_train(M, stats, blk.input_proj[1])
+            x1 = Fn.affine_act(pre, sc, sh)
+        else:
+            x1 = Fn.linear(xt, p["in"])
+        # LN statistics once, q|k|v of all three branches in one GEMM
+        st1 = Fn.row_stats(x1)
+        qkv = Fn.linear(x1, p["qkv"], prologue=L.PRO_LNHAT, row_stats=st1)              # (M,1,9C)
     qkv3 = qkv.view(M, 3, 3 * C)
     b9 = p["qkv"].b.view(3, 3 * C)
     att = Fn.attention3(qkv3, B, H, W, C, blk.num_heads, ws=blk.window_size, shift=blk.shift_size,

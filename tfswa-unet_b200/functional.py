@@ -102,6 +102,21 @@ def branch_tail(att: Tensor, res: Tensor, proj: LinW, fc1: LinW, fc2: LinW) -> T
     return ops.branch_tail_tc(att, res, proj.tc()[0], fc1.tc()[0], fc2.tc()[0], proj.b, fc1.b, fc2.b)
 
 
+USE_FUSED_HEAD = True   # one kernel for input_proj + LN statistics + q|k|v GEMM at C in {32, 64} (inference, bf16)
+
+
+def fused_head_ok(x: Tensor, inp: LinW, qkv: LinW) -> bool:
+    C_ = x.shape[2]
+    return (USE_TC and USE_FUSED_HEAD and x.dtype == torch.bfloat16 and x.shape[1] == 1 and C_ in (32, 64)
+            and tuple(inp.w.shape) == (1, C_, C_) and tuple(qkv.w.shape) == (1, 9 * C_, C_)
+            and inp.b is not None and qkv.b is not None and not _needs_grad(x, inp.w, qkv.w))
+
+
+def block_head(x: Tensor, inp: LinW, qkv: LinW):
+    """x1 = input_proj(x); qkv = qkv_linear(LN_hat(x1)) in one kernel -> (x1 (M,1,C), qkv (M,1,9C))."""
+    return ops.block_head_tc(x, inp.tc()[0], qkv.tc()[0], inp.b, qkv.b)
+
+
 def attention(qkv: Tensor, B: int, H: int, W: int, C: int, heads: int, geom: int, *, ws: int = 8, shift: int = 0,
               pad_kv: Optional[Tensor] = None, rel_bias: Optional[Tensor] = None, use_shift_mask: bool = False) -> Tensor:
     """qkv (M, 3C) view -> (M, C)."""

@@ -198,6 +198,33 @@ def branch_tail_tc(att: Tensor, res: Tensor, wp: Tensor, w1: Tensor, w2: Tensor,
     return out
 
 
+def block_head_tc(x: Tensor, wi: Tensor, wq: Tensor, bi: Tensor, bq: Tensor, eps: float = 1e-5):
+    """Fused input_proj + LayerNorm + q|k|v GEMM of a block (see tfswa_block_head_tc_fwd).  x (M,1,C) bf16;
+    wi (1,C,C), wq (1,9C,C) bf16; bi (1,C), bq (1,9C) fp32 -> x1 (M,1,C), qkv (M,1,9C)."""
+    _cuda(x, wi, wq)
+    M, nb, C_ = x.shape
+    if nb != 1 or x.dtype != torch.bfloat16:
+        raise ValueError(f"block_head_tc: x {tuple(x.shape)}/{x.dtype}")
+    for name, w, shape in (("wi", wi, (1, C_, C_)), ("wq", wq, (1, 9 * C_, C_))):
+        if tuple(w.shape) != shape or w.dtype != torch.bfloat16 or not w.is_contiguous():
+            raise ValueError(f"block_head_tc: {name} {tuple(w.shape)}/{w.dtype}, expected contiguous bf16 {shape}")
+    for name, b, n in (("bi", bi, C_), ("bq", bq, 9 * C_)):
+        if tuple(b.shape) != (1, n):
+            raise ValueError(f"block_head_tc: {name} {tuple(b.shape)}, expected {(1, n)}")
+        _f32c(b)
+    x1 = torch.empty((M, 1, C_), dtype=x.dtype, device=x.device)
+    qkv = torch.empty((M, 1, 9 * C_), dtype=x.dtype, device=x.device)
+    a = L.HeadArgs()
+    a.x, a.ldx = x.data_ptr(), _tok3(x, "x")[0]
+    a.wi, a.wq, a.bi, a.bq = wi.data_ptr(), wq.data_ptr(), bi.data_ptr(), bq.data_ptr()
+    a.x1, a.ld1 = x1.data_ptr(), C_
+    a.qkv, a.ldq = qkv.data_ptr(), 9 * C_
+    a.M, a.C, a.eps = M, C_, eps
+    _call("tfswa_block_head_tc_fwd", C.byref(a), _stream(), tag=f"head_tc[C={C_}]",
+          work={"flops": 2 * M * (C_ * C_ + 9 * C_ * C_), "bytes": 2 * M * C_ * 11})
+    return x1, qkv
+
+
 def row_stats(x: Tensor) -> Tensor:
     """(M, nb, K) -> (nb, M, 2) fp32 {mean, rstd} over K (LayerNorm statistics, eps 1e-5)."""
     _cuda(x)
