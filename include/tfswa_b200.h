@@ -81,7 +81,8 @@ int tfswa_linear_tc_fwd(const tfswa_linear_args* a, const void* w_bf16, const fl
  * :378,:387), bf16, tcgen05:    y = att Wp^T + bp + res;   out = y + W2 gelu(W1' LN_hat(y) + b1') + b2
  * with the LayerNorm affine folded into W1'/b1' by the host.  One launch replaces tfswa_linear_tc_fwd (proj) +
  * tfswa_row_stats + tfswa_linear_tc_fwd (fc1, GELU) + tfswa_linear_tc_fwd (fc2); y, its statistics and the 4C-wide
- * hidden activations never leave the SM.  C in {32, 64}, hidden == 4*C; other widths return TFSWA_EINVAL (callers use
+ * hidden activations never leave the SM.  C in {32, 64, 128} (at 128 the weights stream through a TMA ring instead of
+ * staying resident), hidden == 4*C; other widths return TFSWA_EINVAL (callers use
  * the unfused sequence).  `batch` independent branches: att/out (M, batch, C) addressed by element strides; res is
  * (M, C), shared by all branches when res_bs == 0.  Weights bf16 row-major (nn.Linear layout), biases fp32. */
 typedef struct {

@@ -38,7 +38,7 @@ def _run(t):
                               t["bp"].contiguous(), t["b1"].contiguous(), t["b2"].contiguous())
 
 
-@pytest.mark.parametrize("C", [32, 64])
+@pytest.mark.parametrize("C", [32, 64, 128])
 @pytest.mark.parametrize("M,nb,res_nb", [(1, 1, 1), (127, 3, 1), (128, 1, 1), (1000, 3, 1), (1000, 3, 3), (333, 2, 2)])
 def test_tail_vs_fp32(C, M, nb, res_nb):
     t = _case(M, nb, C, res_nb, seed=M + nb)
@@ -51,10 +51,10 @@ def test_tail_vs_fp32(C, M, nb, res_nb):
     assert (out - ref).abs().max() < 0.08 * max(1.0, ref.abs().max().item() / 4)
 
 
-@pytest.mark.parametrize("C", [32, 64])
+@pytest.mark.parametrize("C", [32, 64, 128])
 def test_tail_many_tiles_per_cta(C):
     """more tiles than the persistent grid holds: exercises the prefetch double buffer and barrier phases"""
-    M = 128 * 1500 + 77
+    M = 128 * (1500 if C < 128 else 700) + 77
     t = _case(M, 3, C, 1, seed=5)
     out = _run(t).float()
     ref = _ref(t)
@@ -66,7 +66,7 @@ def test_tail_many_tiles_per_cta(C):
     assert (d / n).max() < 2e-2
 
 
-@pytest.mark.parametrize("C", [32, 64])
+@pytest.mark.parametrize("C", [32, 64, 128])
 def test_tail_matches_unfused_sequence(C):
     """same rounding points as proj -> row_stats -> fc1(GELU) -> fc2 on tfswa_linear_tc_fwd, except that y stays fp32"""
     from tfswa_unet_b200 import _lib as L
@@ -87,7 +87,7 @@ def test_tail_matches_unfused_sequence(C):
 
 def test_tail_rejects_other_widths():
     from tfswa_unet_b200 import ops
-    t = _case(64, 1, 128, 1)
+    t = _case(64, 1, 256, 1)
     with pytest.raises(RuntimeError, match="not in"):
         _run(t)
     t = _case(64, 1, 32, 1)

@@ -305,6 +305,8 @@ static int launch_tail(const tfswa_tail_args* a, cudaStream_t st) {
   return check_launch("branch_tail_tc");
 }
 
+int launch_tail128(const tfswa_tail_args* a, cudaStream_t st);   // tc_tail128.cu: weights streamed through a TMA ring
+
 }  // namespace tfswa
 
 using namespace tfswa;
@@ -312,10 +314,11 @@ using namespace tfswa;
 extern "C" int tfswa_branch_tail_tc_fwd(const tfswa_tail_args* a, void* stream) {
   TFSWA_REQUIRE(a && a->att && a->res && a->wp && a->w1 && a->w2 && a->bp && a->b1 && a->b2 && a->out, "branch_tail_tc: null pointer");
   TFSWA_REQUIRE(a->M > 0 && a->M / 128 < (1 << 24) && a->batch > 0 && a->batch <= 64, "branch_tail_tc: bad M / batch");
-  TFSWA_REQUIRE(a->C == 32 || a->C == 64, "branch_tail_tc: C=%d not in {32, 64} (use the unfused tfswa_linear_tc_fwd sequence)", a->C);
+  TFSWA_REQUIRE(a->C == 32 || a->C == 64 || a->C == 128, "branch_tail_tc: C=%d not in {32, 64, 128} (use the unfused tfswa_linear_tc_fwd sequence)", a->C);
   TFSWA_REQUIRE(a->hidden == 4 * a->C, "branch_tail_tc: hidden=%d must be 4*C", a->hidden);
   TFSWA_REQUIRE(a->lda % 8 == 0 && a->att_bs % 8 == 0 && a->ldr % 8 == 0 && a->res_bs % 8 == 0 && a->ldo % 8 == 0 && a->out_bs % 8 == 0,
                 "branch_tail_tc: 16-byte alignment of ld/strides");
   TFSWA_REQUIRE(a->eps > 0.f, "branch_tail_tc: eps must be positive");
+  if (a->C == 128) return launch_tail128(a, (cudaStream_t)stream);
   return a->C == 32 ? launch_tail<32>(a, (cudaStream_t)stream) : launch_tail<64>(a, (cudaStream_t)stream);
 }

@@ -87,12 +87,13 @@ def linear(x: Tensor, lw: LinW, *, prologue: int = 0, epilogue: int = 0,
     return ops.linear(x, w, bias, prologue=prologue, epilogue=epilogue, row_stats=row_stats, r1=r1, r2=r2)
 
 
-USE_FUSED_TAIL = True   # one kernel for proj + residual + LN + MLP + residual at C in {32, 64} (inference, bf16)
+USE_FUSED_TAIL = True   # one kernel for proj + residual + LN + MLP + residual at C in {32, 64, 128} (inference, bf16)
+FUSED_TAIL_WIDTHS = (32, 64, 128)
 
 
 def fused_tail_ok(att: Tensor, res: Tensor, proj: LinW, fc1: LinW, fc2: LinW) -> bool:
     C_ = att.shape[2]
-    return (USE_TC and USE_FUSED_TAIL and att.dtype == torch.bfloat16 and C_ in (32, 64) and fc1.w.shape[1] == 4 * C_
+    return (USE_TC and USE_FUSED_TAIL and att.dtype == torch.bfloat16 and C_ in FUSED_TAIL_WIDTHS and fc1.w.shape[1] == 4 * C_
             and proj.b is not None and fc1.b is not None and fc2.b is not None
             and not _needs_grad(att, res, proj.w, fc1.w, fc2.w))
 

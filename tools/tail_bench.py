@@ -25,7 +25,7 @@ def timeit(fn, n=5):
     return s.elapsed_time(e) / n
 
 
-for stage, C in ((1, 32), (2, 64)):
+for stage, C in ((1, 32), (2, 64), (3, 128)):
     h, w = H, W
     for _ in range(stage - 1):
         h, w = (h + 1) // 2, (w + 1) // 2
