@@ -209,7 +209,7 @@ tc_tail_kernel(const __grid_constant__ CUtensorMap tm_att, const __grid_constant
         for (int q4 = 0; q4 < 4; ++q4) {
           float v[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = gelu_erf_fast(__uint_as_float(raw[q4 * 8 + j]) + s_b1[t * 64 + ch * 32 + q4 * 8 + j]);
+          for (int j = 0; j < 8; ++j) v[j] = gelu_hidden(__uint_as_float(raw[q4 * 8 + j]) + s_b1[t * 64 + ch * 32 + q4 * 8 + j]);
           uint32_t off = r * 128 + (ch * 4 + q4) * 16;
           off ^= ((off >> 7) & 7u) << 4;
           store8(reinterpret_cast<bf16*>(a2 + off), v);

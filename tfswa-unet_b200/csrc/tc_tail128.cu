@@ -254,8 +254,8 @@ tc_tail128_kernel(const __grid_constant__ CUtensorMap tm_att, const __grid_const
         uint32_t pk[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float g0 = gelu_erf_fast(__uint_as_float(raw[2 * j]) + s_b1[c * T8_HC + t * 16 + 2 * j]);
-          const float g1 = gelu_erf_fast(__uint_as_float(raw[2 * j + 1]) + s_b1[c * T8_HC + t * 16 + 2 * j + 1]);
+          const float g0 = gelu_hidden(__uint_as_float(raw[2 * j]) + s_b1[c * T8_HC + t * 16 + 2 * j]);
+          const float g1 = gelu_hidden(__uint_as_float(raw[2 * j + 1]) + s_b1[c * T8_HC + t * 16 + 2 * j + 1]);
           asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(pk[j]) : "f"(g1), "f"(g0));
         }
         __syncwarp();
