@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(AX_THREADS, MINB) attn_axial_mma_kernel(const 
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
-  const int row = blockIdx.y, q0 = blockIdx.x * QB, slab = blockIdx.z;
+  const int row = blockIdx.y, q0 = p.q_begin + blockIdx.x * QB, slab = blockIdx.z;
   const int N = p.geom == TFSWA_GEOM_TSA ? p.H : p.W;
   const int q_end = p.q_end ? p.q_end : N;
   const int T = (N + AX_KT - 1) / AX_KT;
@@ -332,12 +332,12 @@ static int launch_axial(const AttnParams& p, int q_count, int rows, cudaStream_t
   return check_launch("attn_axial_mma");
 }
 
-// queries [0, p.q_end) of every sequence; p.kext must hold the per-sequence k extrema (attn_kext_kernel)
+// queries [p.q_begin, p.q_end) of every sequence (q_end = 0: to the end); p.kext must hold the per-sequence k extrema
 int attn_axial_mma_bf16(const AttnParams& p, cudaStream_t st) {
   const int D = p.C / p.heads;
   const int N = p.geom == TFSWA_GEOM_TSA ? p.H : p.W;
   const int rows = p.geom == TFSWA_GEOM_TSA ? p.B * p.W : p.B * p.H;
-  const int q_count = p.q_end ? p.q_end : N;
+  const int q_count = (p.q_end ? p.q_end : N) - p.q_begin;
   if (rows > 65535 || p.heads % 8 != 0) { set_error("attn_axial_mma: rows=%d heads=%d unsupported", rows, p.heads); return TFSWA_EINVAL; }
 #ifdef TFSWA_AX_MT2
   if (D == 4) return launch_axial<4, 2, 3>(p, q_count, rows, st);

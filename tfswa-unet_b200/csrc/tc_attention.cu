@@ -609,11 +609,9 @@ extern "C" int tfswa_attn_tc_fwd(const tfswa_attn_args* a, void* scratch, int64_
   static int force = -1;                              // 0 = default choice, 1 = umma, 2 = mma
   if (force < 0) { const char* e = getenv("TFSWA_AXIAL_KERNEL"); force = !e ? 0 : (e[0] == 'm' ? 2 : 1); }
   const bool use_mma = force == 2 || (force == 0 && D >= 8);
-  if (use_mma && a->heads % 8 == 0) {
-    int rc = attn_axial_mma_bf16(p, st);
-    if (rc) return rc;
-    if (q_tc < N) { AttnParams ps = p; ps.q_begin = q_tc; ps.q_end = 0; return attn_simt_axial_bf16(ps, st); }
-    return TFSWA_OK;
+  if (use_mma && a->heads % 8 == 0) {                // 16-row granularity: no separate remainder pass
+    AttnParams pm = p; pm.q_begin = 0; pm.q_end = 0;
+    return attn_axial_mma_bf16(pm, st);
   }
   static bool attr_set = false;
   if (!attr_set) {
@@ -627,11 +625,14 @@ extern "C" int tfswa_attn_tc_fwd(const tfswa_attn_args* a, void* scratch, int64_
   if (D == 4) tc_attn_axial_kernel<4><<<grid, TA_NTHREADS, smem_bytes<4>(), st>>>(p);
   else if (D == 8) tc_attn_axial_kernel<8><<<grid, TA_NTHREADS, smem_bytes<8>(), st>>>(p);
   else tc_attn_axial_kernel<16><<<grid, TA_NTHREADS, smem_bytes<16>(), st>>>(p);
-  if (q_tc < N) {
+  if (q_tc < N) {                                    // ragged remainder (< 32 queries per sequence)
     int rc = check_launch("attn_tc");
     if (rc) return rc;
     AttnParams ps = p;
     ps.q_begin = q_tc; ps.q_end = 0;
+    // 3+ left-over queries: one 16-row tile of the register-resident kernel (FSA, 5 queries: 90 -> 42 us at B=1);
+    // 1-2 queries: the key-split warp kernel is still ahead (36 vs 40 us)
+    if (a->heads % 8 == 0 && force != 1 && N - q_tc > 2) return attn_axial_mma_bf16(ps, st);
     return attn_simt_axial_bf16(ps, st);
   }
   return check_launch("attn_tc");
