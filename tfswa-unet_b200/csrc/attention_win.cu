@@ -42,7 +42,10 @@ __device__ __forceinline__ float ex2_poly_w(float x) {
 
 constexpr int WIN_TOK = 64;            // tokens per window (ws = 8)
 constexpr int WIN_THREADS = 256;
-constexpr int WIN_POLY_EVERY = 4;      // every 4th exponential on the FMA pipe instead of MUFU
+#ifndef TFSWA_WIN_POLY_EVERY
+#define TFSWA_WIN_POLY_EVERY 0
+#endif
+constexpr int WIN_POLY_EVERY = TFSWA_WIN_POLY_EVERY;   // every n-th exponential on the FMA pipe instead of MUFU (0 = none: this kernel is issue-bound)
 
 // D = head_dim, CS = channels per CTA slab (min(C, 64))
 template <int D, int CS>
