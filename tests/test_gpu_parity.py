@@ -132,6 +132,22 @@ def test_unet_forward_golden(golden, name, precision):
         assert float((masks.cpu() - case["y"]).abs().max()) <= 2e-2
 
 
+def test_unet_config0_shape_vs_oracle():
+    """BASELINE.json configs[0] (the reference's tests/test_model.py forward): TFSWA-UNet 15.4 M params, input
+    (2,2,256,512) fp32 - fp32 kernels against the CPU oracle on the same seeded weights and input."""
+    T = _T()
+    T.set_precision("fp32")
+    m, sd = _filled("unet", 32, 5, gain=0.7, cin=2, cout=2)
+    m.eval().cuda()
+    assert sum(p.numel() for p in m.parameters()) == 15404834
+    x = seeded((2, 2, 256, 512), 6)
+    with torch.no_grad():
+        masks = m(x.cuda())
+        ref = O.unet_forward(x, sd)
+    assert masks.shape == (2, 2, 256, 512) and masks.dtype == torch.float32
+    assert_close("config0.masks", masks, ref, 2e-4)
+
+
 @pytest.mark.parametrize("shape,C,shift", [((1, 32, 65, 41), 32, 4), ((2, 64, 33, 50), 64, 4), ((1, 128, 24, 40), 128, 0),
                                            ((1, 256, 16, 24), 256, 4), ((1, 32, 8, 8), 32, 4), ((1, 32, 130, 9), 32, 4)])
 def test_block_vs_oracle_odd_sizes(shape, C, shift):
