@@ -12,6 +12,9 @@ namespace tfswa {
 
 enum { KIND_LINEAR = 0, KIND_CONV3 = 1, KIND_DOWN = 2, KIND_UP = 3 };
 
+// bf16 linear weight gradient on the tensor cores (wgrad_mma.cu); returns 1 when the shape is not covered
+int wgrad_mma_bf16(const tfswa_linear_args* a, const void* g, int64_t ldg, int64_t g_bs, float* dw, float* dbias, cudaStream_t st);
+
 struct IgemmParams {
   const void* x; int64_t ldx;
   const float* w; const float* bias;
@@ -438,6 +441,10 @@ int tfswa_linear_wgrad(const tfswa_linear_args* a, const void* g, int64_t ldg, i
   TFSWA_REQUIRE(a->K % 4 == 0 && a->N % 4 == 0 && a->ldx % 4 == 0 && ldg % 4 == 0 && a->x_bs % 4 == 0 && g_bs % 4 == 0,
                 "linear_wgrad: alignment (multiples of 4 elements)");
   TFSWA_REQUIRE(!(a->prologue & TFSWA_PRO_LNHAT) || a->row_stats, "linear_wgrad: PRO_LNHAT needs row_stats");
+  if (a->dtype == TFSWA_BF16) {                      // tensor-core path (wgrad_mma.cu); 1 = shape not covered, fall through
+    const int rc = wgrad_mma_bf16(a, g, ldg, g_bs, dw, dbias, (cudaStream_t)stream);
+    if (rc != 1) return rc;
+  }
   IgemmParams p = {};
   p.x = a->x; p.ldx = a->ldx; p.x_bs = a->x_bs; p.row_stats = a->row_stats; p.rs_bs = a->rs_bs;
   p.in_scale = a->in_scale; p.in_shift = a->in_shift; p.prologue = a->prologue;

@@ -1,0 +1,170 @@
+// Weight gradient of a (batched) token linear on the tensor cores, bf16 activations:
+//     dW[b][n][k] += sum_m G[m,b,n] * pro(X)[m,b,k],      dbias[b][n] += sum_m G[m,b,n]
+// (the backward of nn.Linear / 1x1 conv in attention.py:70,86,121-128 and blocks.py:53-56,85-89).
+//
+// The reduction runs over millions of tokens while the result is at most 1152 x 1024, so the GEMM is "tall": one CTA
+// owns a 64 (n) x 64 (k) output tile and a slice of the tokens (split-M), keeps the tile in MMA accumulators and
+// finishes with fp32 atomics.  Both operands are token-major in memory (G: tokens x N, X: tokens x K) while the MMA
+// wants the tokens along its K dimension, so the fragments are read from the shared-memory token tiles with
+// ldmatrix.trans - no transposed copy is ever made.  The LayerNorm / GELU / BatchNorm-affine prologues of the forward
+// are applied while X is staged (fp32 math, then rounded to bf16 for the MMA).  The bias gradient rides along as one
+// more MMA against a ones operand.  Replaces the CUDA-core wgrad_kernel (igemm.cu) for bf16, where the weight
+// gradients were 28 % of a training step.
+#include "common.cuh"
+
+namespace tfswa {
+
+struct WgradMmaParams {
+  const bf16* x; int64_t ldx, x_bs;
+  const bf16* g; int64_t ldg, g_bs;
+  const float* row_stats; int64_t rs_bs;
+  const float* in_scale; const float* in_shift;
+  float* dw; int64_t w_bs;
+  float* dbias; int64_t bias_bs;
+  int64_t M, rows_per_cta;
+  int N, K, prologue, msplit;
+};
+
+constexpr int WM_T = 64;            // output tile edge (n and k)
+constexpr int WM_MC = 64;           // tokens per shared-memory chunk
+constexpr int WM_PITCH = WM_T + 8;  // padded row (conflict-free ldmatrix)
+constexpr int WM_THREADS = 256;
+
+__device__ __forceinline__ void wm_mma(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void wm_ldsm_x4_trans(uint32_t (&r)[4], const void* smem_row) {
+  const uint32_t addr = (uint32_t)__cvta_generic_to_shared(smem_row);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void wm_ldsm_x2_trans(uint32_t& r0, uint32_t& r1, const void* smem_row) {
+  const uint32_t addr = (uint32_t)__cvta_generic_to_shared(smem_row);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
+}
+
+__global__ void __launch_bounds__(WM_THREADS) wgrad_mma_kernel(const WgradMmaParams p) {
+  __shared__ __align__(16) bf16 Gs[WM_MC][WM_PITCH];
+  __shared__ __align__(16) bf16 As[WM_MC][WM_PITCH];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int k0 = blockIdx.x * WM_T, n0 = blockIdx.y * WM_T;
+  const int zb = blockIdx.z / p.msplit, split = blockIdx.z % p.msplit;
+  const bf16* x = p.x + (int64_t)zb * p.x_bs;
+  const bf16* g = p.g + (int64_t)zb * p.g_bs;
+  const float* rs = p.row_stats ? p.row_stats + (int64_t)zb * p.rs_bs : nullptr;
+  const int64_t m_begin = (int64_t)split * p.rows_per_cta;
+  const int64_t m_end = m_begin + p.rows_per_cta < p.M ? m_begin + p.rows_per_cta : p.M;
+
+  // staging: thread -> (token row lr + 32 i, 8 columns at lc), i = 0, 1, for G and for X
+  const int lr = tid >> 3, lc = (tid & 7) * 8;
+  const bool g_ok = n0 + lc < p.N, a_ok = k0 + lc < p.K;          // N, K are multiples of 8
+  // compute: warp -> 16 n rows (nt) x 32 k columns (kh)
+  const int nt = warp & 3, kh = warp >> 2;
+  float acc[4][4], bacc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+
+  uint4 gv[2], av[2];
+  auto load_chunk = [&](int64_t mc) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int64_t m = mc + lr + 32 * i;
+      gv[i] = make_uint4(0, 0, 0, 0); av[i] = gv[i];
+      if (m < m_end) {
+        if (g_ok) gv[i] = *reinterpret_cast<const uint4*>(g + m * p.ldg + n0 + lc);
+        if (a_ok) {
+          if (p.prologue == TFSWA_PRO_NONE) {
+            av[i] = *reinterpret_cast<const uint4*>(x + m * p.ldx + k0 + lc);
+          } else {
+            float v[8];
+            load8(x + m * p.ldx + k0 + lc, v);
+            if (p.prologue & TFSWA_PRO_AFFINE) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] = v[j] * p.in_scale[k0 + lc + j] + p.in_shift[k0 + lc + j];
+            }
+            if (p.prologue & TFSWA_PRO_LNHAT) {
+              const float mean = rs[m * 2], rstd = rs[m * 2 + 1];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] = (v[j] - mean) * rstd;
+            }
+            if (p.prologue & TFSWA_PRO_GELU) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] = gelu_erf(v[j]);
+            }
+            bf16 tmp[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) tmp[j] = __float2bfloat16(v[j]);
+            av[i] = *reinterpret_cast<const uint4*>(tmp);
+          }
+        }
+      }
+    }
+  };
+
+  constexpr uint32_t ONES = 0x3F803F80u;
+  load_chunk(m_begin);
+  for (int64_t mc = m_begin; mc < m_end; mc += WM_MC) {
+    __syncthreads();                                               // previous chunk's fragments have been read
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      *reinterpret_cast<uint4*>(&Gs[lr + 32 * i][lc]) = gv[i];
+      *reinterpret_cast<uint4*>(&As[lr + 32 * i][lc]) = av[i];
+    }
+    __syncthreads();
+    if (mc + WM_MC < m_end) load_chunk(mc + WM_MC);                // global latency of the next chunk under the MMAs
+#pragma unroll
+    for (int ks = 0; ks < WM_MC / 16; ++ks) {
+      // A = G^T: (n rows, token cols).  x4.trans blocks: (tokens 0-7, n 0-7), (tokens 0-7, n 8-15), (tokens 8-15, n 0-7), (tokens 8-15, n 8-15)
+      uint32_t a[4];
+      wm_ldsm_x4_trans(a, &Gs[ks * 16 + (lane & 7) + ((lane >> 4) << 3)][nt * 16 + ((lane >> 3) & 1) * 8]);
+#pragma unroll
+      for (int kt = 0; kt < 4; ++kt) {
+        uint32_t b0, b1;                                           // B = X: tokens 0-7 / 8-15 x 8 k columns
+        wm_ldsm_x2_trans(b0, b1, &As[ks * 16 + (lane & 15)][kh * 32 + kt * 8]);
+        wm_mma(acc[kt], a, b0, b1);
+      }
+      if (kh == 0) wm_mma(bacc, a, ONES, ONES);                    // every column of bacc = sum over tokens of G
+    }
+  }
+  // ---- split-M partial -> global with fp32 atomics ----
+  const int gq = lane >> 2, tq = lane & 3;
+  float* dw = p.dw + (int64_t)zb * p.w_bs;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int n = n0 + nt * 16 + gq + h * 8;
+    if (n >= p.N) continue;
+#pragma unroll
+    for (int kt = 0; kt < 4; ++kt) {
+      const int k = k0 + kh * 32 + kt * 8 + 2 * tq;
+      if (k < p.K) {
+        atomicAdd(dw + (int64_t)n * p.K + k, acc[kt][h * 2]);
+        atomicAdd(dw + (int64_t)n * p.K + k + 1, acc[kt][h * 2 + 1]);
+      }
+    }
+    if (p.dbias && kh == 0 && tq == 0 && blockIdx.x == 0) atomicAdd(p.dbias + (int64_t)zb * p.bias_bs + n, bacc[h * 2]);
+  }
+}
+
+// bf16 linear weight gradient; returns TFSWA_EINVAL-free "not handled" (1) when the shape is outside this kernel
+int wgrad_mma_bf16(const tfswa_linear_args* a, const void* g, int64_t ldg, int64_t g_bs, float* dw, float* dbias, cudaStream_t st) {
+  if (a->K % 8 || a->N % 8 || a->ldx % 8 || ldg % 8 || a->x_bs % 8 || g_bs % 8 || (((uintptr_t)a->x | (uintptr_t)g) & 15)) return 1;
+  WgradMmaParams p = {};
+  p.x = (const bf16*)a->x; p.ldx = a->ldx; p.x_bs = a->x_bs; p.g = (const bf16*)g; p.ldg = ldg; p.g_bs = g_bs;
+  p.row_stats = a->row_stats; p.rs_bs = a->rs_bs; p.in_scale = a->in_scale; p.in_shift = a->in_shift;
+  p.dw = dw; p.w_bs = (int64_t)a->N * a->K; p.dbias = dbias; p.bias_bs = a->N;
+  p.M = a->M; p.N = a->N; p.K = a->K; p.prologue = a->prologue;
+  const int kt = (p.K + WM_T - 1) / WM_T, nt = (p.N + WM_T - 1) / WM_T;
+  int64_t want = 148 * 8 / ((int64_t)kt * nt * a->batch);
+  if (want < 1) want = 1;
+  const int64_t max_split = (p.M + 511) / 512;
+  if (want > max_split) want = max_split;
+  if (want > 4096) want = 4096;
+  p.rows_per_cta = ((p.M + want - 1) / want + WM_MC - 1) / WM_MC * WM_MC;
+  p.msplit = (int)((p.M + p.rows_per_cta - 1) / p.rows_per_cta);
+  dim3 grid(kt, nt, a->batch * p.msplit);
+  wgrad_mma_kernel<<<grid, WM_THREADS, 0, st>>>(p);
+  return check_launch("linear_wgrad");
+}
+
+}  // namespace tfswa
