@@ -86,6 +86,20 @@ class LinearFn(torch.autograd.Function):
         return dx, dw, db, None, dr1, dr2, None, None, None
 
 
+class GeluFn(torch.autograd.Function):
+    """h = GELU(u) as its own node (bf16 training path): keeping h lets fc2 run forward, data- and weight-gradient on
+    the tensor-core kernels with a plain A operand instead of the CUDA-core GEMM with a GELU-on-load prologue."""
+    @staticmethod
+    def forward(ctx, u):
+        ctx.save_for_backward(u)
+        return ops.affine_act(u, None, None, epilogue=L.EPI_GELU)
+
+    @staticmethod
+    def backward(ctx, dh):
+        (u,) = ctx.saved_tensors
+        return ops.act_bwd(_contig(dh), u, 0)
+
+
 class AttentionFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, qkv, pad_kv, rel_bias, B, H, W, C, heads, geom, ws, shift, use_shift_mask):

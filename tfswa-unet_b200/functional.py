@@ -87,6 +87,14 @@ def linear(x: Tensor, lw: LinW, *, prologue: int = 0, epilogue: int = 0,
     return ops.linear(x, w, bias, prologue=prologue, epilogue=epilogue, row_stats=row_stats, r1=r1, r2=r2)
 
 
+def gelu(u: Tensor) -> Tensor:
+    """exact erf GELU of a dense token tensor (own autograd node when a gradient is needed)"""
+    if _needs_grad(u):
+        from .autograd import GeluFn
+        return GeluFn.apply(u)
+    return ops.affine_act(u, None, None, epilogue=L.EPI_GELU)
+
+
 USE_FUSED_TAIL = True   # one kernel for proj + residual + LN + MLP + residual at C in {32, 64, 128} (inference, bf16)
 FUSED_TAIL_WIDTHS = (32, 64, 128)
 
