@@ -244,6 +244,10 @@ extern "C" int tfswa_attn_bwd(const tfswa_attn_args* a, const void* dout, void* 
     TFSWA_REQUIRE((p.Hp == a->H && p.Wp == a->W) || a->pad_kv, "attn_bwd: padded windows need pad_kv");
   }
   cudaStream_t st = (cudaStream_t)stream;
+  if (a->dtype == TFSWA_BF16 && a->geom != TFSWA_GEOM_SWA) {       // tensor-core path (attention_bwd_mma.cu); 1 = not covered
+    const int rc = attn_bwd_mma_bf16(p, st);
+    if (rc != 1) return rc;
+  }
 #define TFSWA_ATTN_D(T)                                       \
   switch (D) {                                                \
     case 4: return launch_attn_bwd<T, 4>(p, st);              \

@@ -1,0 +1,425 @@
+// Backward of the axial (TSA / FSA) attention on warp-level tensor-core MMAs, bf16 activations, head_dim 4 / 8 / 16
+// (autograd of attention.py:70-85 through the same index maps as the forward).  Flash-style recomputation from q, k and
+// the saved log2-sum-exp, everything in the FlashAttention-2 register layout (no N x N tensor, no atomics):
+//     s = q.k * scale,  p = exp2(s*log2e - lse),  dp = dO.v,  ds = p (dp - D),  D_i = dO_i . O_i
+//     dq_i = scale * sum_j ds_ij k_j        (dq kernel: a warp owns 16 query rows of one head, streams 64-key tiles)
+//     dk_j = scale * sum_i ds_ij q_i,  dv_j = sum_i p_ij dO_i
+//                                           (dkv kernel: a warp owns 16 keys of one head, streams 64-query tiles)
+// In the dq kernel S = Q K^T and dP = dO V^T are two MMAs per 8 keys, dS is re-packed in place as the A operand of
+// dQ += dS K.  The dkv kernel works on the transposed problem (S^T = K Q^T, dP^T = V dO^T), so P^T and dS^T come out of
+// the accumulators already in A-operand layout for dV += P^T dO and dK += dS^T Q.  Operands with the reduction index
+// along tokens are read from the token-major shared-memory tiles with ldmatrix.trans.
+// One CTA = one sequence x 64 rows x 8 heads (warp = head); tiles arrive by cp.async into a 3-deep ring.
+// Replaces the CUDA-core attn_bwd_dq/dkv kernels for these shapes (55 % of a bf16 training step before).
+#include "attn_common.cuh"
+
+namespace tfswa {
+
+namespace {
+
+__device__ __forceinline__ void b_mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void b_mma16816_z(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+               : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "f"(0.f));
+}
+__device__ __forceinline__ void b_mma1688_z(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t b0) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%7,%7,%7,%7};"
+               : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+               : "r"(a0), "r"(a1), "r"(b0), "f"(0.f));
+}
+__device__ __forceinline__ void b_ldsm_x2_trans(uint32_t& r0, uint32_t& r1, const void* smem_row) {
+  const uint32_t addr = (uint32_t)__cvta_generic_to_shared(smem_row);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
+}
+__device__ __forceinline__ uint32_t b_pack(float lo, float hi) {
+  uint32_t y;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(y) : "f"(hi), "f"(lo));
+  return y;
+}
+__device__ __forceinline__ void b_cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void b_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void b_cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+constexpr int BW_T = 64;             // rows per streamed tile
+constexpr int BW_THREADS = 256;      // 8 warps = 8 heads
+template <int D> __host__ __device__ constexpr int bw_mt() { return D == 16 ? 2 : 4; }   // 16-row tiles owned by a warp (register budget)
+
+// S-type product of one 16-row A fragment set against 8 columns (one n-tile): D <= 8 uses one k8 step
+template <int D>
+__device__ __forceinline__ void s_mma(float (&d)[4], const uint32_t (&a)[(D + 15) / 16][4], const uint32_t (&b)[(D + 15) / 16][2]) {
+  if (D <= 8) {
+    b_mma1688_z(d, a[0][0], a[0][1], b[0][0]);
+  } else {
+    b_mma16816_z(d, a[0], b[0][0], b[0][1]);
+#pragma unroll
+    for (int ks = 1; ks < (D + 15) / 16; ++ks) b_mma16816(d, a[ks], b[ks][0], b[ks][1]);
+  }
+}
+
+// A-operand fragments (16 rows x head dims) of rows (r0 + g, r0 + g + 8) of a token-major global tensor; absent rows = 0
+template <int D>
+__device__ __forceinline__ void load_a_frag(uint32_t (&a)[(D + 15) / 16][4], const bf16* base, int64_t ld, int64_t tok0, int64_t tok1,
+                                            bool ok0, bool ok1, int t) {
+#pragma unroll
+  for (int ks = 0; ks < (D + 15) / 16; ++ks) {
+#pragma unroll
+    for (int hi = 0; hi < 2; ++hi) {
+      const int dcol = ks * 16 + hi * 8 + 2 * t;
+      a[ks][hi * 2 + 0] = (dcol < D && ok0) ? *reinterpret_cast<const uint32_t*>(base + tok0 * ld + dcol) : 0u;
+      a[ks][hi * 2 + 1] = (dcol < D && ok1) ? *reinterpret_cast<const uint32_t*>(base + tok1 * ld + dcol) : 0u;
+    }
+  }
+}
+
+}  // namespace
+
+template <int D> __host__ __device__ constexpr int bw_smem_bytes() { return 3 * 2 * BW_T * (8 * D + 8) * 2; }
+
+// ------------------------------------------------------------------------------------------------
+// dq (and D_i = dO_i . O_i): grid (ceil(N/64), sequences, heads/8)
+// ------------------------------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_dq_mma_kernel(const AttnParams p) {
+  constexpr int CS = 8 * D, PITCH = CS + 8, KS = (D + 15) / 16, DN = (D + 7) / 8, CPT = CS / 8, MT = bw_mt<D>();
+  extern __shared__ __align__(16) uint8_t bw_smem[];
+  typedef bf16 (*tile_t)[BW_T][PITCH];
+  tile_t Ks = reinterpret_cast<tile_t>(bw_smem);
+  tile_t Vs = reinterpret_cast<tile_t>(bw_smem + 3 * BW_T * PITCH * 2);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+  const int row = blockIdx.y, q0 = blockIdx.x * (16 * MT), slab = blockIdx.z;
+  const int N = p.geom == TFSWA_GEOM_TSA ? p.H : p.W;
+  const int T = (N + BW_T - 1) / BW_T;
+  int64_t tok_base, tok_stride;
+  if (p.geom == TFSWA_GEOM_TSA) { const int b = row / p.W; tok_base = (int64_t)b * p.H * p.W + (row - b * p.W); tok_stride = p.W; }
+  else { tok_base = (int64_t)row * p.W; tok_stride = 1; }
+  const bf16* qkv = (const bf16*)p.qkv;
+  const int cbase = warp * D, head = slab * 8 + warp;
+  const int mt_valid = min(MT, (N - q0 + 15) / 16);
+
+  auto stage = [&](int tt, int b) {
+    if (tt < T) {
+      for (int v = tid; v < BW_T * 2 * CPT; v += BW_THREADS) {
+        const int j = v / (2 * CPT), rem = v - j * 2 * CPT, part = rem / CPT, chunk = rem - part * CPT;
+        const int key = tt * BW_T + j;
+        bf16* dst = part ? &Vs[b][j][chunk * 8] : &Ks[b][j][chunk * 8];
+        if (key < N) b_cp_async16(dst, qkv + (tok_base + (int64_t)key * tok_stride) * p.ldq + (1 + part) * p.C + slab * CS + chunk * 8);
+        else *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
+      }
+    }
+    b_cp_commit();
+  };
+  stage(0, 0);
+  stage(1, 1);
+
+  // ---- my rows: Q and dO fragments, lse, D = dO . O ----
+  uint32_t qa[MT][KS][4], ga[MT][KS][4];
+  float lse[MT][2], dsm[MT][2], dq[MT][DN][4];
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt) {
+    const int qn0 = q0 + mt * 16 + g, qn1 = qn0 + 8;
+    const bool ok0 = qn0 < N, ok1 = qn1 < N;
+    const int64_t tok0 = tok_base + (int64_t)(ok0 ? qn0 : 0) * tok_stride, tok1 = tok_base + (int64_t)(ok1 ? qn1 : 0) * tok_stride;
+    load_a_frag<D>(qa[mt], qkv + slab * CS + cbase, p.ldq, tok0, tok1, ok0, ok1, t);
+    load_a_frag<D>(ga[mt], (const bf16*)p.dout + slab * CS + cbase, p.ldo, tok0, tok1, ok0, ok1, t);
+    uint32_t oa[KS][4];
+    load_a_frag<D>(oa, (const bf16*)p.o + slab * CS + cbase, p.ldo, tok0, tok1, ok0, ok1, t);
+    float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+#pragma unroll
+      for (int hi = 0; hi < 2; ++hi) {
+        const uint32_t g0 = ga[mt][ks][hi * 2], g1 = ga[mt][ks][hi * 2 + 1], o0 = oa[ks][hi * 2], o1 = oa[ks][hi * 2 + 1];
+        d0 += __uint_as_float(g0 << 16) * __uint_as_float(o0 << 16) + __uint_as_float(g0 & 0xFFFF0000u) * __uint_as_float(o0 & 0xFFFF0000u);
+        d1 += __uint_as_float(g1 << 16) * __uint_as_float(o1 << 16) + __uint_as_float(g1 & 0xFFFF0000u) * __uint_as_float(o1 & 0xFFFF0000u);
+      }
+    }
+    d0 += __shfl_xor_sync(0xffffffffu, d0, 1); d0 += __shfl_xor_sync(0xffffffffu, d0, 2);
+    d1 += __shfl_xor_sync(0xffffffffu, d1, 1); d1 += __shfl_xor_sync(0xffffffffu, d1, 2);
+    dsm[mt][0] = d0; dsm[mt][1] = d1;
+    lse[mt][0] = ok0 ? p.lse[tok0 * p.heads + head] : CUDART_INF_F;
+    lse[mt][1] = ok1 ? p.lse[tok1 * p.heads + head] : CUDART_INF_F;
+    if (t == 0) {
+      if (ok0) p.dsum[tok0 * p.heads + head] = d0;
+      if (ok1) p.dsum[tok1 * p.heads + head] = d1;
+    }
+#pragma unroll
+    for (int dn = 0; dn < DN; ++dn) dq[mt][dn][0] = dq[mt][dn][1] = dq[mt][dn][2] = dq[mt][dn][3] = 0.f;
+  }
+  const float c = p.qscale;
+
+  for (int tt = 0; tt < T; ++tt) {
+    b_cp_wait<1>();
+    __syncthreads();
+    stage(tt + 2, (tt + 2) % 3);
+    const int b = tt % 3;
+    const int kcount = min(BW_T, N - tt * BW_T);
+    // K and V as "n = key" operands (for S and dP), K as "k = key" operand (for dQ)
+    uint32_t kb[8][KS][2], vb[8][KS][2], kt[4][DN][2];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        const int dcol = ks * 16 + 2 * t;
+        kb[nt][ks][0] = dcol < D ? *reinterpret_cast<const uint32_t*>(&Ks[b][nt * 8 + g][cbase + dcol]) : 0u;
+        kb[nt][ks][1] = dcol + 8 < D ? *reinterpret_cast<const uint32_t*>(&Ks[b][nt * 8 + g][cbase + dcol + 8]) : 0u;
+        vb[nt][ks][0] = dcol < D ? *reinterpret_cast<const uint32_t*>(&Vs[b][nt * 8 + g][cbase + dcol]) : 0u;
+        vb[nt][ks][1] = dcol + 8 < D ? *reinterpret_cast<const uint32_t*>(&Vs[b][nt * 8 + g][cbase + dcol + 8]) : 0u;
+      }
+    }
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+      for (int dn = 0; dn < DN; ++dn) {
+        const int col = D >= 8 ? cbase + dn * 8 : (cbase & ~7);
+        b_ldsm_x2_trans(kt[kk][dn][0], kt[kk][dn][1], &Ks[b][kk * 16 + (lane & 15)][col]);
+      }
+    }
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+      if (mt < mt_valid) {
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          uint32_t pa[4];
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            const int nt = 2 * kk + half;
+            float s[4], dp[4];
+            s_mma<D>(s, qa[mt], kb[nt]);
+            s_mma<D>(dp, ga[mt], vb[nt]);
+            float ds[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int h2 = i >> 1;
+              float pw = fast_exp2(fmaf(s[i], c, -lse[mt][h2]));
+              if (nt * 8 + 2 * t + (i & 1) >= kcount) pw = 0.f;     // absent keys of the last tile
+              ds[i] = pw * (dp[i] - dsm[mt][h2]);
+            }
+            pa[half * 2 + 0] = b_pack(ds[0], ds[1]);
+            pa[half * 2 + 1] = b_pack(ds[2], ds[3]);
+          }
+#pragma unroll
+          for (int dn = 0; dn < DN; ++dn) b_mma16816(dq[mt][dn], pa, kt[kk][dn][0], kt[kk][dn][1]);
+        }
+      }
+    }
+  }
+  b_cp_wait<0>();
+  // ---- dq = scale * acc ----
+  bf16* dqkv = (bf16*)p.dqkv;
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+    for (int h2 = 0; h2 < 2; ++h2) {
+      const int qn = q0 + mt * 16 + g + h2 * 8;
+      if (qn >= N) continue;
+      const int64_t tok = tok_base + (int64_t)qn * tok_stride;
+      if (D >= 8) {
+#pragma unroll
+        for (int dn = 0; dn < DN; ++dn)
+          *reinterpret_cast<uint32_t*>(dqkv + tok * p.ldq + slab * CS + cbase + dn * 8 + 2 * t) =
+              b_pack(dq[mt][dn][h2 * 2] * p.scale, dq[mt][dn][h2 * 2 + 1] * p.scale);
+      } else {
+        const int first = cbase & 7;
+        if (2 * t >= first && 2 * t < first + 4)
+          *reinterpret_cast<uint32_t*>(dqkv + tok * p.ldq + slab * CS + (cbase & ~7) + 2 * t) =
+              b_pack(dq[mt][0][h2 * 2] * p.scale, dq[mt][0][h2 * 2 + 1] * p.scale);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// dk, dv: grid (ceil(N/64), sequences, heads/8); needs dsum from the dq kernel
+// ------------------------------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_dkv_mma_kernel(const AttnParams p) {
+  constexpr int CS = 8 * D, PITCH = CS + 8, KS = (D + 15) / 16, DN = (D + 7) / 8, CPT = CS / 8, MT = bw_mt<D>();
+  extern __shared__ __align__(16) uint8_t bw_smem[];
+  typedef bf16 (*tile_t)[BW_T][PITCH];
+  tile_t Qs = reinterpret_cast<tile_t>(bw_smem);
+  tile_t Gs = reinterpret_cast<tile_t>(bw_smem + 3 * BW_T * PITCH * 2);
+  __shared__ __align__(8) float Ls[3][8][BW_T], Ds[3][8][BW_T];          // [ring slot][head][query]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+  const int row = blockIdx.y, k0 = blockIdx.x * (16 * MT), slab = blockIdx.z;
+  const int N = p.geom == TFSWA_GEOM_TSA ? p.H : p.W;
+  const int T = (N + BW_T - 1) / BW_T;
+  int64_t tok_base, tok_stride;
+  if (p.geom == TFSWA_GEOM_TSA) { const int b = row / p.W; tok_base = (int64_t)b * p.H * p.W + (row - b * p.W); tok_stride = p.W; }
+  else { tok_base = (int64_t)row * p.W; tok_stride = 1; }
+  const bf16* qkv = (const bf16*)p.qkv;
+  const bf16* dout = (const bf16*)p.dout;
+  const int cbase = warp * D;
+  const int mt_valid = min(MT, (N - k0 + 15) / 16);
+
+  auto stage = [&](int tt, int b) {
+    if (tt < T) {
+      for (int v = tid; v < BW_T * 2 * CPT; v += BW_THREADS) {
+        const int j = v / (2 * CPT), rem = v - j * 2 * CPT, part = rem / CPT, chunk = rem - part * CPT;
+        const int qn = tt * BW_T + j;
+        bf16* dst = part ? &Gs[b][j][chunk * 8] : &Qs[b][j][chunk * 8];
+        if (qn < N) {
+          const int64_t tok = tok_base + (int64_t)qn * tok_stride;
+          b_cp_async16(dst, part ? dout + tok * p.ldo + slab * CS + chunk * 8 : qkv + tok * p.ldq + slab * CS + chunk * 8);
+        } else {
+          *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
+        }
+      }
+      for (int v = tid; v < BW_T * 8; v += BW_THREADS) {                 // lse / D of the tile's queries, all 8 heads
+        const int j = v >> 3, h = v & 7;
+        const int qn = tt * BW_T + j;
+        float l = CUDART_INF_F, d = 0.f;                                 // +inf -> p = 0 for absent queries
+        if (qn < N) {
+          const int64_t tok = tok_base + (int64_t)qn * tok_stride;
+          l = p.lse[tok * p.heads + slab * 8 + h];
+          d = p.dsum[tok * p.heads + slab * 8 + h];
+        }
+        Ls[b][h][j] = l; Ds[b][h][j] = d;
+      }
+    }
+    b_cp_commit();
+  };
+  stage(0, 0);
+  stage(1, 1);
+
+  // ---- my keys: K and V fragments as A operands (rows = keys) ----
+  uint32_t ka[MT][KS][4], va[MT][KS][4];
+  float dk[MT][DN][4], dv[MT][DN][4];
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt) {
+    const int kn0 = k0 + mt * 16 + g, kn1 = kn0 + 8;
+    const bool ok0 = kn0 < N, ok1 = kn1 < N;
+    const int64_t tok0 = tok_base + (int64_t)(ok0 ? kn0 : 0) * tok_stride, tok1 = tok_base + (int64_t)(ok1 ? kn1 : 0) * tok_stride;
+    load_a_frag<D>(ka[mt], qkv + p.C + slab * CS + cbase, p.ldq, tok0, tok1, ok0, ok1, t);
+    load_a_frag<D>(va[mt], qkv + 2 * p.C + slab * CS + cbase, p.ldq, tok0, tok1, ok0, ok1, t);
+#pragma unroll
+    for (int dn = 0; dn < DN; ++dn) {
+      dk[mt][dn][0] = dk[mt][dn][1] = dk[mt][dn][2] = dk[mt][dn][3] = 0.f;
+      dv[mt][dn][0] = dv[mt][dn][1] = dv[mt][dn][2] = dv[mt][dn][3] = 0.f;
+    }
+  }
+  const float c = p.qscale;
+
+  for (int tt = 0; tt < T; ++tt) {
+    b_cp_wait<1>();
+    __syncthreads();
+    stage(tt + 2, (tt + 2) % 3);
+    const int b = tt % 3;
+    // Q and dO as "n = query" operands (S^T, dP^T) and as "k = query" operands (dK, dV)
+    uint32_t qb[8][KS][2], gb[8][KS][2], qt[4][DN][2], gt[4][DN][2];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        const int dcol = ks * 16 + 2 * t;
+        qb[nt][ks][0] = dcol < D ? *reinterpret_cast<const uint32_t*>(&Qs[b][nt * 8 + g][cbase + dcol]) : 0u;
+        qb[nt][ks][1] = dcol + 8 < D ? *reinterpret_cast<const uint32_t*>(&Qs[b][nt * 8 + g][cbase + dcol + 8]) : 0u;
+        gb[nt][ks][0] = dcol < D ? *reinterpret_cast<const uint32_t*>(&Gs[b][nt * 8 + g][cbase + dcol]) : 0u;
+        gb[nt][ks][1] = dcol + 8 < D ? *reinterpret_cast<const uint32_t*>(&Gs[b][nt * 8 + g][cbase + dcol + 8]) : 0u;
+      }
+    }
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+      for (int dn = 0; dn < DN; ++dn) {
+        const int col = D >= 8 ? cbase + dn * 8 : (cbase & ~7);
+        b_ldsm_x2_trans(qt[kk][dn][0], qt[kk][dn][1], &Qs[b][kk * 16 + (lane & 15)][col]);
+        b_ldsm_x2_trans(gt[kk][dn][0], gt[kk][dn][1], &Gs[b][kk * 16 + (lane & 15)][col]);
+      }
+    }
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+      if (mt < mt_valid) {
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          uint32_t pa[4], da[4];
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            const int nt = 2 * kk + half;
+            float s[4], dp[4];
+            s_mma<D>(s, ka[mt], qb[nt]);                               // S^T: rows = my keys, columns = queries
+            s_mma<D>(dp, va[mt], gb[nt]);                              // dP^T
+            const float2 l2 = *reinterpret_cast<const float2*>(&Ls[b][warp][nt * 8 + 2 * t]);
+            const float2 d2 = *reinterpret_cast<const float2*>(&Ds[b][warp][nt * 8 + 2 * t]);
+            float pw[4], ds[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              pw[i] = fast_exp2(fmaf(s[i], c, -((i & 1) ? l2.y : l2.x)));
+              ds[i] = pw[i] * (dp[i] - ((i & 1) ? d2.y : d2.x));
+            }
+            pa[half * 2 + 0] = b_pack(pw[0], pw[1]); pa[half * 2 + 1] = b_pack(pw[2], pw[3]);
+            da[half * 2 + 0] = b_pack(ds[0], ds[1]); da[half * 2 + 1] = b_pack(ds[2], ds[3]);
+          }
+#pragma unroll
+          for (int dn = 0; dn < DN; ++dn) {
+            b_mma16816(dv[mt][dn], pa, gt[kk][dn][0], gt[kk][dn][1]);
+            b_mma16816(dk[mt][dn], da, qt[kk][dn][0], qt[kk][dn][1]);
+          }
+        }
+      }
+    }
+  }
+  b_cp_wait<0>();
+  bf16* dqkv = (bf16*)p.dqkv;
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+    for (int h2 = 0; h2 < 2; ++h2) {
+      const int kn = k0 + mt * 16 + g + h2 * 8;
+      if (kn >= N) continue;
+      const int64_t tok = tok_base + (int64_t)kn * tok_stride;
+      bf16* base = dqkv + tok * p.ldq + slab * CS;
+      if (D >= 8) {
+#pragma unroll
+        for (int dn = 0; dn < DN; ++dn) {
+          const int col = cbase + dn * 8 + 2 * t;
+          *reinterpret_cast<uint32_t*>(base + p.C + col) = b_pack(dk[mt][dn][h2 * 2] * p.scale, dk[mt][dn][h2 * 2 + 1] * p.scale);
+          *reinterpret_cast<uint32_t*>(base + 2 * p.C + col) = b_pack(dv[mt][dn][h2 * 2], dv[mt][dn][h2 * 2 + 1]);
+        }
+      } else {
+        const int first = cbase & 7;
+        if (2 * t >= first && 2 * t < first + 4) {
+          const int col = (cbase & ~7) + 2 * t;
+          *reinterpret_cast<uint32_t*>(base + p.C + col) = b_pack(dk[mt][0][h2 * 2] * p.scale, dk[mt][0][h2 * 2 + 1] * p.scale);
+          *reinterpret_cast<uint32_t*>(base + 2 * p.C + col) = b_pack(dv[mt][0][h2 * 2], dv[mt][0][h2 * 2 + 1]);
+        }
+      }
+    }
+  }
+}
+
+template <int D>
+static int launch_bwd_mma(const AttnParams& p, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e1 = cudaFuncSetAttribute(attn_bwd_dq_mma_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, bw_smem_bytes<D>());
+    cudaError_t e2 = cudaFuncSetAttribute(attn_bwd_dkv_mma_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, bw_smem_bytes<D>());
+    if (e1 != cudaSuccess || e2 != cudaSuccess) { set_error("attn_bwd_mma: cudaFuncSetAttribute failed"); return TFSWA_ECUDA; }
+    attr_set = true;
+  }
+  const int N = p.geom == TFSWA_GEOM_TSA ? p.H : p.W;
+  const int rows = p.geom == TFSWA_GEOM_TSA ? p.B * p.W : p.B * p.H;
+  dim3 grid((N + 16 * bw_mt<D>() - 1) / (16 * bw_mt<D>()), rows, p.heads / 8);
+  attn_bwd_dq_mma_kernel<D><<<grid, BW_THREADS, bw_smem_bytes<D>(), st>>>(p);
+  attn_bwd_dkv_mma_kernel<D><<<grid, BW_THREADS, bw_smem_bytes<D>(), st>>>(p);
+  return check_launch("attn_bwd_mma");
+}
+
+// bf16 axial attention backward; returns 1 when the shape is not covered (caller falls back to the CUDA-core kernels)
+int attn_bwd_mma_bf16(const AttnParams& p, cudaStream_t st) {
+  const int D = p.C / p.heads;
+  const int rows = p.geom == TFSWA_GEOM_TSA ? p.B * p.W : p.B * p.H;
+  if (p.geom == TFSWA_GEOM_SWA || p.heads % 8 != 0 || rows > 65535 || (D != 4 && D != 8 && D != 16)) return 1;
+  if ((p.ldq % 8) || (p.ldo % 8) || (((uintptr_t)p.qkv | (uintptr_t)p.dqkv | (uintptr_t)p.dout) & 15) || (((uintptr_t)p.o) & 3)) return 1;
+  if (D == 4) return launch_bwd_mma<4>(p, st);
+  if (D == 8) return launch_bwd_mma<8>(p, st);
+  return launch_bwd_mma<16>(p, st);
+}
+
+}  // namespace tfswa
