@@ -96,7 +96,7 @@ __device__ __forceinline__ float gelu_erf_fast(float x) {
 }
 // GELU of the MLP hidden activations in the fused bf16 tail kernels (the value is rounded to bf16 and consumed by fc2):
 // x * Phi(x) with Phi(x) = 0.5 (1 + tanh(u)), u = x (c1 + c3 x^2 + c5 x^4) FITTED TO THE ERF FORM (not the classic
-// "tanh GELU": max |error| of the fit against erf-GELU is 3.0e-5 over the reals, tests/test_oracle_golden.py pins it) and
+// "tanh GELU": max |error| of the fit against erf-GELU is 3.0e-5 over the reals, tests/test_gelu_fit.py pins it) and
 // one MUFU.TANH (2^-11 relative).  9 instructions / 1 MUFU instead of 17 / 2: the tail kernels are bound by exactly this.
 // Total deviation from erf-GELU <= 3e-5 + 2.5e-4 min(|x|, 6) under the worst-case tanh error model: below the bf16
 // rounding of the result for x > -1.15 and below 1.5e-3 absolute everywhere; measured end to end (tail output against the
