@@ -231,6 +231,24 @@ int tfswa_head_tail_bwd(const void* v, const float* scale, const float* shift, c
                         const float* dmasks_nchw, const float* dlogits_nchw, void* dv, float* dw3, float* db3, float* dscale,
                         float* dshift, int32_t B, int32_t H, int32_t W, int32_t C, int32_t Cout, int32_t dtype, void* stream);
 
+/* =====================================================================================================
+ * Optimiser step over a flat fp32 parameter arena (row f1 of SURVEY 8f).  Replaces
+ * torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm) + optimizer.step() of src/training/trainer.py:214-219
+ * for the AdamW of scripts/train.py:251-255 (one parameter group, decoupled weight decay on every parameter).
+ * All buffers hold n fp32 elements (n % 4 == 0, 16-byte aligned); nothing synchronises with the host.
+ * ===================================================================================================== */
+
+/* *sumsq = sum_i g[i]^2 (zeroed by the call; double so that the order of the per-CTA atomics is immaterial) */
+int tfswa_grad_sumsq(const float* g, int64_t n, double* sumsq, void* stream);
+/* g_eff = g * grad_scale * min(1, max_norm / (sqrt(*sumsq)*grad_scale + 1e-6))   (max_norm <= 0: no clipping;
+ *         grad_scale = 1/world when g holds the all-reduced SUM of the per-rank gradients)
+ * p *= 1 - lr*weight_decay;  m = beta1 m + (1-beta1) g_eff;  v = beta2 v + (1-beta2) g_eff^2;
+ * p -= lr/(1-beta1^step) * m / (sqrt(v)/sqrt(1-beta2^step) + eps)                 (torch.optim.AdamW, step >= 1)
+ * norm_out (optional, device) receives the unclipped total norm; a non-finite norm skips the update. */
+int tfswa_adamw_clip_step(float* p, const float* g, float* m, float* v, int64_t n, const double* sumsq, float* norm_out,
+                          float grad_scale, float max_norm, float lr, float beta1, float beta2, float eps, float weight_decay,
+                          int64_t step, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
