@@ -65,3 +65,48 @@ def test_window_features_stay_on_simt():
     finally:
         ops.enable_timing(False)
     assert tags[0].startswith("attn[swa")
+
+
+@pytest.mark.parametrize("B,H,W,C,shift,heads", [
+    (1, 8, 8, 32, 0, 8), (2, 13, 21, 32, 4, 8),       # head_dim 4: one window; padded + shifted windows
+    (1, 24, 16, 64, 4, 8), (2, 11, 30, 64, 0, 8),     # head_dim 8
+    (1, 16, 24, 128, 4, 8), (1, 9, 17, 128, 0, 8),    # head_dim 16: two 32-row CTAs per window
+    (1, 40, 16, 64, 4, 16),                           # two 8-head slabs
+])
+def test_window_attention_backward_mma_matches_simt(B, H, W, C, shift, heads):
+    """tfswa_attn_bwd on SW-MSA windows: the warp-MMA kernels (default for bf16) against the CUDA-core kernels
+    (TFSWA_ATTN_BWD_SIMT=1) on the same q|k|v, output gradient and saved log-sum-exp; pad-token gradients included."""
+    import os
+    from tfswa_unet_b200 import ops
+    M = B * H * W
+    qkv = seeded((M, 3 * C), 41, 1.2).cuda().to(torch.bfloat16)
+    dout = seeded((M, C), 42, 1.0).cuda().to(torch.bfloat16)
+    pad_kv = seeded((2 * C,), 43, 0.7).cuda().float().contiguous()
+    out = torch.empty((M, C), dtype=torch.bfloat16, device="cuda")
+    lse = torch.empty((M, heads), dtype=torch.float32, device="cuda")
+    ops.attention(qkv, out, B, H, W, C, heads, 2, ws=8, shift=shift, pad_kv=pad_kv, lse=lse)
+    res = {}
+    for mode in ("mma", "simt"):
+        dqkv = torch.full((M, 3 * C), float("nan"), dtype=torch.bfloat16, device="cuda")
+        dsum = torch.zeros((M, heads), dtype=torch.float32, device="cuda")
+        dpad = torch.zeros((2 * C,), dtype=torch.float32, device="cuda")
+        if mode == "simt":
+            os.environ["TFSWA_ATTN_BWD_SIMT"] = "1"
+        try:
+            ops.attention_bwd(qkv, out, lse, dout, dqkv, dsum, B, H, W, C, heads, 2, ws=8, shift=shift, pad_kv=pad_kv, dpad=dpad)
+            torch.cuda.synchronize()
+        finally:
+            os.environ.pop("TFSWA_ATTN_BWD_SIMT", None)
+        res[mode] = (dqkv.float(), dsum, dpad)
+    (a, sa, pa), (b, sb, pb) = res["mma"], res["simt"]
+    assert torch.isfinite(a).all(), "every token's dq|dk|dv must be written"
+    for name, lo in (("dq", 0), ("dk", C), ("dv", 2 * C)):
+        x, y = a[:, lo:lo + C], b[:, lo:lo + C]
+        rel = float((x - y).norm() / y.norm())
+        assert rel <= 2e-2, f"{name}: mma vs simt rel-L2 {rel:.3e}"          # P, dS rounded to bf16 as MMA operands
+    assert float((sa - sb).abs().max()) <= 1e-3 * float(sb.abs().max()) + 1e-5
+    if (H % 8) or (W % 8):
+        assert float(pb.abs().max()) > 0
+        assert float((pa - pb).norm() / pb.norm()) <= 2e-2, "pad-token gradient"
+    else:
+        assert float(pa.abs().max()) == 0.0

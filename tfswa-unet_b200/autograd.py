@@ -215,6 +215,15 @@ def conv_layout(w_oihw: Tensor, kind: str) -> Tensor:
     return up_phase_weights(w_oihw)
 
 
+def _conv_any(x: Tensor, wl: Tensor, bias: Tensor, kind: int, out_hw) -> Tensor:
+    """plain convolution (no epilogue / statistics) on the best available kernel: tcgen05 implicit GEMM for bf16
+    activations with tileable channel counts, CUDA-core implicit GEMM otherwise (the data gradients of ConvFn)"""
+    from . import functional as Fn
+    if (Fn.USE_TC and x.dtype == torch.bfloat16 and x.shape[1] % 32 == 0 and bias.shape[0] % 16 == 0 and bias.shape[0] <= 256):
+        return ops.conv_tc(x, wl.to(torch.bfloat16).contiguous(), bias, kind, out_hw)
+    return ops.conv(x, wl, bias, kind, out_hw)
+
+
 class ConvFn(torch.autograd.Function):
     """w is Cout-first OIHW (a ConvTranspose2d weight is passed already permuted to Cout-first)."""
 
@@ -255,11 +264,11 @@ class ConvFn(torch.autograd.Function):
             zb = torch.zeros((x.shape[1],), dtype=torch.float32, device=x.device)
             hw = tuple(x.shape[2:])
             if kind == "down":      # data gradient of the stride-2 conv = transposed conv (kind 2) with (Cin_d, Cout_d) swapped
-                dx = ops.conv(gpre, up_phase_weights(w.permute(1, 0, 2, 3)), zb, 2, hw)
+                dx = _conv_any(gpre, up_phase_weights(w.permute(1, 0, 2, 3)), zb, 2, hw)
             elif kind == "up":      # data gradient of the transposed conv = stride-2 conv (kind 1)
-                dx = ops.conv(gpre, w.permute(1, 2, 3, 0).contiguous(), zb, 1, hw)
+                dx = _conv_any(gpre, w.permute(1, 2, 3, 0).contiguous(), zb, 1, hw)
             else:                   # 3x3 s1 p1: flipped taps, swapped channels
-                dx = ops.conv(gpre, w.flip(2, 3).permute(1, 2, 3, 0).contiguous(), zb, 0, hw)
+                dx = _conv_any(gpre, w.flip(2, 3).permute(1, 2, 3, 0).contiguous(), zb, 0, hw)
         return dx, dw, db, None, None, None, None, None
 
 

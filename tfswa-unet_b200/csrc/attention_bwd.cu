@@ -7,6 +7,7 @@
 // With s = scale * q.k, p = softmax(s):  ds = p * (dO.v - D),  dq = scale * sum_j ds k_j,
 // dk = scale * sum_i ds q_i,  dv = sum_i p dO_i.
 #include "attn_common.cuh"
+#include <stdlib.h>
 
 namespace tfswa {
 
@@ -244,7 +245,7 @@ extern "C" int tfswa_attn_bwd(const tfswa_attn_args* a, const void* dout, void* 
     TFSWA_REQUIRE((p.Hp == a->H && p.Wp == a->W) || a->pad_kv, "attn_bwd: padded windows need pad_kv");
   }
   cudaStream_t st = (cudaStream_t)stream;
-  if (a->dtype == TFSWA_BF16 && a->geom != TFSWA_GEOM_SWA) {       // tensor-core path (attention_bwd_mma.cu); 1 = not covered
+  if (a->dtype == TFSWA_BF16 && !getenv("TFSWA_ATTN_BWD_SIMT")) {  // tensor-core path (attention_bwd_mma.cu); 1 = not covered
     const int rc = attn_bwd_mma_bf16(p, st);
     if (rc != 1) return rc;
   }

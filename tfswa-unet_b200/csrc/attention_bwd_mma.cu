@@ -1,5 +1,7 @@
-// Backward of the axial (TSA / FSA) attention on warp-level tensor-core MMAs, bf16 activations, head_dim 4 / 8 / 16
-// (autograd of attention.py:70-85 through the same index maps as the forward).  Flash-style recomputation from q, k and
+// Backward of the axial (TSA / FSA) and 8x8-window (SW-MSA) attention on warp-level tensor-core MMAs, bf16 activations,
+// head_dim 4 / 8 / 16 (autograd of attention.py:70-85 through the same index maps as the forward; for windows the
+// pad / roll / partition chain of attention.py:358-375 is the token map, zero-padded tokens are real keys whose k|v is
+// the folded qkv bias `pad_kv` and whose gradient reduces into `dpad`, and are absent as queries: their output is cropped).  Flash-style recomputation from q, k and
 // the saved log2-sum-exp, everything in the FlashAttention-2 register layout (no N x N tensor, no atomics):
 //     s = q.k * scale,  p = exp2(s*log2e - lse),  dp = dO.v,  ds = p (dp - D),  D_i = dO_i . O_i
 //     dq_i = scale * sum_j ds_ij k_j        (dq kernel: a warp owns 16 query rows of one head, streams 64-key tiles)
@@ -9,7 +11,7 @@
 // dQ += dS K.  The dkv kernel works on the transposed problem (S^T = K Q^T, dP^T = V dO^T), so P^T and dS^T come out of
 // the accumulators already in A-operand layout for dV += P^T dO and dK += dS^T Q.  Operands with the reduction index
 // along tokens are read from the token-major shared-memory tiles with ldmatrix.trans.
-// One CTA = one sequence x 64 rows x 8 heads (warp = head); tiles arrive by cp.async into a 3-deep ring.
+// One CTA = one sequence (or window: N = 64, one tile) x 64 rows x 8 heads (warp = head); tiles arrive by cp.async into a 3-deep ring.
 // Replaces the CUDA-core attn_bwd_dq/dkv kernels for these shapes (55 % of a bf16 training step before).
 #include "attn_common.cuh"
 
@@ -78,14 +80,39 @@ __device__ __forceinline__ void load_a_frag(uint32_t (&a)[(D + 15) / 16][4], con
   }
 }
 
+// token of element n of sequence / window `row`.  Returns false when n lies outside the sequence; real = false for the
+// zero-padded tokens of a window (present as keys with k|v = pad_kv, absent as queries).
+template <bool WIN>
+__device__ __forceinline__ bool seq_token(const AttnParams& p, int row, int n, int N, int64_t tok_base, int64_t tok_stride,
+                                          int64_t& tok, bool& real) {
+  tok = 0; real = false;
+  if (n >= N) return false;
+  if (WIN) tok = token_of<true>(p, row, n, real);
+  else { tok = tok_base + (int64_t)n * tok_stride; real = true; }
+  return true;
+}
+
+// rows (0: g, 1: g + 8) of an A fragment set filled from a per-channel fp32 vector (the pad token's k or v)
+template <int D>
+__device__ __forceinline__ void fill_a_frag_row(uint32_t (&a)[(D + 15) / 16][4], const float* vec, int which, int t) {
+#pragma unroll
+  for (int ks = 0; ks < (D + 15) / 16; ++ks) {
+#pragma unroll
+    for (int hi = 0; hi < 2; ++hi) {
+      const int dcol = ks * 16 + hi * 8 + 2 * t;
+      if (dcol < D) a[ks][hi * 2 + which] = b_pack(vec[dcol], vec[dcol + 1]);
+    }
+  }
+}
+
 }  // namespace
 
 template <int D> __host__ __device__ constexpr int bw_smem_bytes() { return 3 * 2 * BW_T * (8 * D + 8) * 2; }
 
 // ------------------------------------------------------------------------------------------------
-// dq (and D_i = dO_i . O_i): grid (ceil(N/64), sequences, heads/8)
+// dq (and D_i = dO_i . O_i): grid (ceil(N/64), sequences, heads/8); windows: (windows, ceil(64/rows per CTA), heads/8)
 // ------------------------------------------------------------------------------------------------
-template <int D>
+template <int D, bool WIN>
 __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_dq_mma_kernel(const AttnParams p) {
   constexpr int CS = 8 * D, PITCH = CS + 8, KS = (D + 15) / 16, DN = (D + 7) / 8, CPT = CS / 8, MT = bw_mt<D>();
   extern __shared__ __align__(16) uint8_t bw_smem[];
@@ -93,12 +120,14 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_dq_mma_kernel(const At
   tile_t Ks = reinterpret_cast<tile_t>(bw_smem);
   tile_t Vs = reinterpret_cast<tile_t>(bw_smem + 3 * BW_T * PITCH * 2);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
-  const int row = blockIdx.y, q0 = blockIdx.x * (16 * MT), slab = blockIdx.z;
-  const int N = p.geom == TFSWA_GEOM_TSA ? p.H : p.W;
+  const int row = WIN ? blockIdx.x : blockIdx.y, q0 = (WIN ? blockIdx.y : blockIdx.x) * (16 * MT), slab = blockIdx.z;
+  const int N = WIN ? p.ws * p.ws : (p.geom == TFSWA_GEOM_TSA ? p.H : p.W);
   const int T = (N + BW_T - 1) / BW_T;
-  int64_t tok_base, tok_stride;
-  if (p.geom == TFSWA_GEOM_TSA) { const int b = row / p.W; tok_base = (int64_t)b * p.H * p.W + (row - b * p.W); tok_stride = p.W; }
-  else { tok_base = (int64_t)row * p.W; tok_stride = 1; }
+  int64_t tok_base = 0, tok_stride = 1;
+  if (!WIN) {
+    if (p.geom == TFSWA_GEOM_TSA) { const int b = row / p.W; tok_base = (int64_t)b * p.H * p.W + (row - b * p.W); tok_stride = p.W; }
+    else { tok_base = (int64_t)row * p.W; }
+  }
   const bf16* qkv = (const bf16*)p.qkv;
   const int cbase = warp * D, head = slab * 8 + warp;
   const int mt_valid = min(MT, (N - q0 + 15) / 16);
@@ -107,10 +136,17 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_dq_mma_kernel(const At
     if (tt < T) {
       for (int v = tid; v < BW_T * 2 * CPT; v += BW_THREADS) {
         const int j = v / (2 * CPT), rem = v - j * 2 * CPT, part = rem / CPT, chunk = rem - part * CPT;
-        const int key = tt * BW_T + j;
         bf16* dst = part ? &Vs[b][j][chunk * 8] : &Ks[b][j][chunk * 8];
-        if (key < N) b_cp_async16(dst, qkv + (tok_base + (int64_t)key * tok_stride) * p.ldq + (1 + part) * p.C + slab * CS + chunk * 8);
-        else *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
+        int64_t tok; bool real;
+        const bool in = seq_token<WIN>(p, row, tt * BW_T + j, N, tok_base, tok_stride, tok, real);
+        if (in && real) {
+          b_cp_async16(dst, qkv + tok * p.ldq + (1 + part) * p.C + slab * CS + chunk * 8);
+        } else if (WIN && in) {                                        // zero-padded window token: k|v = folded qkv bias
+          const float* pk = p.pad_kv + part * p.C + slab * CS + chunk * 8;
+          *reinterpret_cast<uint4*>(dst) = make_uint4(b_pack(pk[0], pk[1]), b_pack(pk[2], pk[3]), b_pack(pk[4], pk[5]), b_pack(pk[6], pk[7]));
+        } else {
+          *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
+        }
       }
     }
     b_cp_commit();
@@ -123,9 +159,9 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_dq_mma_kernel(const At
   float lse[MT][2], dsm[MT][2], dq[MT][DN][4];
 #pragma unroll
   for (int mt = 0; mt < MT; ++mt) {
-    const int qn0 = q0 + mt * 16 + g, qn1 = qn0 + 8;
-    const bool ok0 = qn0 < N, ok1 = qn1 < N;
-    const int64_t tok0 = tok_base + (int64_t)(ok0 ? qn0 : 0) * tok_stride, tok1 = tok_base + (int64_t)(ok1 ? qn1 : 0) * tok_stride;
+    int64_t tok0, tok1; bool r0, r1;
+    const bool ok0 = seq_token<WIN>(p, row, q0 + mt * 16 + g, N, tok_base, tok_stride, tok0, r0) && r0;
+    const bool ok1 = seq_token<WIN>(p, row, q0 + mt * 16 + g + 8, N, tok_base, tok_stride, tok1, r1) && r1;
     load_a_frag<D>(qa[mt], qkv + slab * CS + cbase, p.ldq, tok0, tok1, ok0, ok1, t);
     load_a_frag<D>(ga[mt], (const bf16*)p.dout + slab * CS + cbase, p.ldo, tok0, tok1, ok0, ok1, t);
     uint32_t oa[KS][4];
@@ -217,9 +253,8 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_dq_mma_kernel(const At
   for (int mt = 0; mt < MT; ++mt) {
 #pragma unroll
     for (int h2 = 0; h2 < 2; ++h2) {
-      const int qn = q0 + mt * 16 + g + h2 * 8;
-      if (qn >= N) continue;
-      const int64_t tok = tok_base + (int64_t)qn * tok_stride;
+      int64_t tok; bool real;                              // recomputed rather than kept live across the key loop
+      if (!(seq_token<WIN>(p, row, q0 + mt * 16 + g + h2 * 8, N, tok_base, tok_stride, tok, real) && real)) continue;
       if (D >= 8) {
 #pragma unroll
         for (int dn = 0; dn < DN; ++dn)
@@ -236,9 +271,9 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_dq_mma_kernel(const At
 }
 
 // ------------------------------------------------------------------------------------------------
-// dk, dv: grid (ceil(N/64), sequences, heads/8); needs dsum from the dq kernel
+// dk, dv: same grids as the dq kernel; needs dsum from the dq kernel
 // ------------------------------------------------------------------------------------------------
-template <int D>
+template <int D, bool WIN>
 __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_dkv_mma_kernel(const AttnParams p) {
   constexpr int CS = 8 * D, PITCH = CS + 8, KS = (D + 15) / 16, DN = (D + 7) / 8, CPT = CS / 8, MT = bw_mt<D>();
   extern __shared__ __align__(16) uint8_t bw_smem[];
@@ -247,12 +282,14 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_dkv_mma_kernel(const A
   tile_t Gs = reinterpret_cast<tile_t>(bw_smem + 3 * BW_T * PITCH * 2);
   __shared__ __align__(8) float Ls[3][8][BW_T], Ds[3][8][BW_T];          // [ring slot][head][query]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
-  const int row = blockIdx.y, k0 = blockIdx.x * (16 * MT), slab = blockIdx.z;
-  const int N = p.geom == TFSWA_GEOM_TSA ? p.H : p.W;
+  const int row = WIN ? blockIdx.x : blockIdx.y, k0 = (WIN ? blockIdx.y : blockIdx.x) * (16 * MT), slab = blockIdx.z;
+  const int N = WIN ? p.ws * p.ws : (p.geom == TFSWA_GEOM_TSA ? p.H : p.W);
   const int T = (N + BW_T - 1) / BW_T;
-  int64_t tok_base, tok_stride;
-  if (p.geom == TFSWA_GEOM_TSA) { const int b = row / p.W; tok_base = (int64_t)b * p.H * p.W + (row - b * p.W); tok_stride = p.W; }
-  else { tok_base = (int64_t)row * p.W; tok_stride = 1; }
+  int64_t tok_base = 0, tok_stride = 1;
+  if (!WIN) {
+    if (p.geom == TFSWA_GEOM_TSA) { const int b = row / p.W; tok_base = (int64_t)b * p.H * p.W + (row - b * p.W); tok_stride = p.W; }
+    else { tok_base = (int64_t)row * p.W; }
+  }
   const bf16* qkv = (const bf16*)p.qkv;
   const bf16* dout = (const bf16*)p.dout;
   const int cbase = warp * D;
@@ -262,21 +299,19 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_dkv_mma_kernel(const A
     if (tt < T) {
       for (int v = tid; v < BW_T * 2 * CPT; v += BW_THREADS) {
         const int j = v / (2 * CPT), rem = v - j * 2 * CPT, part = rem / CPT, chunk = rem - part * CPT;
-        const int qn = tt * BW_T + j;
         bf16* dst = part ? &Gs[b][j][chunk * 8] : &Qs[b][j][chunk * 8];
-        if (qn < N) {
-          const int64_t tok = tok_base + (int64_t)qn * tok_stride;
+        int64_t tok; bool real;
+        if (seq_token<WIN>(p, row, tt * BW_T + j, N, tok_base, tok_stride, tok, real) && real) {
           b_cp_async16(dst, part ? dout + tok * p.ldo + slab * CS + chunk * 8 : qkv + tok * p.ldq + slab * CS + chunk * 8);
-        } else {
+        } else {                                                         // absent or zero-padded (cropped) query
           *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
         }
       }
       for (int v = tid; v < BW_T * 8; v += BW_THREADS) {                 // lse / D of the tile's queries, all 8 heads
         const int j = v >> 3, h = v & 7;
-        const int qn = tt * BW_T + j;
         float l = CUDART_INF_F, d = 0.f;                                 // +inf -> p = 0 for absent queries
-        if (qn < N) {
-          const int64_t tok = tok_base + (int64_t)qn * tok_stride;
+        int64_t tok; bool real;
+        if (seq_token<WIN>(p, row, tt * BW_T + j, N, tok_base, tok_stride, tok, real) && real) {
           l = p.lse[tok * p.heads + slab * 8 + h];
           d = p.dsum[tok * p.heads + slab * 8 + h];
         }
@@ -293,11 +328,15 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_dkv_mma_kernel(const A
   float dk[MT][DN][4], dv[MT][DN][4];
 #pragma unroll
   for (int mt = 0; mt < MT; ++mt) {
-    const int kn0 = k0 + mt * 16 + g, kn1 = kn0 + 8;
-    const bool ok0 = kn0 < N, ok1 = kn1 < N;
-    const int64_t tok0 = tok_base + (int64_t)(ok0 ? kn0 : 0) * tok_stride, tok1 = tok_base + (int64_t)(ok1 ? kn1 : 0) * tok_stride;
-    load_a_frag<D>(ka[mt], qkv + p.C + slab * CS + cbase, p.ldq, tok0, tok1, ok0, ok1, t);
-    load_a_frag<D>(va[mt], qkv + 2 * p.C + slab * CS + cbase, p.ldq, tok0, tok1, ok0, ok1, t);
+    int64_t tok0, tok1; bool r0, r1;
+    const bool in0 = seq_token<WIN>(p, row, k0 + mt * 16 + g, N, tok_base, tok_stride, tok0, r0);
+    const bool in1 = seq_token<WIN>(p, row, k0 + mt * 16 + g + 8, N, tok_base, tok_stride, tok1, r1);
+    load_a_frag<D>(ka[mt], qkv + p.C + slab * CS + cbase, p.ldq, tok0, tok1, in0 && r0, in1 && r1, t);
+    load_a_frag<D>(va[mt], qkv + 2 * p.C + slab * CS + cbase, p.ldq, tok0, tok1, in0 && r0, in1 && r1, t);
+    if (WIN) {
+      if (in0 && !r0) { fill_a_frag_row<D>(ka[mt], p.pad_kv + slab * CS + cbase, 0, t); fill_a_frag_row<D>(va[mt], p.pad_kv + p.C + slab * CS + cbase, 0, t); }
+      if (in1 && !r1) { fill_a_frag_row<D>(ka[mt], p.pad_kv + slab * CS + cbase, 1, t); fill_a_frag_row<D>(va[mt], p.pad_kv + p.C + slab * CS + cbase, 1, t); }
+    }
 #pragma unroll
     for (int dn = 0; dn < DN; ++dn) {
       dk[mt][dn][0] = dk[mt][dn][1] = dk[mt][dn][2] = dk[mt][dn][3] = 0.f;
@@ -371,9 +410,29 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_dkv_mma_kernel(const A
   for (int mt = 0; mt < MT; ++mt) {
 #pragma unroll
     for (int h2 = 0; h2 < 2; ++h2) {
-      const int kn = k0 + mt * 16 + g + h2 * 8;
-      if (kn >= N) continue;
-      const int64_t tok = tok_base + (int64_t)kn * tok_stride;
+      int64_t tok; bool real;                              // recomputed rather than kept live across the query loop
+      if (!seq_token<WIN>(p, row, k0 + mt * 16 + g + h2 * 8, N, tok_base, tok_stride, tok, real)) continue;
+      if (WIN && !real) {                                  // zero-padded key: its gradient belongs to the folded qkv bias
+        if (p.dpad) {
+          float* dp = p.dpad + slab * CS;
+          if (D >= 8) {
+#pragma unroll
+            for (int dn = 0; dn < DN; ++dn) {
+              const int col = cbase + dn * 8 + 2 * t;
+              atomicAdd(dp + col, dk[mt][dn][h2 * 2] * p.scale); atomicAdd(dp + col + 1, dk[mt][dn][h2 * 2 + 1] * p.scale);
+              atomicAdd(dp + p.C + col, dv[mt][dn][h2 * 2]); atomicAdd(dp + p.C + col + 1, dv[mt][dn][h2 * 2 + 1]);
+            }
+          } else {
+            const int first = cbase & 7;
+            if (2 * t >= first && 2 * t < first + 4) {
+              const int col = (cbase & ~7) + 2 * t;
+              atomicAdd(dp + col, dk[mt][0][h2 * 2] * p.scale); atomicAdd(dp + col + 1, dk[mt][0][h2 * 2 + 1] * p.scale);
+              atomicAdd(dp + p.C + col, dv[mt][0][h2 * 2]); atomicAdd(dp + p.C + col + 1, dv[mt][0][h2 * 2 + 1]);
+            }
+          }
+        }
+        continue;
+      }
       bf16* base = dqkv + tok * p.ldq + slab * CS;
       if (D >= 8) {
 #pragma unroll
@@ -394,32 +453,45 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_dkv_mma_kernel(const A
   }
 }
 
-template <int D>
+template <int D, bool WIN>
 static int launch_bwd_mma(const AttnParams& p, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e1 = cudaFuncSetAttribute(attn_bwd_dq_mma_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, bw_smem_bytes<D>());
-    cudaError_t e2 = cudaFuncSetAttribute(attn_bwd_dkv_mma_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, bw_smem_bytes<D>());
+    cudaError_t e1 = cudaFuncSetAttribute(attn_bwd_dq_mma_kernel<D, WIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, bw_smem_bytes<D>());
+    cudaError_t e2 = cudaFuncSetAttribute(attn_bwd_dkv_mma_kernel<D, WIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, bw_smem_bytes<D>());
     if (e1 != cudaSuccess || e2 != cudaSuccess) { set_error("attn_bwd_mma: cudaFuncSetAttribute failed"); return TFSWA_ECUDA; }
     attr_set = true;
   }
-  const int N = p.geom == TFSWA_GEOM_TSA ? p.H : p.W;
-  const int rows = p.geom == TFSWA_GEOM_TSA ? p.B * p.W : p.B * p.H;
-  dim3 grid((N + 16 * bw_mt<D>() - 1) / (16 * bw_mt<D>()), rows, p.heads / 8);
-  attn_bwd_dq_mma_kernel<D><<<grid, BW_THREADS, bw_smem_bytes<D>(), st>>>(p);
-  attn_bwd_dkv_mma_kernel<D><<<grid, BW_THREADS, bw_smem_bytes<D>(), st>>>(p);
+  const int per_cta = 16 * bw_mt<D>();
+  dim3 grid;
+  if (WIN) {
+    grid = dim3((unsigned)(p.B * p.nWh * p.nWw), (p.ws * p.ws + per_cta - 1) / per_cta, p.heads / 8);
+  } else {
+    const int N = p.geom == TFSWA_GEOM_TSA ? p.H : p.W;
+    const int rows = p.geom == TFSWA_GEOM_TSA ? p.B * p.W : p.B * p.H;
+    grid = dim3((N + per_cta - 1) / per_cta, rows, p.heads / 8);
+  }
+  attn_bwd_dq_mma_kernel<D, WIN><<<grid, BW_THREADS, bw_smem_bytes<D>(), st>>>(p);
+  attn_bwd_dkv_mma_kernel<D, WIN><<<grid, BW_THREADS, bw_smem_bytes<D>(), st>>>(p);
   return check_launch("attn_bwd_mma");
 }
 
-// bf16 axial attention backward; returns 1 when the shape is not covered (caller falls back to the CUDA-core kernels)
+// bf16 attention backward; returns 1 when the shape is not covered (caller falls back to the CUDA-core kernels)
 int attn_bwd_mma_bf16(const AttnParams& p, cudaStream_t st) {
   const int D = p.C / p.heads;
+  const bool win = p.geom == TFSWA_GEOM_SWA;
   const int rows = p.geom == TFSWA_GEOM_TSA ? p.B * p.W : p.B * p.H;
-  if (p.geom == TFSWA_GEOM_SWA || p.heads % 8 != 0 || rows > 65535 || (D != 4 && D != 8 && D != 16)) return 1;
+  if (p.heads % 8 != 0 || (D != 4 && D != 8 && D != 16)) return 1;
+  if (win ? (p.ws != 8) : (rows > 65535)) return 1;
   if ((p.ldq % 8) || (p.ldo % 8) || (((uintptr_t)p.qkv | (uintptr_t)p.dqkv | (uintptr_t)p.dout) & 15) || (((uintptr_t)p.o) & 3)) return 1;
-  if (D == 4) return launch_bwd_mma<4>(p, st);
-  if (D == 8) return launch_bwd_mma<8>(p, st);
-  return launch_bwd_mma<16>(p, st);
+  if (win) {
+    if (D == 4) return launch_bwd_mma<4, true>(p, st);
+    if (D == 8) return launch_bwd_mma<8, true>(p, st);
+    return launch_bwd_mma<16, true>(p, st);
+  }
+  if (D == 4) return launch_bwd_mma<4, false>(p, st);
+  if (D == 8) return launch_bwd_mma<8, false>(p, st);
+  return launch_bwd_mma<16, false>(p, st);
 }
 
 }  // namespace tfswa
