@@ -317,7 +317,7 @@ def main():
     top_kernels = {tag: {"ms_per_step": k["ms"] / args.steps, "launches_per_step": k["launches"] / args.steps,
                          "tflops": (k["flops"] / (k["ms"] / 1e3) / 1e12) if k["flops"] else None,
                          "gbs": (k["bytes"] / (k["ms"] / 1e3) / 1e9) if k["bytes"] else None} for tag, k in top}
-    from oracle.tfswa_oracle import count_model_flops
+    from tfswa_unet_b200.flops import model_flops as count_model_flops
     flops = count_model_flops(B, 2, 2, H_BINS, W_FRAMES)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

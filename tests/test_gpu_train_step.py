@@ -85,8 +85,14 @@ def test_train_step_matches_stock_optimizer_loop(precision):
         a = T.TFSWAUNet(4, 4, [1, 1, 1, 1], [32, 64, 128, 256], 8, 4, 8).train().cuda()
         b = T.TFSWAUNet(4, 4, [1, 1, 1, 1], [32, 64, 128, 256], 8, 4, 8).train().cuda()
         b.load_state_dict(a.state_dict())
-        ts = TrainStep(a, lr=1e-3, weight_decay=1e-2, max_grad_norm=1.0)
-        ropt = torch.optim.AdamW(b.parameters(), lr=1e-3, weight_decay=1e-2)
+        # bf16 runs are not bit-reproducible (the BatchNorm column sums and split-M weight gradients use fp32 atomics; a
+        # last-bit change flips bf16 roundings downstream), and Adam at eps=1e-8 turns every gradient element that is
+        # below that noise into a +-lr step: two runs of the SAME stock loop then differ by 2*lr on such weights
+        # (tools/debug/trainstep_diff.py measures that floor).  eps=1e-3 keeps the update a smooth function of the
+        # gradient, so the comparison tests the plumbing rather than the noise; fp32 keeps the default eps.
+        eps = 1e-3 if precision == "bf16" else 1e-8
+        ts = TrainStep(a, lr=1e-3, weight_decay=1e-2, max_grad_norm=1.0, eps=eps)
+        ropt = torch.optim.AdamW(b.parameters(), lr=1e-3, weight_decay=1e-2, eps=eps)
         g = torch.Generator(device="cuda").manual_seed(2)
         stats = {}
         for step in range(2):
@@ -106,7 +112,7 @@ def test_train_step_matches_stock_optimizer_loop(precision):
             tot += float((p.detach() - q.detach()).double().pow(2).sum())
             den += float(q.detach().double().pow(2).sum())
         stats["param_rel_l2"] = (tot / den) ** 0.5
-        stats["bn_running"] = max(float((u - v).abs().max() / v.abs().max().clamp_min(1e-6))
+        stats["bn_running"] = max(float(((u - v).abs() / (v.abs() + 1e-2)).max())       # running means sit near zero: mixed abs/rel
                                   for (k, u), (_, v) in zip(a.state_dict().items(), b.state_dict().items()) if "running" in k)
         # eval after training sees the updated weights (prepared-weight caches key on version counters)
         a.eval()

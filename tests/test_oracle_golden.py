@@ -132,3 +132,14 @@ def test_flop_model_matches_survey():
     assert O.count_block_flops(2, 64, 20, 28) == 446_824_448
     assert O.count_model_flops(1, 2, 2, 64, 96) == 13_127_385_088
     assert abs(O.count_model_flops(8, 2, 2, 1025, 517) / 1e12 - 13.38) < 0.01
+
+
+def test_product_flop_model_equals_the_checker():
+    """bench.py divides by tfswa_unet_b200.flops (product side); it must agree with the oracle's independent count."""
+    from tfswa_unet_b200 import flops
+    for args in [(1, 32, 32, 48), (2, 64, 20, 28), (8, 32, 1025, 517)]:
+        assert flops.block_flops(*args) == O.count_block_flops(*args)
+    assert flops.block_flops(1, 32, 32, 48) == 154140672                   # SURVEY A.2: FlopCounterMode on the reference
+    for args in [(1, 2, 2, 64, 96), (8, 2, 2, 1025, 517), (8, 4, 4, 1025, 517)]:
+        assert flops.model_flops(*args) == O.count_model_flops(*args)
+    assert flops.model_flops(1, 2, 2, 64, 96) == 13127385088

@@ -44,9 +44,27 @@ __device__ __forceinline__ void wm_ldsm_x2_trans(uint32_t& r0, uint32_t& r1, con
   asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
 }
 
+constexpr int WM_STAGES = 3;        // cp.async ring depth: two chunks (2 x 18 KB per CTA) in flight under the MMAs of the third
+constexpr int WM_SMEM = WM_STAGES * (2 * WM_MC * WM_PITCH * 2 + WM_MC * 8);
+
+// 16-byte asynchronous copy global -> shared; bytes = 0 zero-fills the destination (rows / columns outside the problem)
+__device__ __forceinline__ void wm_cp_async16(void* smem_dst, const void* gsrc, int bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void wm_cp_async8(void* smem_dst, const void* gsrc, int bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc), "r"(bytes) : "memory");
+}
+
+// The kernel is a stream over the tokens at an arithmetic intensity of ~50 FLOP/B (far below the ridge), i.e. HBM-bound:
+// what matters is bytes in flight.  G and X chunks go global -> shared with cp.async through a WM_STAGES-deep ring (the
+// first version staged one chunk through registers and was latency-bound: 1.4 TB/s, long-scoreboard stall 10 per issue,
+// profiles/r1zz_train_ncu_summary.md); the prologue, when there is one, is applied in place in shared memory.
 __global__ void __launch_bounds__(WM_THREADS) wgrad_mma_kernel(const WgradMmaParams p) {
-  __shared__ __align__(16) bf16 Gs[WM_MC][WM_PITCH];
-  __shared__ __align__(16) bf16 As[WM_MC][WM_PITCH];
+  extern __shared__ __align__(16) uint8_t wm_smem[];
+  typedef bf16 (*tile_t)[WM_MC][WM_PITCH];
+  tile_t Gs = reinterpret_cast<tile_t>(wm_smem);
+  tile_t As = reinterpret_cast<tile_t>(wm_smem + WM_STAGES * WM_MC * WM_PITCH * 2);
+  float2 (*Rs)[WM_MC] = reinterpret_cast<float2 (*)[WM_MC]>(wm_smem + 2 * WM_STAGES * WM_MC * WM_PITCH * 2);   // (mean, rstd) per token
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int k0 = blockIdx.x * WM_T, n0 = blockIdx.y * WM_T;
   const int zb = blockIdx.z / p.msplit, split = blockIdx.z % p.msplit;
@@ -55,6 +73,7 @@ __global__ void __launch_bounds__(WM_THREADS) wgrad_mma_kernel(const WgradMmaPar
   const float* rs = p.row_stats ? p.row_stats + (int64_t)zb * p.rs_bs : nullptr;
   const int64_t m_begin = (int64_t)split * p.rows_per_cta;
   const int64_t m_end = m_begin + p.rows_per_cta < p.M ? m_begin + p.rows_per_cta : p.M;
+  const int nchunks = (int)((m_end - m_begin + WM_MC - 1) / WM_MC);
 
   // staging: thread -> (token row lr + 32 i, 8 columns at lc), i = 0, 1, for G and for X
   const int lr = tid >> 3, lc = (tid & 7) * 8;
@@ -65,68 +84,76 @@ __global__ void __launch_bounds__(WM_THREADS) wgrad_mma_kernel(const WgradMmaPar
 #pragma unroll
   for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
 
-  uint4 gv[2], av[2];
-  auto load_chunk = [&](int64_t mc) {
+  auto issue = [&](int c) {
+    if (c < nchunks) {
+      const int slot = c % WM_STAGES;
+      const int64_t mc = m_begin + (int64_t)c * WM_MC;
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const int64_t m = mc + lr + 32 * i;
-      gv[i] = make_uint4(0, 0, 0, 0); av[i] = gv[i];
-      if (m < m_end) {
-        if (g_ok) gv[i] = *reinterpret_cast<const uint4*>(g + m * p.ldg + n0 + lc);
-        if (a_ok) {
-          if (p.prologue == TFSWA_PRO_NONE) {
-            av[i] = *reinterpret_cast<const uint4*>(x + m * p.ldx + k0 + lc);
-          } else {
-            float v[8];
-            load8(x + m * p.ldx + k0 + lc, v);
-            if (p.prologue & TFSWA_PRO_AFFINE) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] = v[j] * p.in_scale[k0 + lc + j] + p.in_shift[k0 + lc + j];
-            }
-            if (p.prologue & TFSWA_PRO_LNHAT) {
-              const float mean = rs[m * 2], rstd = rs[m * 2 + 1];
-#pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] = (v[j] - mean) * rstd;
-            }
-            if (p.prologue & TFSWA_PRO_GELU) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] = gelu_erf(v[j]);
-            }
-            bf16 tmp[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) tmp[j] = __float2bfloat16(v[j]);
-            av[i] = *reinterpret_cast<const uint4*>(tmp);
-          }
-        }
+      for (int i = 0; i < 2; ++i) {
+        const int r = lr + 32 * i;
+        const int64_t m = mc + r;
+        const bool in = m < m_end;
+        const int64_t ms = in ? m : m_begin;                       // any valid address when nothing is copied
+        wm_cp_async16(&Gs[slot][r][lc], g + ms * p.ldg + (g_ok ? n0 + lc : 0), (in && g_ok) ? 16 : 0);
+        wm_cp_async16(&As[slot][r][lc], x + ms * p.ldx + (a_ok ? k0 + lc : 0), (in && a_ok) ? 16 : 0);
+        if (rs && lc == 0) wm_cp_async8(&Rs[slot][r], rs + ms * 2, in ? 8 : 0);
       }
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
   };
 
   constexpr uint32_t ONES = 0x3F803F80u;
-  load_chunk(m_begin);
-  for (int64_t mc = m_begin; mc < m_end; mc += WM_MC) {
-    __syncthreads();                                               // previous chunk's fragments have been read
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      *reinterpret_cast<uint4*>(&Gs[lr + 32 * i][lc]) = gv[i];
-      *reinterpret_cast<uint4*>(&As[lr + 32 * i][lc]) = av[i];
+  for (int c = 0; c < WM_STAGES - 1; ++c) issue(c);
+  for (int c = 0; c < nchunks; ++c) {
+    const int slot = c % WM_STAGES;
+    asm volatile("cp.async.wait_group %0;" ::"n"(WM_STAGES - 2) : "memory");
+    __syncthreads();                                               // chunk c visible; chunk c-1's fragments have been read
+    issue(c + WM_STAGES - 1);                                      // refills the slot chunk c-1 used
+    if (p.prologue != TFSWA_PRO_NONE) {                            // pro(X) in place (fp32 math, rounded to bf16 for the MMA)
+      if (a_ok) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int r = lr + 32 * i;
+          float v[8];
+          load8(&As[slot][r][lc], v);
+          if (p.prologue & TFSWA_PRO_AFFINE) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = v[j] * p.in_scale[k0 + lc + j] + p.in_shift[k0 + lc + j];
+          }
+          if (p.prologue & TFSWA_PRO_LNHAT) {
+            const float2 st = Rs[slot][r];                         // zero-filled (mean 0, rstd 0) for rows past m_end
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = (v[j] - st.x) * st.y;
+          }
+          if (p.prologue & TFSWA_PRO_GELU) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = gelu_erf(v[j]);
+          }
+          if (m_begin + (int64_t)c * WM_MC + r >= m_end) {         // affine / GELU of a zero-filled row must stay zero
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = 0.f;
+          }
+          store8(&As[slot][r][lc], v);
+        }
+      }
+      __syncthreads();
     }
-    __syncthreads();
-    if (mc + WM_MC < m_end) load_chunk(mc + WM_MC);                // global latency of the next chunk under the MMAs
 #pragma unroll
     for (int ks = 0; ks < WM_MC / 16; ++ks) {
       // A = G^T: (n rows, token cols).  x4.trans blocks: (tokens 0-7, n 0-7), (tokens 0-7, n 8-15), (tokens 8-15, n 0-7), (tokens 8-15, n 8-15)
       uint32_t a[4];
-      wm_ldsm_x4_trans(a, &Gs[ks * 16 + (lane & 7) + ((lane >> 4) << 3)][nt * 16 + ((lane >> 3) & 1) * 8]);
+      wm_ldsm_x4_trans(a, &Gs[slot][ks * 16 + (lane & 7) + ((lane >> 4) << 3)][nt * 16 + ((lane >> 3) & 1) * 8]);
 #pragma unroll
       for (int kt = 0; kt < 4; ++kt) {
         uint32_t b0, b1;                                           // B = X: tokens 0-7 / 8-15 x 8 k columns
-        wm_ldsm_x2_trans(b0, b1, &As[ks * 16 + (lane & 15)][kh * 32 + kt * 8]);
+        wm_ldsm_x2_trans(b0, b1, &As[slot][ks * 16 + (lane & 15)][kh * 32 + kt * 8]);
         wm_mma(acc[kt], a, b0, b1);
       }
       if (kh == 0) wm_mma(bacc, a, ONES, ONES);                    // every column of bacc = sum over tokens of G
     }
   }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   // ---- split-M partial -> global with fp32 atomics ----
   const int gq = lane >> 2, tq = lane & 3;
   float* dw = p.dw + (int64_t)zb * p.w_bs;
@@ -163,7 +190,15 @@ int wgrad_mma_bf16(const tfswa_linear_args* a, const void* g, int64_t ldg, int64
   p.rows_per_cta = ((p.M + want - 1) / want + WM_MC - 1) / WM_MC * WM_MC;
   p.msplit = (int)((p.M + p.rows_per_cta - 1) / p.rows_per_cta);
   dim3 grid(kt, nt, a->batch * p.msplit);
-  wgrad_mma_kernel<<<grid, WM_THREADS, 0, st>>>(p);
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(wgrad_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WM_SMEM) != cudaSuccess) {
+      set_error("wgrad_mma: cudaFuncSetAttribute failed");
+      return TFSWA_ECUDA;
+    }
+    attr_set = true;
+  }
+  wgrad_mma_kernel<<<grid, WM_THREADS, WM_SMEM, st>>>(p);
   return check_launch("linear_wgrad");
 }
 

@@ -52,18 +52,14 @@ class LinW:
         return self._tc
 
 
-_BF16_CACHE = {}
-
-
 def _bf16_of(w: Tensor) -> Tensor:
-    """bf16 copy of a prepared (cached, immutable) weight tensor, keyed by storage + version"""
-    key = (w.data_ptr(), w._version, tuple(w.shape))
-    hit = _BF16_CACHE.get(key)
-    if hit is None:
-        if len(_BF16_CACHE) > 256:
-            _BF16_CACHE.clear()
-        hit = _BF16_CACHE[key] = w.detach().to(torch.bfloat16).contiguous()
-    return hit
+    """bf16 copy of a prepared (cached, immutable) weight tensor.  The copy hangs on the tensor OBJECT (not on its
+    address: the caching allocator hands a freed weight's address to the next rebuilt one) and is tied to its version."""
+    hit = getattr(w, "_tfswa_bf16", None)
+    if hit is None or hit[0] != w._version:
+        hit = (w._version, w.detach().to(torch.bfloat16).contiguous())
+        w._tfswa_bf16 = hit
+    return hit[1]
 
 
 USE_TC = True   # tcgen05 path for bf16 activations (set False to force the SIMT engine, e.g. for A/B tests)

@@ -222,10 +222,11 @@ class TrainStep:
     """One data-parallel optimisation step of ``model`` (a ``TFSWAUNet`` of this package) on this rank's batch."""
 
     def __init__(self, model: nn.Module, lr: float = 1e-3, weight_decay: float = 1e-2, max_grad_norm: float = 1.0,
+                 betas: Sequence[float] = (0.9, 0.999), eps: float = 1e-8,
                  group: Optional[dist.ProcessGroup] = None, bucket_bytes: int = 16 << 20):
         self.model = model
         self.arena = FlatArena(model, group, bucket_bytes)
-        self.optim = FusedClipAdamW(self.arena, lr=lr, weight_decay=weight_decay, max_grad_norm=max_grad_norm)
+        self.optim = FusedClipAdamW(self.arena, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, max_grad_norm=max_grad_norm)
 
     def __call__(self, model_input: Tensor, mixture_mag: Tensor, target_mags: Sequence[Tensor], lr: Optional[float] = None):
         """-> (loss, grad_norm) as device tensors; no host synchronisation."""

@@ -1,6 +1,6 @@
 """Single-TFSWABlock microbenchmark (BASELINE.json configs[1]): fwd (eval) and fwd+bwd (train) at the stage-1/2/3
 resolutions of the 6 s / n_fft 2048 workload, fp32 and bf16, batch 1.  Prints one JSON line per case:
-model FLOPs (oracle.count_block_flops, backward counted as 2x forward), achieved TFLOP/s and the fraction of the measured
+model FLOPs (tfswa_unet_b200.flops.block_flops, backward counted as 2x forward), achieved TFLOP/s and the fraction of the measured
 bf16 tensor peak (MEASURED_PEAKS.json) - the "tensor-pipe util" half of the headline metric.
 
     python tools/block_bench.py [B] > profiles/rXX_block_bench.jsonl
@@ -14,7 +14,7 @@ sys.path.insert(0, ROOT)
 import torch
 
 import tfswa_unet_b200 as T
-from oracle.tfswa_oracle import count_block_flops
+from tfswa_unet_b200.flops import block_flops as count_block_flops
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 peak = 1408.6
