@@ -91,6 +91,9 @@ def test_train_step_matches_stock_optimizer_loop(precision):
         # (tools/debug/trainstep_diff.py measures that floor).  eps=1e-3 keeps the update a smooth function of the
         # gradient, so the comparison tests the plumbing rather than the noise; fp32 keeps the default eps.
         eps = 1e-3 if precision == "bf16" else 1e-8
+        with torch.no_grad():                                   # populate the prepared-weight caches before training
+            a.eval()(torch.randn(1, 4, 40, 24, device="cuda"))
+            a.train()
         ts = TrainStep(a, lr=1e-3, weight_decay=1e-2, max_grad_norm=1.0, eps=eps)
         ropt = torch.optim.AdamW(b.parameters(), lr=1e-3, weight_decay=1e-2, eps=eps)
         g = torch.Generator(device="cuda").manual_seed(2)
@@ -114,17 +117,25 @@ def test_train_step_matches_stock_optimizer_loop(precision):
         stats["param_rel_l2"] = (tot / den) ** 0.5
         stats["bn_running"] = max(float(((u - v).abs() / (v.abs() + 1e-2)).max())       # running means sit near zero: mixed abs/rel
                                   for (k, u), (_, v) in zip(a.state_dict().items(), b.state_dict().items()) if "running" in k)
-        # eval after training sees the updated weights (prepared-weight caches key on version counters)
+        # eval after training must see the updated weights (the prepared-weight caches key on version counters, which the
+        # in-place arena update has to bump): compare with a cache-free model built from the trained state_dict
+        fresh = T.TFSWAUNet(4, 4, [1, 1, 1, 1], [32, 64, 128, 256], 8, 4, 8).cuda()
+        fresh.load_state_dict(a.state_dict())
         a.eval()
+        fresh.eval()
         b.eval()
         with torch.no_grad():
-            ya, yb = a(x), b(x)
+            ya, yf, yb = a(x), fresh(x), b(x)
+        stats["eval_vs_fresh"] = float((ya - yf).abs().max())
         stats["eval_masks"] = float((ya - yb).abs().max())
         # Both sides run the same kernels; they differ by the accumulation order of the split-M weight-gradient atomics and,
         # from the second step on, by what bf16 rounding of the activations makes of that noise (Adam normalises every
         # element's update to O(lr), so noise-dominated gradient elements move the weights by up to lr either way).
-        lim = ({"loss": 2e-3, "norm": 5e-2, "param_rel_l2": 5e-3, "bn_running": 2e-2, "eval_masks": 5e-2} if precision == "bf16" else
-               {"loss": 1e-5, "norm": 2e-3, "param_rel_l2": 1e-4, "bn_running": 1e-3, "eval_masks": 1e-3})
+        # bf16 floors measured between two runs of the same stock loop (tools/debug/trainstep_diff.py): running means of
+        # near-zero-mean channels and the eval masks of a barely-warmed-up BatchNorm move by a few percent
+        lim = ({"loss": 2e-3, "norm": 5e-2, "param_rel_l2": 5e-3, "bn_running": 0.2, "eval_masks": 0.2, "eval_vs_fresh": 1e-3}
+               if precision == "bf16" else
+               {"loss": 1e-5, "norm": 2e-3, "param_rel_l2": 1e-4, "bn_running": 1e-3, "eval_masks": 1e-3, "eval_vs_fresh": 1e-5})
         bad = {k: v for k, v in stats.items() if v > lim[k.rstrip("01")]}
         assert not bad, f"{bad} (all: {stats})"
     finally:

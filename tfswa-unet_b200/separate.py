@@ -33,7 +33,7 @@ class ShardedSeparator:
     # ---- segment plan (inference.py:187-201) --------------------------------------------------
     def plan(self, total: int) -> List[int]:
         if total <= self.segment_samples:
-            return [0]
+            return [0]                                           # (separate() takes the single-segment path for these)
         n = (total - self.segment_samples) // self.hop_samples + 1
         return [i * self.hop_samples for i in range(n)]          # samples past the last full hop stay uncovered (reference quirk)
 
@@ -61,6 +61,11 @@ class ShardedSeparator:
             audio = audio[None]
         mono = audio.mean(dim=0) if audio.shape[0] > 1 else audio[0]               # inference.py:84-85
         total = mono.shape[0]
+        if total <= self.segment_samples:                                          # inference.py:92-95: one segment as it is -
+            spec, masks = self._masks(mono[None])                                  # no padding, no window, ISTFT's own length
+            win = torch.hann_window(self.n_fft, device=mono.device)
+            return {name: torch.istft(spec * masks[:, i], self.n_fft, self.hop, self.n_fft, win, center=True, normalized=False,
+                                      onesided=True) for i, name in enumerate(stem_names[:masks.shape[1]])}
         starts = self.plan(total)
         world = dist.get_world_size(self.group) if dist.is_initialized() else 1
         rank = dist.get_rank(self.group) if dist.is_initialized() else 0
@@ -73,15 +78,18 @@ class ShardedSeparator:
             idx = starts[b0:min(b0 + self.batch, hi)]
             seg = torch.stack([torch.nn.functional.pad(mono[s:s + S], (0, max(0, S - (total - s)))) for s in idx])
             spec, masks = self._masks(seg)
+            # The reference reconstructs without a target length (inference.py:148-150 -> stft_processor.py:136-184): a segment
+            # comes back (frames-1)*hop samples long - 264 192 of 264 600 for 6 s at hop 512 - and only that many samples,
+            # weighted by the FIRST part of the full-length Hann window, enter the overlap-add (inference.py:209-216).
+            L = (spec.shape[-1] - 1) * self.hop
             for i in range(min(n_st, masks.shape[1])):
                 wav = torch.istft(spec * masks[:, i], self.n_fft, self.hop, self.n_fft,
-                                  torch.hann_window(self.n_fft, device=seg.device), center=True, normalized=False,
-                                  onesided=True, length=S)
+                                  torch.hann_window(self.n_fft, device=seg.device), center=True, normalized=False, onesided=True)
                 for j, s in enumerate(idx):
-                    n = min(S, total - s)
+                    n = min(S, total - s, L)
                     acc[i, s:s + n] += wav[j, :n] * win_seg[:n]
             for s in idx:
-                n = min(S, total - s)
+                n = min(S, total - s, L)
                 acc[n_st, s:s + n] += win_seg[:n]
         if world > 1:
             dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=self.group)           # the single exchange step
