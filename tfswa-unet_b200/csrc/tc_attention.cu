@@ -495,6 +495,8 @@ __global__ void __launch_bounds__(TA_NTHREADS, 2) tc_attn_axial_kernel(const Att
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar_b);                           // P(t) in TMEM
       }
+      // (measured: consuming S in four 16-column chunks with the tcgen05.ld of chunk k+1 / k+2 in flight under the
+      // exponentials of chunk k is 4-6 % slower - the load latency is already covered by the other warps of the SMSP)
       // (measured: splitting P / PV per 32-column chunk with two barrier pairs, to give each chunk a whole tile of
       // slack, is 11 % slower - the extra tcgen05.wait::st, arrives and issuer wake-ups cost more than the sleep they remove)
       // ---- drain: PV(0..T-2) were consumed inside the loop, PV(T-1) is the one outstanding completion ----
