@@ -632,6 +632,8 @@ extern "C" int tfswa_attn_tc_fwd(const tfswa_attn_args* a, void* scratch, int64_
     if (rc) return rc;
     AttnParams ps = p;
     ps.q_begin = q_tc; ps.q_end = 0;
+    // (measured: forking this launch onto a side stream so that it runs under the main kernel changes nothing -
+    // 10.594 vs 10.585 ms at B=8 - the main kernel owns every SM until its last wave)
     // 3+ left-over queries: one 16-row tile of the register-resident kernel (FSA, 5 queries: 90 -> 42 us at B=1);
     // 1-2 queries: the key-split warp kernel is still ahead (36 vs 40 us)
     if (a->heads % 8 == 0 && force != 1 && N - q_tc > 2) return attn_axial_mma_bf16(ps, st);
