@@ -89,3 +89,24 @@ def test_tc_linear_strided_slab_views():
     y2 = ops.linear_tc(big.view(M, 1, 3 * C), wf, None, None)
     ref2 = big.view(M, 3 * C).float() @ wf[0].float().t()
     assert float((y2[:, 0].float() - ref2).abs().max()) <= 1e-2 * float(ref2.abs().max())
+
+
+@pytest.mark.parametrize("M,K,N", [(1000, 32, 32), (128 * 5 + 17, 96, 32), (4096 + 3, 384, 128), (700, 768, 256), (300, 64, 64)])
+def test_tc_linear_column_statistics(M, K, N):
+    """train-mode BatchNorm sums from the tcgen05 epilogue: sum and sum of squares of the STORED (bf16) output over the
+    valid rows only (the last 128-row tile is ragged), every N tile."""
+    from tfswa_unet_b200 import ops
+    x = seeded((M, 1, K), 61, 1.0).cuda().to(torch.bfloat16)
+    w = seeded((1, N, K), 62, K ** -0.5).cuda().to(torch.bfloat16)
+    b = seeded((1, N), 63, 0.5).cuda().float()
+    stats = torch.zeros((2, N), dtype=torch.float32, device="cuda")
+    y = ops.linear_tc(x, w, None, b, col_stats=stats)
+    torch.cuda.synchronize()
+    ref = x[:, 0].float() @ w[0].float().t() + b[0]
+    assert float((y[:, 0].float() - ref).abs().max()) <= 2e-2 * float(ref.abs().max())
+    yf = y[:, 0].double()
+    s1, s2 = yf.sum(0), (yf * yf).sum(0)
+    assert float((stats[0].double() - s1).abs().max()) <= 1e-4 * float(yf.abs().sum(0).max()) + 1e-3
+    assert float((stats[1].double() - s2).abs().max()) <= 1e-4 * float(s2.max())
+    with pytest.raises(RuntimeError, match="col_stats"):
+        ops.linear_tc(x, w, None, b, col_stats=torch.zeros((2, N), device="cuda"), epilogue=1)

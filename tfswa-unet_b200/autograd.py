@@ -45,7 +45,10 @@ class LinearFn(torch.autograd.Function):
                    None if r1 is None else r1.shape[1], None if r2 is None else r2.shape[1], x.shape[1])
         if want_col_stats:
             stats = torch.zeros((2, w.shape[1]), dtype=torch.float32, device=x.device)
-            pre = ops.linear(x, w, b, prologue=prologue, row_stats=row_stats, col_stats=stats)
+            if _tc_ok(x, w.shape[1], w.shape[2]) and prologue == L.PRO_NONE and x.shape[1] == 1:
+                pre = ops.linear_tc(x, w.to(torch.bfloat16).contiguous(), None, b, col_stats=stats)   # BatchNorm sums from the epilogue
+            else:
+                pre = ops.linear(x, w, b, prologue=prologue, row_stats=row_stats, col_stats=stats)
             ctx.save_for_backward(x, w, row_stats, pre)
             return pre, stats
         if epilogue == L.EPI_GELU:

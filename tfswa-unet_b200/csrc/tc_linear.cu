@@ -66,6 +66,7 @@ struct TcLinearParams {
   int64_t M; int N, K;
   int BN, BK, KB, stages;
   int epilogue, ln;
+  float* col_stats;          // optional (2, N) fp32: sum and sum of squares of the (bf16-rounded) outputs over the rows (train-mode BatchNorm)
   uint32_t tmem_cols;
   int OB;                    // columns per output TMA box (64 / 32 / 16): BN/OB boxes of 128 rows x OB*2 bytes, swizzled
 };
@@ -237,8 +238,29 @@ __global__ void __launch_bounds__(TC_THREADS) tc_linear_kernel(const __grid_cons
     asm volatile("bar.sync 1, 256;" ::: "memory");
     if (threadIdx.x == 64) {
       for (int b = 0; b < p.BN / p.OB; ++b) tma_store_3d(&tmy, tiles + b * box_bytes, n0 + b * p.OB, (int)m0, z);
-      tma_store_commit_wait();
     }
+    if (p.col_stats) {
+      // Train-mode BatchNorm statistics of the tile, from the staged (bf16-rounded, i.e. exactly what is stored) values:
+      // two threads per column walk the 128 rows of the swizzled tile, one fp32 atomic pair per column half and CTA.
+      const int col = et >> 1, rhalf = et & 1;
+      if (col < p.BN) {
+        const int64_t left = p.M - m0;
+        const int rows_valid = left < TC_BM ? (int)left : TC_BM;     // rows beyond M hold bias, not data
+        const uint32_t blk = (uint32_t)col >> ob_shift, chunk = ((uint32_t)col & (p.OB - 1)) >> 3;
+        float s1 = 0.f, s2 = 0.f;
+        for (int r = rhalf * 64; r < rhalf * 64 + 64 && r < rows_valid; ++r) {
+          uint32_t off = (uint32_t)r * ob_bytes + chunk * 16u;
+          off ^= ((off >> 7) & swz_mask) << 4;
+          const float v = __bfloat162float(*reinterpret_cast<const bf16*>(tiles + blk * box_bytes + off + (col & 7) * 2));
+          s1 += v; s2 = fmaf(v, v, s2);
+        }
+        if (rhalf * 64 < rows_valid) {
+          atomicAdd(p.col_stats + n0 + col, s1);
+          atomicAdd(p.col_stats + p.N + n0 + col, s2);
+        }
+      }
+    }
+    if (threadIdx.x == 64) tma_store_commit_wait();
   }
   tc_fence_before();
   __syncthreads();
@@ -267,7 +289,9 @@ extern "C" int tfswa_linear_tc_fwd(const tfswa_linear_args* a, const void* w_bf1
   TFSWA_REQUIRE(a->K % 32 == 0 && a->K >= 32 && a->N % 16 == 0, "linear_tc: need K%%32==0 and N%%16==0 (K=%d N=%d)", a->K, a->N);
   TFSWA_REQUIRE(a->prologue == TFSWA_PRO_NONE || a->prologue == TFSWA_PRO_LNHAT, "linear_tc: prologue %d unsupported", a->prologue);
   TFSWA_REQUIRE(a->prologue != TFSWA_PRO_LNHAT || (a->row_stats && wsum), "linear_tc: LN needs row_stats and wsum");
-  TFSWA_REQUIRE(!a->pre && !a->col_stats, "linear_tc: pre/col_stats outputs are not produced by this kernel");
+  TFSWA_REQUIRE(!a->pre, "linear_tc: the pre-activation output is not produced by this kernel");
+  TFSWA_REQUIRE(!a->col_stats || (a->batch == 1 && a->epilogue == TFSWA_EPI_NONE && !a->r1 && !a->r2),
+                "linear_tc: col_stats needs batch 1 and a plain epilogue (the statistics are those of the stored tensor)");
   TFSWA_REQUIRE(a->ldy % 8 == 0 && a->y_bs % 8 == 0 && a->ldx % 8 == 0 && a->x_bs % 8 == 0, "linear_tc: 16-byte alignment of ld/strides");
   TFSWA_REQUIRE((!a->r1 || (a->ldr1 % 8 == 0 && a->r1_bs % 8 == 0)) && (!a->r2 || (a->ldr2 % 8 == 0 && a->r2_bs % 8 == 0)),
                 "linear_tc: residual alignment");
@@ -285,6 +309,7 @@ extern "C" int tfswa_linear_tc_fwd(const tfswa_linear_args* a, const void* w_bf1
   p.r1 = (const bf16*)a->r1; p.ldr1 = a->ldr1; p.r1_bs = a->r1_bs; p.r2 = (const bf16*)a->r2; p.ldr2 = a->ldr2; p.r2_bs = a->r2_bs;
   p.y = (bf16*)a->y; p.ldy = a->ldy; p.y_bs = a->y_bs;
   p.M = a->M; p.N = a->N; p.K = a->K; p.epilogue = a->epilogue; p.ln = a->prologue == TFSWA_PRO_LNHAT;
+  p.col_stats = a->col_stats;
   p.OB = (p.BN % 64 == 0) ? 64 : ((p.BN % 32 == 0) ? 32 : 16);
   CUtensorMap tmx, tmw, tmy;
   int rc = make_tmap_bf16_3d(&tmx, a->x, a->K, a->M, a->batch, a->ldx, a->x_bs, p.BK, TC_BM);

@@ -78,7 +78,11 @@ def linear(x: Tensor, lw: LinW, *, prologue: int = 0, epilogue: int = 0,
         return ops.linear_tc(x, wb, wsum, bias, prologue=prologue, epilogue=epilogue, row_stats=row_stats, r1=r1, r2=r2)
     if want_col_stats:
         stats = torch.zeros((2, w.shape[1]), dtype=torch.float32, device=x.device)
-        pre = ops.linear(x, w, bias, prologue=prologue, row_stats=row_stats, col_stats=stats)
+        if (USE_TC and x.dtype == torch.bfloat16 and prologue == L.PRO_NONE and x.shape[1] == 1
+                and w.shape[2] % 32 == 0 and w.shape[1] % 16 == 0):
+            pre = ops.linear_tc(x, lw.tc()[0], None, bias, col_stats=stats)
+        else:
+            pre = ops.linear(x, w, bias, prologue=prologue, row_stats=row_stats, col_stats=stats)
         return pre, stats
     return ops.linear(x, w, bias, prologue=prologue, epilogue=epilogue, row_stats=row_stats, r1=r1, r2=r2)
 

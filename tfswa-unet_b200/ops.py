@@ -137,8 +137,9 @@ def linear(x: Tensor, w: Tensor, bias: Optional[Tensor] = None, *, prologue: int
 
 def linear_tc(x: Tensor, w_bf16: Tensor, wsum: Optional[Tensor], bias: Optional[Tensor] = None, *, prologue: int = 0,
               epilogue: int = 0, row_stats: Optional[Tensor] = None, r1: Optional[Tensor] = None,
-              r2: Optional[Tensor] = None) -> Tensor:
-    """tcgen05 version of :func:`linear` (bf16 activations, TMA-fed, TMEM accumulators; see tfswa_linear_tc_fwd)."""
+              r2: Optional[Tensor] = None, col_stats: Optional[Tensor] = None) -> Tensor:
+    """tcgen05 version of :func:`linear` (bf16 activations, TMA-fed, TMEM accumulators; see tfswa_linear_tc_fwd).
+    ``col_stats`` (2, N) fp32, zero-initialised: receives the column sums / sums of squares of the stored output."""
     _cuda(x, w_bf16)
     M, nb, K = x.shape
     nbw, N, Kw = w_bf16.shape
@@ -160,6 +161,11 @@ def linear_tc(x: Tensor, w_bf16: Tensor, wsum: Optional[Tensor], bias: Optional[
     a.y = y.data_ptr(); a.ldy, a.y_bs = _tok3(y, "y")
     a.M, a.N, a.K = M, N, K
     a.prologue, a.epilogue, a.batch, a.dtype = prologue, epilogue, nb, L.BF16
+    if col_stats is not None:
+        if tuple(col_stats.shape) != (2, N) or nb != 1:
+            raise ValueError(f"linear_tc: col_stats {tuple(col_stats.shape)} needs shape (2, {N}) and a single problem")
+        _f32c(col_stats)
+        a.col_stats = col_stats.data_ptr()
     _call("tfswa_linear_tc_fwd", C.byref(a), w_bf16.data_ptr(), _p(wsum), _stream(), tag=f"linear_tc[K={K},N={N},nb={nb}]",
           work={"flops": 2 * M * N * K * nb, "bytes": 2 * M * nb * (K + N) + (2 * M * nb * N if r1 is not None else 0)
                 + (2 * M * nb * N if r2 is not None else 0)})
