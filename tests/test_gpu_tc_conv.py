@@ -40,3 +40,29 @@ def test_tc_conv_matches_reference(kind, B, Cin, Cout, H, W, gelu):
     assert y.shape == ref.shape
     assert float((y.float() - ref).abs().max()) <= 1e-2 * scale + 1e-3
     assert float((y.float() - y2.float()).abs().max()) <= 1e-2 * scale + 1e-3
+
+
+@pytest.mark.parametrize("kind,B,Cin,Cout,H,W", [
+    ("conv3", 2, 32, 32, 37, 21), ("down", 2, 32, 64, 37, 21), ("down", 1, 128, 256, 32, 17),
+    ("up", 2, 64, 32, 18, 10), ("up", 1, 256, 128, 16, 8), ("up", 1, 128, 64, 33, 16),
+])
+def test_tc_conv_column_statistics(kind, B, Cin, Cout, H, W):
+    """train-mode BatchNorm sums from the tcgen05 conv epilogue = channel sums / sums of squares of the stored output
+    (ragged last tile, phase-grid cells without an output pixel and every Cout tile included)"""
+    from tfswa_unet_b200 import ops
+    from tfswa_unet_b200.autograd import conv_layout
+    x = seeded((B, Cin, H, W), 11).cuda().to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    k = 3 if kind == "conv3" else 4
+    w = (seeded((Cout, Cin, k, k), 12) / (Cin * k * k) ** 0.5).cuda().to(torch.bfloat16).float()
+    b = seeded((Cout,), 13, 0.3).cuda()
+    out_hw = {"conv3": (H, W), "down": ((H - 2) // 2 + 1, (W - 2) // 2 + 1), "up": (2 * H, 2 * W)}[kind]
+    kid = {"conv3": 0, "down": 1, "up": 2}[kind]
+    stats = torch.zeros((2, Cout), dtype=torch.float32, device="cuda")
+    y = ops.conv_tc(x, conv_layout(w, kind).to(torch.bfloat16).contiguous(), b, kid, out_hw, col_stats=stats)
+    y_plain = ops.conv_tc(x, conv_layout(w, kind).to(torch.bfloat16).contiguous(), b, kid, out_hw)
+    torch.cuda.synchronize()
+    assert torch.equal(y, y_plain), "collecting statistics must not change the output"
+    yd = y.double()
+    s1, s2 = yd.sum((0, 2, 3)), (yd * yd).sum((0, 2, 3))
+    assert float((stats[0].double() - s1).abs().max()) <= 1e-4 * float(yd.abs().sum((0, 2, 3)).max()) + 1e-3
+    assert float((stats[1].double() - s2).abs().max()) <= 1e-4 * float(s2.max())

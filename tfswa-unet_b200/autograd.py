@@ -237,8 +237,12 @@ class ConvFn(torch.autograd.Function):
         wl = conv_layout(w, kind)
         stats = torch.zeros((2, b.shape[0]), dtype=torch.float32, device=x.device) if want_col_stats else None
         save_pre = epilogue == L.EPI_GELU and not want_col_stats
+        from . import functional as Fn
         if kind == "stem":
             res = ops.stem(x, wl, b, dtype, epilogue=epilogue, col_stats=stats, save_pre=save_pre)
+        elif (want_col_stats and epilogue == L.EPI_NONE and Fn.USE_TC and x.dtype == torch.bfloat16 and x.shape[1] % 32 == 0
+              and b.shape[0] % 16 == 0 and b.shape[0] <= 256):
+            res = ops.conv_tc(x, wl.to(torch.bfloat16).contiguous(), b, _KIND[kind], out_hw, col_stats=stats)   # train-mode BN sums from the epilogue
         else:
             res = ops.conv(x, wl, b, _KIND[kind], out_hw, epilogue=epilogue, col_stats=stats, save_pre=save_pre)
         y, pre = res if save_pre else (res, None)

@@ -27,6 +27,7 @@ struct TcConvParams {
   int64_t M;                  // GEMM rows per launch z (output pixels, or phase-grid cells)
   int K, BN, BK, KB, stages, OB;
   uint32_t tmem_cols;
+  float* col_stats;          // optional (2, Cout) fp32: sum / sum of squares of the stored outputs (train-mode BatchNorm)
 };
 
 constexpr int CV_BM = 128;
@@ -172,7 +173,12 @@ __global__ void __launch_bounds__(CV_THREADS) tc_conv_kernel(const __grid_consta
       }
       if (p.kind == CK_UP) {
         if (up_off >= 0) { store8(p.y + up_off + c, lo); store8(p.y + up_off + c + 8, hi); }
-      } else {
+      }
+      if (p.col_stats && !(p.kind == CK_UP ? up_off >= 0 : row_ok)) {   // rows that produce no output must not count
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { lo[j] = 0.f; hi[j] = 0.f; }
+      }
+      if (p.kind != CK_UP || p.col_stats) {
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf) {
           const int cc = c + hf * 8;
@@ -183,13 +189,30 @@ __global__ void __launch_bounds__(CV_THREADS) tc_conv_kernel(const __grid_consta
         }
       }
     }
-    if (p.kind != CK_UP) {
+    if (p.kind != CK_UP || p.col_stats) {
       fence_async_smem();
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (threadIdx.x == 64) {
+      if (p.kind != CK_UP && threadIdx.x == 64) {
         for (int bx = 0; bx < p.BN / p.OB; ++bx) tma_store_3d(&tmy, tiles + bx * box_bytes, n0 + bx * p.OB, (int)m0, 0);
-        tma_store_commit_wait();
       }
+      if (p.col_stats) {
+        // BatchNorm statistics of the tile from the staged bf16 values (rows without an output were staged as zeros):
+        // two threads per column walk the 128 rows of the swizzled tile, one fp32 atomic pair per column half and CTA
+        const int col = et >> 1, rhalf = et & 1;
+        if (col < p.BN) {
+          const uint32_t blk = (uint32_t)col >> ob_shift, chunk = ((uint32_t)col & (p.OB - 1)) >> 3;
+          float s1 = 0.f, s2 = 0.f;
+          for (int r = rhalf * 64; r < rhalf * 64 + 64; ++r) {
+            uint32_t off = (uint32_t)r * ob_bytes + chunk * 16u;
+            off ^= ((off >> 7) & oswz) << 4;
+            const float v = __bfloat162float(*reinterpret_cast<const bf16*>(tiles + blk * box_bytes + off + (col & 7) * 2));
+            s1 += v; s2 = fmaf(v, v, s2);
+          }
+          atomicAdd(p.col_stats + n0 + col, s1);
+          atomicAdd(p.col_stats + p.Cout + n0 + col, s2);
+        }
+      }
+      if (p.kind != CK_UP && threadIdx.x == 64) tma_store_commit_wait();
     }
   }
   tc_fence_before();
@@ -204,12 +227,13 @@ using namespace tfswa;
 extern "C" int tfswa_conv_tc_fwd(const tfswa_conv_args* a, const void* w_bf16, void* stream) {
   TFSWA_REQUIRE(a && a->x && w_bf16 && a->y && a->bias, "conv_tc: null pointer");
   TFSWA_REQUIRE(a->dtype == TFSWA_BF16, "conv_tc: bf16 activations only");
-  TFSWA_REQUIRE(!a->pre && !a->col_stats, "conv_tc: pre / col_stats outputs are not produced by this kernel");
+  TFSWA_REQUIRE(!a->pre, "conv_tc: the pre-activation output is not produced by this kernel");
+  TFSWA_REQUIRE(!a->col_stats || a->epilogue == TFSWA_EPI_NONE, "conv_tc: col_stats are those of the stored tensor (no epilogue)");
   TFSWA_REQUIRE(a->Cin % 32 == 0 && a->Cout % 16 == 0 && a->Cout <= 256, "conv_tc: need Cin%%32==0, Cout%%16==0, Cout<=256");
   TcConvParams p = {};
   p.x = (const bf16*)a->x; p.y = (bf16*)a->y; p.bias = a->bias;
   p.B = a->B; p.Hin = a->Hin; p.Win = a->Win; p.Cin = a->Cin; p.Hout = a->Hout; p.Wout = a->Wout; p.Cout = a->Cout;
-  p.kind = a->kind; p.epilogue = a->epilogue;
+  p.kind = a->kind; p.epilogue = a->epilogue; p.col_stats = a->col_stats;
   int taps, zdim = 1;
   if (a->kind == CK_CONV3) {
     TFSWA_REQUIRE(a->Hout == a->Hin && a->Wout == a->Win, "conv_tc 3x3: output size must equal input size");

@@ -194,8 +194,11 @@ def conv(x: Tensor, w_oihw: Tensor, wl: Tensor, b: Tensor, kind: str, out_hw, dt
     if _needs_grad(x, w_oihw, b):
         from .autograd import ConvFn
         return ConvFn.apply(x, w_oihw, b, kind, tuple(out_hw), dtype, epilogue, want_col_stats)
-    if (USE_TC and kind != "stem" and not want_col_stats and x.dtype == torch.bfloat16 and x.shape[1] % 32 == 0
-            and b.shape[0] % 16 == 0 and b.shape[0] <= 256):
+    if (USE_TC and kind != "stem" and x.dtype == torch.bfloat16 and x.shape[1] % 32 == 0
+            and b.shape[0] % 16 == 0 and b.shape[0] <= 256 and (not want_col_stats or epilogue == L.EPI_NONE)):
+        if want_col_stats:
+            stats = torch.zeros((2, b.shape[0]), dtype=torch.float32, device=x.device)
+            return ops.conv_tc(x, _bf16_of(wl), b, _KIND[kind], out_hw, col_stats=stats), stats
         return ops.conv_tc(x, _bf16_of(wl), b, _KIND[kind], out_hw, epilogue=epilogue)
     stats = torch.zeros((2, b.shape[0]), dtype=torch.float32, device=x.device) if want_col_stats else None
     if kind == "stem":

@@ -311,8 +311,10 @@ def conv(x: Tensor, w: Tensor, bias: Tensor, kind: int, out_hw: Tuple[int, int],
     return (y, pre) if save_pre else y
 
 
-def conv_tc(x: Tensor, w_bf16: Tensor, bias: Tensor, kind: int, out_hw: Tuple[int, int], *, epilogue: int = 0) -> Tensor:
-    """tcgen05 version of :func:`conv` (bf16, no pre / col_stats); w_bf16 = kernel-layout weights cast to bf16."""
+def conv_tc(x: Tensor, w_bf16: Tensor, bias: Tensor, kind: int, out_hw: Tuple[int, int], *, epilogue: int = 0,
+            col_stats: Optional[Tensor] = None) -> Tensor:
+    """tcgen05 version of :func:`conv` (bf16, no pre output); w_bf16 = kernel-layout weights cast to bf16.
+    ``col_stats`` (2, Cout) fp32, zero-initialised: receives the channel sums / sums of squares of the stored output."""
     _cuda(x, w_bf16)
     B, Cin, Hin, Win = x.shape
     Hout, Wout = out_hw
@@ -325,6 +327,11 @@ def conv_tc(x: Tensor, w_bf16: Tensor, bias: Tensor, kind: int, out_hw: Tuple[in
     a.x, a.y, a.bias = x.data_ptr(), y.data_ptr(), bias.data_ptr()
     a.B, a.Hin, a.Win, a.Cin, a.Hout, a.Wout, a.Cout = B, Hin, Win, Cin, Hout, Wout, Cout
     a.kind, a.epilogue, a.dtype = kind, epilogue, L.BF16
+    if col_stats is not None:
+        if tuple(col_stats.shape) != (2, Cout):
+            raise ValueError(f"conv_tc: col_stats {tuple(col_stats.shape)}, expected (2, {Cout})")
+        _f32c(col_stats)
+        a.col_stats = col_stats.data_ptr()
     taps = (9, 16, 16)[kind]
     _call("tfswa_conv_tc_fwd", C.byref(a), w_bf16.data_ptr(), _stream(), tag=f"conv_tc[kind={kind},Cin={Cin},Cout={Cout}]",
           work={"flops": 2 * B * Hout * Wout * Cout * Cin * (taps if kind != 2 else 4),
