@@ -14,6 +14,7 @@ enum { KIND_LINEAR = 0, KIND_CONV3 = 1, KIND_DOWN = 2, KIND_UP = 3 };
 
 // bf16 linear weight gradient on the tensor cores (wgrad_mma.cu); returns 1 when the shape is not covered
 int wgrad_mma_bf16(const tfswa_linear_args* a, const void* g, int64_t ldg, int64_t g_bs, float* dw, float* dbias, cudaStream_t st);
+int conv_wgrad_mma_bf16(const tfswa_conv_args* a, const void* g, float* dw, float* dbias, cudaStream_t st);
 
 struct IgemmParams {
   const void* x; int64_t ldx;
@@ -470,6 +471,10 @@ int tfswa_conv_wgrad(const tfswa_conv_args* a, const void* g, float* dw, float* 
     p.w_bs = (int64_t)a->Cout * 4 * a->Cin;
   } else TFSWA_REQUIRE(false, "conv_wgrad: bad kind %d", a->kind);
   cudaStream_t st = (cudaStream_t)stream;
+  if (a->dtype == TFSWA_BF16 && !getenv("TFSWA_CONV_WGRAD_SIMT")) {   // tensor-core path (wgrad_mma.cu); 1 = shape not covered
+    const int rc = conv_wgrad_mma_bf16(a, g, dw, dbias, st);
+    if (rc != 1) return rc;
+  }
 #define TFSWA_DISPATCH(T)                                                  \
   switch (kind) {                                                          \
     case KIND_CONV3: return launch_wgrad<T, KIND_CONV3>(p, zdim, st);      \

@@ -23,6 +23,9 @@ struct WgradMmaParams {
   float* dbias; int64_t bias_bs;
   int64_t M, rows_per_cta;
   int N, K, prologue, msplit;
+  // convolution mode (implicit GEMM over output pixels; X rows are gathered per filter tap, see igemm.cu a_offset)
+  int kind;                  // 0: 3x3 s1 p1, 1: 4x4 s2 p1, 2: one phase of the 4x4 s2 transposed conv (blockIdx.z / msplit = phase)
+  int B, Hin, Win, Cin, Hout, Wout, Hq, Wq, cblocks;
 };
 
 constexpr int WM_T = 64;            // output tile edge (n and k)
@@ -59,6 +62,7 @@ __device__ __forceinline__ void wm_cp_async8(void* smem_dst, const void* gsrc, i
 // what matters is bytes in flight.  G and X chunks go global -> shared with cp.async through a WM_STAGES-deep ring (the
 // first version staged one chunk through registers and was latency-bound: 1.4 TB/s, long-scoreboard stall 10 per issue,
 // profiles/r1zz_train_ncu_summary.md); the prologue, when there is one, is applied in place in shared memory.
+template <bool CONV>
 __global__ void __launch_bounds__(WM_THREADS) wgrad_mma_kernel(const WgradMmaParams p) {
   extern __shared__ __align__(16) uint8_t wm_smem[];
   typedef bf16 (*tile_t)[WM_MC][WM_PITCH];
@@ -66,7 +70,10 @@ __global__ void __launch_bounds__(WM_THREADS) wgrad_mma_kernel(const WgradMmaPar
   tile_t As = reinterpret_cast<tile_t>(wm_smem + WM_STAGES * WM_MC * WM_PITCH * 2);
   float2 (*Rs)[WM_MC] = reinterpret_cast<float2 (*)[WM_MC]>(wm_smem + 2 * WM_STAGES * WM_MC * WM_PITCH * 2);   // (mean, rstd) per token
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int k0 = blockIdx.x * WM_T, n0 = blockIdx.y * WM_T;
+  // linear: k-tile = 64 columns of X.  conv: k-tile = (filter tap, 64-channel block); zb = phase of the transposed conv
+  const int tap = CONV ? blockIdx.x / p.cblocks : 0;
+  const int k0 = CONV ? (blockIdx.x - tap * p.cblocks) * WM_T : blockIdx.x * WM_T, n0 = blockIdx.y * WM_T;
+  const int kdim = CONV ? p.Cin : p.K;                               // valid extent of this k-tile's column index
   const int zb = blockIdx.z / p.msplit, split = blockIdx.z % p.msplit;
   const bf16* x = p.x + (int64_t)zb * p.x_bs;
   const bf16* g = p.g + (int64_t)zb * p.g_bs;
@@ -77,7 +84,7 @@ __global__ void __launch_bounds__(WM_THREADS) wgrad_mma_kernel(const WgradMmaPar
 
   // staging: thread -> (token row lr + 32 i, 8 columns at lc), i = 0, 1, for G and for X
   const int lr = tid >> 3, lc = (tid & 7) * 8;
-  const bool g_ok = n0 + lc < p.N, a_ok = k0 + lc < p.K;          // N, K are multiples of 8
+  const bool g_ok = n0 + lc < p.N, a_ok = k0 + lc < kdim;         // N, K, Cin are multiples of 8
   // compute: warp -> 16 n rows (nt) x 32 k columns (kh)
   const int nt = warp & 3, kh = warp >> 2;
   float acc[4][4], bacc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -94,9 +101,33 @@ __global__ void __launch_bounds__(WM_THREADS) wgrad_mma_kernel(const WgradMmaPar
         const int64_t m = mc + r;
         const bool in = m < m_end;
         const int64_t ms = in ? m : m_begin;                       // any valid address when nothing is copied
-        wm_cp_async16(&Gs[slot][r][lc], g + ms * p.ldg + (g_ok ? n0 + lc : 0), (in && g_ok) ? 16 : 0);
-        wm_cp_async16(&As[slot][r][lc], x + ms * p.ldx + (a_ok ? k0 + lc : 0), (in && a_ok) ? 16 : 0);
-        if (rs && lc == 0) wm_cp_async8(&Rs[slot][r], rs + ms * 2, in ? 8 : 0);
+        if (!CONV) {
+          wm_cp_async16(&Gs[slot][r][lc], g + ms * p.ldg + (g_ok ? n0 + lc : 0), (in && g_ok) ? 16 : 0);
+          wm_cp_async16(&As[slot][r][lc], x + ms * p.ldx + (a_ok ? k0 + lc : 0), (in && a_ok) ? 16 : 0);
+          if (rs && lc == 0) wm_cp_async8(&Rs[slot][r], rs + ms * 2, in ? 8 : 0);
+        } else {
+          // output pixel (or phase-grid cell) of row m, the input pixel this tap reads, zero-fill outside the image
+          const int wdim = p.kind == 2 ? p.Wq : p.Wout, hw = (p.kind == 2 ? p.Hq : p.Hout) * wdim;
+          const int b = (int)(ms / hw), rem = (int)(ms - (int64_t)b * hw);
+          const int oy = rem / wdim, ox = rem - oy * wdim;
+          int iy, ix;
+          int64_t goff = ms * p.ldg;
+          bool g_in = in;
+          if (p.kind == 0) { iy = oy + tap / 3 - 1; ix = ox + tap % 3 - 1; }
+          else if (p.kind == 1) { iy = 2 * oy + (tap >> 2) - 1; ix = 2 * ox + (tap & 3) - 1; }
+          else {
+            const int py = zb >> 1, px = zb & 1, ta = tap >> 1, tb = tap & 1;
+            iy = py ? (ta ? oy : oy + 1) : (ta ? oy - 1 : oy);
+            ix = px ? (tb ? ox : ox + 1) : (tb ? ox - 1 : ox);
+            const int yy = 2 * oy + py, xx = 2 * ox + px;
+            g_in = in && yy < p.Hout && xx < p.Wout;                // phase-grid cell outside the output
+            goff = g_in ? (((int64_t)b * p.Hout + yy) * p.Wout + xx) * p.ldg : 0;
+          }
+          const bool x_in = g_in && iy >= 0 && iy < p.Hin && ix >= 0 && ix < p.Win;
+          const int64_t xoff = x_in ? (((int64_t)b * p.Hin + iy) * p.Win + ix) * p.Cin : 0;
+          wm_cp_async16(&Gs[slot][r][lc], g + goff + (g_ok ? n0 + lc : 0), (g_in && g_ok) ? 16 : 0);
+          wm_cp_async16(&As[slot][r][lc], x + xoff + (a_ok ? k0 + lc : 0), (x_in && a_ok) ? 16 : 0);
+        }
       }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
@@ -164,9 +195,10 @@ __global__ void __launch_bounds__(WM_THREADS) wgrad_mma_kernel(const WgradMmaPar
 #pragma unroll
     for (int kt = 0; kt < 4; ++kt) {
       const int k = k0 + kh * 32 + kt * 8 + 2 * tq;
-      if (k < p.K) {
-        atomicAdd(dw + (int64_t)n * p.K + k, acc[kt][h * 2]);
-        atomicAdd(dw + (int64_t)n * p.K + k + 1, acc[kt][h * 2 + 1]);
+      if (k < kdim) {
+        float* dst = dw + (int64_t)n * p.K + (CONV ? tap * p.Cin : 0) + k;
+        atomicAdd(dst, acc[kt][h * 2]);
+        atomicAdd(dst + 1, acc[kt][h * 2 + 1]);
       }
     }
     if (p.dbias && kh == 0 && tq == 0 && blockIdx.x == 0) atomicAdd(p.dbias + (int64_t)zb * p.bias_bs + n, bacc[h * 2]);
@@ -192,14 +224,49 @@ int wgrad_mma_bf16(const tfswa_linear_args* a, const void* g, int64_t ldg, int64
   dim3 grid(kt, nt, a->batch * p.msplit);
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(wgrad_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WM_SMEM) != cudaSuccess) {
+    if (cudaFuncSetAttribute(wgrad_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, WM_SMEM) != cudaSuccess) {
       set_error("wgrad_mma: cudaFuncSetAttribute failed");
       return TFSWA_ECUDA;
     }
     attr_set = true;
   }
-  wgrad_mma_kernel<<<grid, WM_THREADS, WM_SMEM, st>>>(p);
+  wgrad_mma_kernel<false><<<grid, WM_THREADS, WM_SMEM, st>>>(p);
   return check_launch("linear_wgrad");
+}
+
+// bf16 convolution weight gradient (3x3 / 4x4-stride-2 / 4-phase transposed conv; dw in the layout of tfswa_conv_args.w);
+// returns 1 when the shape is outside this kernel
+int conv_wgrad_mma_bf16(const tfswa_conv_args* a, const void* g, float* dw, float* dbias, cudaStream_t st) {
+  if (a->Cin % 8 || a->Cout % 8 || (((uintptr_t)a->x | (uintptr_t)g) & 15) || a->kind < 0 || a->kind > 2) return 1;
+  WgradMmaParams p = {};
+  p.x = (const bf16*)a->x; p.g = (const bf16*)g; p.ldg = a->Cout; p.dw = dw; p.dbias = dbias; p.bias_bs = 0;
+  p.kind = a->kind; p.B = a->B; p.Hin = a->Hin; p.Win = a->Win; p.Cin = a->Cin; p.Hout = a->Hout; p.Wout = a->Wout;
+  p.N = a->Cout; p.prologue = TFSWA_PRO_NONE;
+  int taps, zdim = 1;
+  if (a->kind == 0) { taps = 9; p.M = (int64_t)a->B * a->Hout * a->Wout; }
+  else if (a->kind == 1) { taps = 16; p.M = (int64_t)a->B * a->Hout * a->Wout; }
+  else { taps = 4; p.Hq = (a->Hout + 1) / 2; p.Wq = (a->Wout + 1) / 2; p.M = (int64_t)a->B * p.Hq * p.Wq; zdim = 4; }
+  p.K = taps * a->Cin;
+  p.w_bs = (int64_t)a->Cout * p.K;                     // phase stride of the transposed conv's (4, Cout, 2, 2, Cin) layout
+  p.cblocks = (a->Cin + WM_T - 1) / WM_T;
+  const int kt = taps * p.cblocks, nt = (p.N + WM_T - 1) / WM_T;
+  int64_t want = 148 * 8 / ((int64_t)kt * nt * zdim);
+  if (want < 1) want = 1;
+  const int64_t max_split = (p.M + 511) / 512;
+  if (want > max_split) want = max_split;
+  p.rows_per_cta = ((p.M + want - 1) / want + WM_MC - 1) / WM_MC * WM_MC;
+  p.msplit = (int)((p.M + p.rows_per_cta - 1) / p.rows_per_cta);
+  dim3 grid(kt, nt, zdim * p.msplit);
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(wgrad_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WM_SMEM) != cudaSuccess) {
+      set_error("conv_wgrad_mma: cudaFuncSetAttribute failed");
+      return TFSWA_ECUDA;
+    }
+    attr_set = true;
+  }
+  wgrad_mma_kernel<true><<<grid, WM_THREADS, WM_SMEM, st>>>(p);
+  return check_launch("conv_wgrad");
 }
 
 }  // namespace tfswa
