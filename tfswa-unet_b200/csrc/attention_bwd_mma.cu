@@ -49,6 +49,10 @@ __device__ __forceinline__ void b_cp_async16(void* smem_dst, const void* gsrc) {
 __device__ __forceinline__ void b_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void b_cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// resident CTAs per SM the window instantiations are compiled for: one window is little work behind a long load chain, so
+// at head_dim 4 / 8 a third CTA (80 registers, some spills) beats two at 128 (stage 1, B=8: 4.03 -> 3.68 ms); at head_dim 16
+// the spills cost more than the occupancy buys (0.60 vs 0.73 ms)
+template <int D> __host__ __device__ constexpr int bw_win_ctas() { return D <= 8 ? 3 : 2; }
 constexpr int BW_T = 64;             // rows per streamed tile
 constexpr int BW_THREADS = 256;      // 8 warps = 8 heads
 template <int D> __host__ __device__ constexpr int bw_mt() { return D == 16 ? 2 : 4; }   // 16-row tiles owned by a warp (register budget)
@@ -82,12 +86,15 @@ __device__ __forceinline__ void load_a_frag(uint32_t (&a)[(D + 15) / 16][4], con
 
 // token of element n of sequence / window `row`.  Returns false when n lies outside the sequence; real = false for the
 // zero-padded tokens of a window (present as keys with k|v = pad_kv, absent as queries).
+// Windows: `wtok` is the CTA's shared table of the 64 window positions (token index, -1 for a zero-padded position),
+// filled once per CTA - the pad / roll / partition map costs four integer divisions per lookup otherwise, which was
+// more than half of the window kernels' instructions.
 template <bool WIN>
-__device__ __forceinline__ bool seq_token(const AttnParams& p, int row, int n, int N, int64_t tok_base, int64_t tok_stride,
+__device__ __forceinline__ bool seq_token(const int64_t* wtok, int n, int N, int64_t tok_base, int64_t tok_stride,
                                           int64_t& tok, bool& real) {
   tok = 0; real = false;
   if (n >= N) return false;
-  if (WIN) tok = token_of<true>(p, row, n, real);
+  if (WIN) { const int64_t t = wtok[n]; real = t >= 0; tok = real ? t : 0; }
   else { tok = tok_base + (int64_t)n * tok_stride; real = true; }
   return true;
 }
@@ -113,7 +120,7 @@ template <int D> __host__ __device__ constexpr int bw_smem_bytes() { return 3 * 
 // dq (and D_i = dO_i . O_i): grid (ceil(N/64), sequences, heads/8); windows: (windows, ceil(64/rows per CTA), heads/8)
 // ------------------------------------------------------------------------------------------------
 template <int D, bool WIN>
-__global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_dq_mma_kernel(const AttnParams p) {
+__global__ void __launch_bounds__(BW_THREADS, WIN ? bw_win_ctas<D>() : 2) attn_bwd_dq_mma_kernel(const AttnParams p) {
   constexpr int CS = 8 * D, PITCH = CS + 8, KS = (D + 15) / 16, DN = (D + 7) / 8, CPT = CS / 8, MT = bw_mt<D>();
   extern __shared__ __align__(16) uint8_t bw_smem[];
   typedef bf16 (*tile_t)[BW_T][PITCH];
@@ -124,9 +131,13 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_dq_mma_kernel(const At
   const int N = WIN ? p.ws * p.ws : (p.geom == TFSWA_GEOM_TSA ? p.H : p.W);
   const int T = (N + BW_T - 1) / BW_T;
   int64_t tok_base = 0, tok_stride = 1;
+  __shared__ int64_t s_wtok[WIN ? BW_T : 1];
   if (!WIN) {
     if (p.geom == TFSWA_GEOM_TSA) { const int b = row / p.W; tok_base = (int64_t)b * p.H * p.W + (row - b * p.W); tok_stride = p.W; }
     else { tok_base = (int64_t)row * p.W; }
+  } else {
+    if (tid < BW_T) { bool v; const int64_t tk = token_of<true>(p, row, tid, v); s_wtok[tid] = v ? tk : -1; }
+    __syncthreads();
   }
   const bf16* qkv = (const bf16*)p.qkv;
   const int cbase = warp * D, head = slab * 8 + warp;
@@ -138,7 +149,7 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_dq_mma_kernel(const At
         const int j = v / (2 * CPT), rem = v - j * 2 * CPT, part = rem / CPT, chunk = rem - part * CPT;
         bf16* dst = part ? &Vs[b][j][chunk * 8] : &Ks[b][j][chunk * 8];
         int64_t tok; bool real;
-        const bool in = seq_token<WIN>(p, row, tt * BW_T + j, N, tok_base, tok_stride, tok, real);
+        const bool in = seq_token<WIN>(s_wtok, tt * BW_T + j, N, tok_base, tok_stride, tok, real);
         if (in && real) {
           b_cp_async16(dst, qkv + tok * p.ldq + (1 + part) * p.C + slab * CS + chunk * 8);
         } else if (WIN && in) {                                        // zero-padded window token: k|v = folded qkv bias
@@ -160,8 +171,8 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_dq_mma_kernel(const At
 #pragma unroll
   for (int mt = 0; mt < MT; ++mt) {
     int64_t tok0, tok1; bool r0, r1;
-    const bool ok0 = seq_token<WIN>(p, row, q0 + mt * 16 + g, N, tok_base, tok_stride, tok0, r0) && r0;
-    const bool ok1 = seq_token<WIN>(p, row, q0 + mt * 16 + g + 8, N, tok_base, tok_stride, tok1, r1) && r1;
+    const bool ok0 = seq_token<WIN>(s_wtok, q0 + mt * 16 + g, N, tok_base, tok_stride, tok0, r0) && r0;
+    const bool ok1 = seq_token<WIN>(s_wtok, q0 + mt * 16 + g + 8, N, tok_base, tok_stride, tok1, r1) && r1;
     load_a_frag<D>(qa[mt], qkv + slab * CS + cbase, p.ldq, tok0, tok1, ok0, ok1, t);
     load_a_frag<D>(ga[mt], (const bf16*)p.dout + slab * CS + cbase, p.ldo, tok0, tok1, ok0, ok1, t);
     uint32_t oa[KS][4];
@@ -254,7 +265,7 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_dq_mma_kernel(const At
 #pragma unroll
     for (int h2 = 0; h2 < 2; ++h2) {
       int64_t tok; bool real;                              // recomputed rather than kept live across the key loop
-      if (!(seq_token<WIN>(p, row, q0 + mt * 16 + g + h2 * 8, N, tok_base, tok_stride, tok, real) && real)) continue;
+      if (!(seq_token<WIN>(s_wtok, q0 + mt * 16 + g + h2 * 8, N, tok_base, tok_stride, tok, real) && real)) continue;
       if (D >= 8) {
 #pragma unroll
         for (int dn = 0; dn < DN; ++dn)
@@ -274,7 +285,7 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_dq_mma_kernel(const At
 // dk, dv: same grids as the dq kernel; needs dsum from the dq kernel
 // ------------------------------------------------------------------------------------------------
 template <int D, bool WIN>
-__global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_dkv_mma_kernel(const AttnParams p) {
+__global__ void __launch_bounds__(BW_THREADS, WIN ? bw_win_ctas<D>() : 2) attn_bwd_dkv_mma_kernel(const AttnParams p) {
   constexpr int CS = 8 * D, PITCH = CS + 8, KS = (D + 15) / 16, DN = (D + 7) / 8, CPT = CS / 8, MT = bw_mt<D>();
   extern __shared__ __align__(16) uint8_t bw_smem[];
   typedef bf16 (*tile_t)[BW_T][PITCH];
@@ -286,9 +297,13 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_dkv_mma_kernel(const A
   const int N = WIN ? p.ws * p.ws : (p.geom == TFSWA_GEOM_TSA ? p.H : p.W);
   const int T = (N + BW_T - 1) / BW_T;
   int64_t tok_base = 0, tok_stride = 1;
+  __shared__ int64_t s_wtok[WIN ? BW_T : 1];
   if (!WIN) {
     if (p.geom == TFSWA_GEOM_TSA) { const int b = row / p.W; tok_base = (int64_t)b * p.H * p.W + (row - b * p.W); tok_stride = p.W; }
     else { tok_base = (int64_t)row * p.W; }
+  } else {
+    if (tid < BW_T) { bool v; const int64_t tk = token_of<true>(p, row, tid, v); s_wtok[tid] = v ? tk : -1; }
+    __syncthreads();
   }
   const bf16* qkv = (const bf16*)p.qkv;
   const bf16* dout = (const bf16*)p.dout;
@@ -301,7 +316,7 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_dkv_mma_kernel(const A
         const int j = v / (2 * CPT), rem = v - j * 2 * CPT, part = rem / CPT, chunk = rem - part * CPT;
         bf16* dst = part ? &Gs[b][j][chunk * 8] : &Qs[b][j][chunk * 8];
         int64_t tok; bool real;
-        if (seq_token<WIN>(p, row, tt * BW_T + j, N, tok_base, tok_stride, tok, real) && real) {
+        if (seq_token<WIN>(s_wtok, tt * BW_T + j, N, tok_base, tok_stride, tok, real) && real) {
           b_cp_async16(dst, part ? dout + tok * p.ldo + slab * CS + chunk * 8 : qkv + tok * p.ldq + slab * CS + chunk * 8);
         } else {                                                         // absent or zero-padded (cropped) query
           *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
@@ -311,7 +326,7 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_dkv_mma_kernel(const A
         const int j = v >> 3, h = v & 7;
         float l = CUDART_INF_F, d = 0.f;                                 // +inf -> p = 0 for absent queries
         int64_t tok; bool real;
-        if (seq_token<WIN>(p, row, tt * BW_T + j, N, tok_base, tok_stride, tok, real) && real) {
+        if (seq_token<WIN>(s_wtok, tt * BW_T + j, N, tok_base, tok_stride, tok, real) && real) {
           l = p.lse[tok * p.heads + slab * 8 + h];
           d = p.dsum[tok * p.heads + slab * 8 + h];
         }
@@ -329,8 +344,8 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_dkv_mma_kernel(const A
 #pragma unroll
   for (int mt = 0; mt < MT; ++mt) {
     int64_t tok0, tok1; bool r0, r1;
-    const bool in0 = seq_token<WIN>(p, row, k0 + mt * 16 + g, N, tok_base, tok_stride, tok0, r0);
-    const bool in1 = seq_token<WIN>(p, row, k0 + mt * 16 + g + 8, N, tok_base, tok_stride, tok1, r1);
+    const bool in0 = seq_token<WIN>(s_wtok, k0 + mt * 16 + g, N, tok_base, tok_stride, tok0, r0);
+    const bool in1 = seq_token<WIN>(s_wtok, k0 + mt * 16 + g + 8, N, tok_base, tok_stride, tok1, r1);
     load_a_frag<D>(ka[mt], qkv + p.C + slab * CS + cbase, p.ldq, tok0, tok1, in0 && r0, in1 && r1, t);
     load_a_frag<D>(va[mt], qkv + 2 * p.C + slab * CS + cbase, p.ldq, tok0, tok1, in0 && r0, in1 && r1, t);
     if (WIN) {
@@ -411,7 +426,7 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_dkv_mma_kernel(const A
 #pragma unroll
     for (int h2 = 0; h2 < 2; ++h2) {
       int64_t tok; bool real;                              // recomputed rather than kept live across the query loop
-      if (!seq_token<WIN>(p, row, k0 + mt * 16 + g + h2 * 8, N, tok_base, tok_stride, tok, real)) continue;
+      if (!seq_token<WIN>(s_wtok, k0 + mt * 16 + g + h2 * 8, N, tok_base, tok_stride, tok, real)) continue;
       if (WIN && !real) {                                  // zero-padded key: its gradient belongs to the folded qkv bias
         if (p.dpad) {
           float* dp = p.dpad + slab * CS;
