@@ -160,3 +160,47 @@ def test_fullsize_training_step_is_finite():
     assert all(".0.bias" in n or n.endswith("downsample.0.bias") or n.endswith("upsample.0.bias") for n in zero), zero
     stuck = [n for (n, p), a in zip(model.named_parameters(), before) if torch.equal(a, p.detach()) and n not in zero]
     assert not stuck, f"parameters with a gradient that did not take an AdamW step: {stuck[:5]}"
+
+
+def test_fullsize_forward_is_bitwise_reproducible():
+    """eval forward has no atomics: any run-to-run difference is a synchronisation bug (this test found a barrier race in the
+    tcgen05 attention kernel that corrupted 32 rows of one CTA in about one full-size launch out of ten)"""
+    import tfswa_unet_b200 as T
+    T.set_precision("bf16")
+    torch.manual_seed(0)
+    model = T.TFSWAUNet(2, 2, **MODEL).eval().cuda()
+    x = seeded((2, 2, H, W), 960, 1.0).cuda()
+    with torch.no_grad():
+        ref = model(x, return_logits=True)[1]
+        for i in range(10):
+            junk = torch.randn(32 << 20, device="cuda")                 # perturb allocator state, L2 and leftover shared memory
+            got = model(x, return_logits=True)[1]
+            del junk
+            assert torch.equal(got, ref), f"run {i}: {int((got != ref).sum())} logits differ, max {float((got - ref).abs().max()):.3e}"
+
+
+@pytest.mark.parametrize("geom,C,h,w", [(0, 32, H, W), (1, 32, H, W), (2, 32, H, W), (0, 64, 512, 258), (1, 128, 256, 129)])
+def test_fullsize_attention_backward_is_bitwise_reproducible(geom, C, h, w):
+    """dq|dk|dv are written without atomics: they must not change from launch to launch"""
+    from tfswa_unet_b200 import ops
+    B, heads = 2, 8
+    M = B * h * w
+    qkv = seeded((M, 3 * C), 970 + geom, 1.0).cuda().to(torch.bfloat16)
+    dout = seeded((M, C), 971 + geom, 1.0).cuda().to(torch.bfloat16)
+    pad_kv = seeded((2 * C,), 972, 0.5).cuda().float().contiguous() if geom == 2 else None
+    out = torch.empty((M, C), dtype=torch.bfloat16, device="cuda")
+    lse = torch.empty((M, heads), dtype=torch.float32, device="cuda")
+    kw = dict(ws=8, shift=4, pad_kv=pad_kv) if geom == 2 else {}
+    ops.attention(qkv, out, B, h, w, C, heads, geom, lse=lse, **kw)
+    ref = None
+    for i in range(6):
+        dqkv = torch.empty((M, 3 * C), dtype=torch.bfloat16, device="cuda")
+        dsum = torch.empty((M, heads), dtype=torch.float32, device="cuda")
+        dpad = torch.zeros((2 * C,), dtype=torch.float32, device="cuda") if geom == 2 else None
+        ops.attention_bwd(qkv, out, lse, dout, dqkv, dsum, B, h, w, C, heads, geom, dpad=dpad, **kw)
+        torch.cuda.synchronize()
+        assert torch.isfinite(dqkv.float()).all()
+        if ref is None:
+            ref = dqkv
+        else:
+            assert torch.equal(dqkv, ref), f"launch {i}: {int((dqkv != ref).sum())} elements differ"
