@@ -12,6 +12,8 @@
 // the accumulators already in A-operand layout for dV += P^T dO and dK += dS^T Q.  Operands with the reduction index
 // along tokens are read from the token-major shared-memory tiles with ldmatrix.trans.
 // One CTA = one sequence (or window: N = 64, one tile) x 64 rows x 8 heads (warp = head); tiles arrive by cp.async into a 3-deep ring.
+// head_dim 4 uses 4 of the 8 K slots of its m16n8k8 MMAs; two of the spare slots carry -D_i (as a bf16 hi + lo pair,
+// 16 mantissa bits) against ones in the other operand, so dP - D comes out of the dP MMA and dS costs one multiply.
 // Replaces the CUDA-core attn_bwd_dq/dkv kernels for these shapes (55 % of a bf16 training step before).
 #include "attn_common.cuh"
 
@@ -43,6 +45,12 @@ __device__ __forceinline__ uint32_t b_pack(float lo, float hi) {
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(y) : "f"(hi), "f"(lo));
   return y;
 }
+// x as two bf16 values whose sum carries 16 mantissa bits: packed (hi, lo) for two adjacent K slots of an MMA operand
+__device__ __forceinline__ uint32_t b_split2(float x) {
+  const float hi = __bfloat162float(__float2bfloat16_rn(x));
+  return b_pack(hi, x - hi);
+}
+constexpr uint32_t B_ONES2 = 0x3F803F80u;        // bf16 (1, 1)
 __device__ __forceinline__ void b_cp_async16(void* smem_dst, const void* gsrc) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
 }
@@ -190,6 +198,7 @@ __global__ void __launch_bounds__(BW_THREADS, WIN ? bw_win_ctas<D>() : 2) attn_b
     d0 += __shfl_xor_sync(0xffffffffu, d0, 1); d0 += __shfl_xor_sync(0xffffffffu, d0, 2);
     d1 += __shfl_xor_sync(0xffffffffu, d1, 1); d1 += __shfl_xor_sync(0xffffffffu, d1, 2);
     dsm[mt][0] = d0; dsm[mt][1] = d1;
+    if (D == 4 && t == 2) { ga[mt][0][0] = b_split2(-d0); ga[mt][0][1] = b_split2(-d1); }   // K slots 4, 5 of my two rows
     lse[mt][0] = ok0 ? p.lse[tok0 * p.heads + head] : CUDART_INF_F;
     lse[mt][1] = ok1 ? p.lse[tok1 * p.heads + head] : CUDART_INF_F;
     if (t == 0) {
@@ -219,6 +228,7 @@ __global__ void __launch_bounds__(BW_THREADS, WIN ? bw_win_ctas<D>() : 2) attn_b
         vb[nt][ks][0] = dcol < D ? *reinterpret_cast<const uint32_t*>(&Vs[b][nt * 8 + g][cbase + dcol]) : 0u;
         vb[nt][ks][1] = dcol + 8 < D ? *reinterpret_cast<const uint32_t*>(&Vs[b][nt * 8 + g][cbase + dcol + 8]) : 0u;
       }
+      if (D == 4 && t == 2) vb[nt][0][0] = B_ONES2;
     }
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {
@@ -246,7 +256,7 @@ __global__ void __launch_bounds__(BW_THREADS, WIN ? bw_win_ctas<D>() : 2) attn_b
               const int h2 = i >> 1;
               float pw = fast_exp2(fmaf(s[i], c, -lse[mt][h2]));
               if (nt * 8 + 2 * t + (i & 1) >= kcount) pw = 0.f;     // absent keys of the last tile
-              ds[i] = pw * (dp[i] - dsm[mt][h2]);
+              ds[i] = D == 4 ? pw * dp[i] : pw * (dp[i] - dsm[mt][h2]);
             }
             pa[half * 2 + 0] = b_pack(ds[0], ds[1]);
             pa[half * 2 + 1] = b_pack(ds[2], ds[3]);
@@ -352,6 +362,7 @@ __global__ void __launch_bounds__(BW_THREADS, WIN ? bw_win_ctas<D>() : 2) attn_b
       if (in0 && !r0) { fill_a_frag_row<D>(ka[mt], p.pad_kv + slab * CS + cbase, 0, t); fill_a_frag_row<D>(va[mt], p.pad_kv + p.C + slab * CS + cbase, 0, t); }
       if (in1 && !r1) { fill_a_frag_row<D>(ka[mt], p.pad_kv + slab * CS + cbase, 1, t); fill_a_frag_row<D>(va[mt], p.pad_kv + p.C + slab * CS + cbase, 1, t); }
     }
+    if (D == 4 && t == 2) { va[mt][0][0] = B_ONES2; va[mt][0][1] = B_ONES2; }
 #pragma unroll
     for (int dn = 0; dn < DN; ++dn) {
       dk[mt][dn][0] = dk[mt][dn][1] = dk[mt][dn][2] = dk[mt][dn][3] = 0.f;
@@ -377,6 +388,7 @@ __global__ void __launch_bounds__(BW_THREADS, WIN ? bw_win_ctas<D>() : 2) attn_b
         gb[nt][ks][0] = dcol < D ? *reinterpret_cast<const uint32_t*>(&Gs[b][nt * 8 + g][cbase + dcol]) : 0u;
         gb[nt][ks][1] = dcol + 8 < D ? *reinterpret_cast<const uint32_t*>(&Gs[b][nt * 8 + g][cbase + dcol + 8]) : 0u;
       }
+      if (D == 4 && t == 2) gb[nt][0][0] = b_split2(-Ds[b][warp][nt * 8 + g]);
     }
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {
@@ -405,7 +417,7 @@ __global__ void __launch_bounds__(BW_THREADS, WIN ? bw_win_ctas<D>() : 2) attn_b
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               pw[i] = fast_exp2(fmaf(s[i], c, -((i & 1) ? l2.y : l2.x)));
-              ds[i] = pw[i] * (dp[i] - ((i & 1) ? d2.y : d2.x));
+              ds[i] = D == 4 ? pw[i] * dp[i] : pw[i] * (dp[i] - ((i & 1) ? d2.y : d2.x));
             }
             pa[half * 2 + 0] = b_pack(pw[0], pw[1]); pa[half * 2 + 1] = b_pack(pw[2], pw[3]);
             da[half * 2 + 0] = b_pack(ds[0], ds[1]); da[half * 2 + 1] = b_pack(ds[2], ds[3]);
