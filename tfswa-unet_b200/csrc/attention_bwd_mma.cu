@@ -16,6 +16,7 @@
 // 16 mantissa bits) against ones in the other operand, so dP - D comes out of the dP MMA and dS costs one multiply.
 // Replaces the CUDA-core attn_bwd_dq/dkv kernels for these shapes (55 % of a bf16 training step before).
 #include "attn_common.cuh"
+#include <type_traits>
 
 namespace tfswa {
 
@@ -238,34 +239,40 @@ __global__ void __launch_bounds__(BW_THREADS, WIN ? bw_win_ctas<D>() : 2) attn_b
         b_ldsm_x2_trans(kt[kk][dn][0], kt[kk][dn][1], &Ks[b][kk * 16 + (lane & 15)][col]);
       }
     }
+    // Only the last tile of a sequence holds absent keys; the per-element mask (a compare + select per exponential) is
+    // compiled into that tile's copy of the loop only.
+    auto tile_body = [&](auto masked) {
+      constexpr bool MASK = decltype(masked)::value;
 #pragma unroll
-    for (int mt = 0; mt < MT; ++mt) {
-      if (mt < mt_valid) {
+      for (int mt = 0; mt < MT; ++mt) {
+        if (mt < mt_valid) {
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-          uint32_t pa[4];
+          for (int kk = 0; kk < 4; ++kk) {
+            uint32_t pa[4];
 #pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            const int nt = 2 * kk + half;
-            float s[4], dp[4];
-            s_mma<D>(s, qa[mt], kb[nt]);
-            s_mma<D>(dp, ga[mt], vb[nt]);
-            float ds[4];
+            for (int half = 0; half < 2; ++half) {
+              const int nt = 2 * kk + half;
+              float s[4], dp[4];
+              s_mma<D>(s, qa[mt], kb[nt]);
+              s_mma<D>(dp, ga[mt], vb[nt]);
+              float ds[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int h2 = i >> 1;
-              float pw = fast_exp2(fmaf(s[i], c, -lse[mt][h2]));
-              if (nt * 8 + 2 * t + (i & 1) >= kcount) pw = 0.f;     // absent keys of the last tile
-              ds[i] = D == 4 ? pw * dp[i] : pw * (dp[i] - dsm[mt][h2]);
+              for (int i = 0; i < 4; ++i) {
+                const int h2 = i >> 1;
+                float pw = fast_exp2(fmaf(s[i], c, -lse[mt][h2]));
+                if (MASK && nt * 8 + 2 * t + (i & 1) >= kcount) pw = 0.f;     // absent keys of the last tile
+                ds[i] = D == 4 ? pw * dp[i] : pw * (dp[i] - dsm[mt][h2]);
+              }
+              pa[half * 2 + 0] = b_pack(ds[0], ds[1]);
+              pa[half * 2 + 1] = b_pack(ds[2], ds[3]);
             }
-            pa[half * 2 + 0] = b_pack(ds[0], ds[1]);
-            pa[half * 2 + 1] = b_pack(ds[2], ds[3]);
-          }
 #pragma unroll
-          for (int dn = 0; dn < DN; ++dn) b_mma16816(dq[mt][dn], pa, kt[kk][dn][0], kt[kk][dn][1]);
+            for (int dn = 0; dn < DN; ++dn) b_mma16816(dq[mt][dn], pa, kt[kk][dn][0], kt[kk][dn][1]);
+          }
         }
       }
-    }
+    };
+    if (kcount < BW_T) tile_body(std::true_type{}); else tile_body(std::false_type{});
   }
   b_cp_wait<0>();
   // ---- dq = scale * acc ----
