@@ -41,3 +41,18 @@ def test_saturation_and_monotone_argument():
     x = np.array([-1e4, -100.0, -8.0, 8.0, 100.0, 1e4])
     y = gelu_hidden_model(x)
     assert np.allclose(y[:3], 0.0, atol=1e-6) and np.allclose(y[3:], x[3:], rtol=1e-6)
+
+
+def test_fast_gelu_gradient_formula_matches_exact():
+    """common.cuh::gelu_erf_grad_fast restated in float64: A&S 7.1.26 erf and the Gaussian density share exp(-x^2/2)"""
+    import numpy as np
+    from math import erf, sqrt, pi
+    x = np.linspace(-12, 12, 200001)
+    z = np.abs(x) / sqrt(2.0)
+    t = 1.0 / (1.0 + 0.3275911 * z)
+    e = np.exp(-z * z)
+    p = ((((1.061405429 * t - 1.453152027) * t + 1.421413741) * t - 0.284496736) * t + 0.254829592)
+    erfv = np.sign(x) * (1.0 - p * t * e)
+    fast = 0.5 + 0.5 * erfv + x * (e / sqrt(2.0 * pi))
+    exact = np.array([0.5 * (1.0 + erf(v / sqrt(2.0))) for v in x]) + x * np.exp(-0.5 * x * x) / sqrt(2.0 * pi)
+    assert float(np.abs(fast - exact).max()) < 2e-7          # bf16 resolution of the gradient is 4e-3

@@ -127,7 +127,7 @@ __global__ void affine_act_kernel(const T* __restrict__ v, const float* __restri
     }
     if (epilogue == TFSWA_EPI_GELU) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) a[j] = gelu_erf(a[j]);
+      for (int j = 0; j < 8; ++j) a[j] = gelu_for<T>(a[j]);
     }
     if (r1) { float t[8]; load8(r1 + e, t);
 #pragma unroll

@@ -20,7 +20,7 @@ __global__ void act_bwd_kernel(const T* __restrict__ g, const T* __restrict__ pr
     load8(pre + e, b);
     if (mode == 0) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) a[j] *= gelu_erf_grad(b[j]);
+      for (int j = 0; j < 8; ++j) a[j] *= gelu_grad_for<T>(b[j]);
     } else {
       const int c = (int)(e % C);
 #pragma unroll
@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(256) affine_act_bwd_kernel(const T* __restrict
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float t = x[j] * sc[j] + sh[j];
-      const float gt = (epilogue == TFSWA_EPI_GELU) ? g[j] * gelu_erf_grad(t) : g[j];
+      const float gt = (epilogue == TFSWA_EPI_GELU) ? g[j] * gelu_grad_for<T>(t) : g[j];
       asc[j] += gt * x[j];
       ash[j] += gt;
       g[j] = gt * sc[j];

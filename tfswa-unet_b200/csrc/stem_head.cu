@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(ST_TH * ST_TW) stem_kernel(const float* __rest
   }
   if (epilogue == TFSWA_EPI_GELU) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) acc[i] = gelu_erf(acc[i]);
+    for (int i = 0; i < 32; ++i) acc[i] = gelu_for<T>(acc[i]);
   }
 #pragma unroll
   for (int i = 0; i < 32; i += 8) if (i < nco) { float t[8];
@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(256) head_tail_kernel(const T* __restrict__ v,
     float t[8]; load8(row + c, t);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float u = gelu_erf(t[j] * s_sc[c + j] + s_sh[c + j]);
+      const float u = gelu_for<T>(t[j] * s_sc[c + j] + s_sh[c + j]);
 #pragma unroll
       for (int o = 0; o < 8; ++o) if (o < Cout) acc[o] = fmaf(u, s_w[o * C + c + j], acc[o]);
     }
@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(256) head_tail_bwd_kernel(const T* __restrict_
       float t[8]; load8(row + c, t);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float u = gelu_erf(t[j] * s_sc[c + j] + s_sh[c + j]);
+        const float u = gelu_for<T>(t[j] * s_sc[c + j] + s_sh[c + j]);
 #pragma unroll
         for (int o = 0; o < 8; ++o) if (o < Cout) logit[o] = fmaf(u, s_w[o * C + c + j], logit[o]);
       }
@@ -310,11 +310,11 @@ __global__ void __launch_bounds__(256) head_tail_bwd_kernel(const T* __restrict_
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float tt = t[j] * s_sc[c + j] + s_sh[c + j];
-        const float u = gelu_erf(tt);
+        const float u = gelu_for<T>(tt);
         float du = 0.f;
 #pragma unroll
         for (int o = 0; o < 8; ++o) if (o < Cout) du = fmaf(dl[o], s_w[o * C + c + j], du);
-        const float gt = ok ? du * gelu_erf_grad(tt) : 0.f;
+        const float gt = ok ? du * gelu_grad_for<T>(tt) : 0.f;
         out[j] = gt * s_sc[c + j];
         const float r1 = warp_sum(gt * t[j]), r2 = warp_sum(gt);
         if (lane == 0) { atomicAdd(&a_sc[c + j], r1); atomicAdd(&a_sh[c + j], r2); }
