@@ -16,6 +16,7 @@
 // 16 mantissa bits) against ones in the other operand, so dP - D comes out of the dP MMA and dS costs one multiply.
 // Replaces the CUDA-core attn_bwd_dq/dkv kernels for these shapes (55 % of a bf16 training step before).
 #include "attn_common.cuh"
+#include <stdlib.h>
 #include <type_traits>
 
 namespace tfswa {
@@ -487,6 +488,269 @@ __global__ void __launch_bounds__(BW_THREADS, WIN ? bw_win_ctas<D>() : 2) attn_b
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// One-pass backward for head_dim 4 (TSA / FSA): the dq / dkv pair above computes every P_ij twice, and at head_dim 4 the
+// exponentials and the instructions around them are the whole cost.  Here each (key block, query tile) pair is visited
+// once: S^T, dP^T, P^T and dS^T are formed in the dkv orientation (rows = keys), dV += P^T dO and dK += dS^T Q accumulate in
+// registers over the query loop, and dQ += dS K uses the SAME dS^T fragments, transposed in registers with movmatrix, into
+// an fp32 accumulator of the whole sequence in shared memory (N x 32 channels, pitch 36 floats: conflict-free float2
+// read-modify-write).  One CTA = one sequence x 8 heads, 16 warps: warp = (head, half of the query n-tiles), so the two
+// warps of a head own disjoint rows of the dQ accumulator (no atomics, deterministic) and their dK / dV partials are summed
+// through shared memory once per 32-key block.  D_i = dO_i . O_i comes from a small pre-kernel.
+// ------------------------------------------------------------------------------------------------
+constexpr int FB_THREADS = 512;
+constexpr int FB_KB = 32;                 // keys per outer step: two 16-key m-tiles per warp
+constexpr int FB_QP = 36;                 // fp32 pitch of a dQ accumulator row (32 channels + 4)
+constexpr int FB_PITCH = 40;              // bf16 pitch of the Q / dO tiles (32 channels + 8)
+__host__ __device__ inline int fb_smem_bytes(int N) {
+  const int T = (N + BW_T - 1) / BW_T;
+  return T * BW_T * FB_QP * 4 + 3 * 2 * BW_T * FB_PITCH * 2 + 2 * 3 * 8 * BW_T * 4 + 8 * 2 * 32 * 8 * 4;
+}
+
+__device__ __forceinline__ uint32_t b_movm_trans(uint32_t a) {
+  uint32_t d;
+  asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(d) : "r"(a));
+  return d;
+}
+
+// D_i = dO_i . O_i per (token, head), head_dim 4: one thread per 8 channels = two heads
+__global__ void __launch_bounds__(256) attn_bwd_delta4_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ o, int64_t ldo,
+                                                              float* __restrict__ dsum, int64_t M, int C, int heads) {
+  const int cpt = C / 8;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < M * cpt; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t tok = i / cpt;
+    const int c8 = (int)(i - tok * cpt);
+    float a[8], b[8];
+    load8(dout + tok * ldo + c8 * 8, a);
+    load8(o + tok * ldo + c8 * 8, b);
+    dsum[tok * heads + 2 * c8] = a[0] * b[0] + a[1] * b[1] + a[2] * b[2] + a[3] * b[3];
+    dsum[tok * heads + 2 * c8 + 1] = a[4] * b[4] + a[5] * b[5] + a[6] * b[6] + a[7] * b[7];
+  }
+}
+
+__global__ void __launch_bounds__(FB_THREADS, 1) attn_bwd_fused4_kernel(const AttnParams p) {
+  constexpr int D = 4, CS = 32, CPT = 4;
+  extern __shared__ __align__(16) uint8_t fb_smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+  const int head_l = warp & 7, qh = warp >> 3;
+  const int row = blockIdx.x, slab = blockIdx.y;
+  const int N = p.geom == TFSWA_GEOM_TSA ? p.H : p.W;
+  const int T = (N + BW_T - 1) / BW_T, KSTEPS = (N + FB_KB - 1) / FB_KB;
+  int64_t tok_base, tok_stride;
+  if (p.geom == TFSWA_GEOM_TSA) { const int b = row / p.W; tok_base = (int64_t)b * p.H * p.W + (row - b * p.W); tok_stride = p.W; }
+  else { tok_base = (int64_t)row * p.W; tok_stride = 1; }
+  float* dq_s = reinterpret_cast<float*>(fb_smem);
+  typedef bf16 (*tile_t)[BW_T][FB_PITCH];
+  uint8_t* ptr = fb_smem + (size_t)T * BW_T * FB_QP * 4;
+  tile_t Qs = reinterpret_cast<tile_t>(ptr); ptr += 3 * BW_T * FB_PITCH * 2;
+  tile_t Gs = reinterpret_cast<tile_t>(ptr); ptr += 3 * BW_T * FB_PITCH * 2;
+  typedef float (*stat_t)[8][BW_T];
+  stat_t Ls = reinterpret_cast<stat_t>(ptr); ptr += 3 * 8 * BW_T * 4;
+  stat_t Ds = reinterpret_cast<stat_t>(ptr); ptr += 3 * 8 * BW_T * 4;
+  float* red = reinterpret_cast<float*>(ptr);                       // [head][m-tile][lane][dk 4 | dv 4]
+  const bf16* qkv = (const bf16*)p.qkv;
+  const bf16* dout = (const bf16*)p.dout;
+  const int cbase = head_l * D, head = slab * 8 + head_l;
+  const int first = cbase & 7;
+  const float c = p.qscale;
+
+  for (int i = tid; i < T * BW_T * FB_QP; i += FB_THREADS) dq_s[i] = 0.f;
+
+  const int total = KSTEPS * T;                                     // the query tiles are streamed once per key block
+  auto stage = [&](int gi, int b) {
+    if (gi < total) {
+      const int tt = gi % T;
+      {
+        const int j = tid >> 3, rem = tid & 7, part = rem >> 2, chunk = rem & 3;   // 64 rows x (Q | dO) x 4 chunks = 512 copies
+        const int qn = tt * BW_T + j;
+        bf16* dst = part ? &Gs[b][j][chunk * 8] : &Qs[b][j][chunk * 8];
+        if (qn < N) {
+          const int64_t tok = tok_base + (int64_t)qn * tok_stride;
+          b_cp_async16(dst, part ? dout + tok * p.ldo + slab * CS + chunk * 8 : qkv + tok * p.ldq + slab * CS + chunk * 8);
+        } else {
+          *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
+        }
+      }
+      {
+        const int j = tid >> 3, h = tid & 7;                           // lse / D of the tile's queries, 8 heads
+        const int qn = tt * BW_T + j;
+        float l = CUDART_INF_F, d = 0.f;                               // +inf -> p = 0 for absent queries
+        if (qn < N) {
+          const int64_t tok = tok_base + (int64_t)qn * tok_stride;
+          l = p.lse[tok * p.heads + slab * 8 + h];
+          d = p.dsum[tok * p.heads + slab * 8 + h];
+        }
+        Ls[b][h][j] = l; Ds[b][h][j] = d;
+      }
+    }
+    b_cp_commit();
+  };
+  stage(0, 0);
+  stage(1, 1);
+
+  bf16* dqkv = (bf16*)p.dqkv;
+  for (int ko = 0; ko < KSTEPS; ++ko) {
+    const int k0 = ko * FB_KB;
+    // ---- my keys: K, V as A operands (rows = keys), K once more as the B operand of dQ += dS K ----
+    uint32_t ka[2][1][4], va[2][1][4], kq[2][2];
+    float dk[2][4], dv[2][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      const int kn0 = k0 + mt * 16 + g, kn1 = kn0 + 8;
+      const bool ok0 = kn0 < N, ok1 = kn1 < N;
+      const int64_t tok0 = tok_base + (int64_t)(ok0 ? kn0 : 0) * tok_stride, tok1 = tok_base + (int64_t)(ok1 ? kn1 : 0) * tok_stride;
+      load_a_frag<D>(ka[mt], qkv + p.C + slab * CS + cbase, p.ldq, tok0, tok1, ok0, ok1, t);
+      load_a_frag<D>(va[mt], qkv + 2 * p.C + slab * CS + cbase, p.ldq, tok0, tok1, ok0, ok1, t);
+      if (t == 2) { va[mt][0][0] = B_ONES2; va[mt][0][1] = B_ONES2; }          // the -D_i slots of dO meet ones here
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {                                   // b_r = (keys 2t, 2t+1 of the r-th 8-key half; n = g = dim)
+        const int ke = k0 + mt * 16 + r * 8 + 2 * t;
+        uint32_t lo = 0u, hi = 0u;
+        if (g < D) {
+          if (ke < N) lo = *reinterpret_cast<const uint16_t*>(qkv + (tok_base + (int64_t)ke * tok_stride) * p.ldq + p.C + slab * CS + cbase + g);
+          if (ke + 1 < N) hi = *reinterpret_cast<const uint16_t*>(qkv + (tok_base + (int64_t)(ke + 1) * tok_stride) * p.ldq + p.C + slab * CS + cbase + g);
+        }
+        kq[mt][r] = lo | (hi << 16);
+      }
+      dk[mt][0] = dk[mt][1] = dk[mt][2] = dk[mt][3] = 0.f;
+      dv[mt][0] = dv[mt][1] = dv[mt][2] = dv[mt][3] = 0.f;
+    }
+
+    // rows of an m-tile that lie beyond the sequence (last key block only): their P must be zero - K = 0 gives s = 0, and
+    // exp2(-lse) of a very negative lse would reach dQ as inf * 0
+    const bool tail_block = k0 + FB_KB > N;
+    auto tile_body = [&](auto masked, int tt) {
+      constexpr bool MASK = decltype(masked)::value;
+      const int gi = ko * T + tt;
+      b_cp_wait<1>();
+      __syncthreads();
+      stage(gi + 2, (gi + 2) % 3);
+      const int b = gi % 3;
+      // my four query n-tiles of this tile: Q and dO as "n = query" operands; the two 16-query blocks as "k = query" operands
+      uint32_t qb[4], gb[4], qt[2][2], gt[2][2];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int nt = 4 * qh + j;
+        qb[j] = t < 2 ? *reinterpret_cast<const uint32_t*>(&Qs[b][nt * 8 + g][cbase + 2 * t]) : 0u;
+        gb[j] = t < 2 ? *reinterpret_cast<const uint32_t*>(&Gs[b][nt * 8 + g][cbase + 2 * t]) : 0u;
+        if (t == 2) gb[j] = b_split2(-Ds[b][head_l][nt * 8 + g]);
+      }
+#pragma unroll
+      for (int kl = 0; kl < 2; ++kl) {
+        const int kk = 2 * qh + kl;
+        b_ldsm_x2_trans(qt[kl][0], qt[kl][1], &Qs[b][kk * 16 + (lane & 15)][cbase & ~7]);
+        b_ldsm_x2_trans(gt[kl][0], gt[kl][1], &Gs[b][kk * 16 + (lane & 15)][cbase & ~7]);
+      }
+      float dqa[2][4];
+#pragma unroll
+      for (int kl = 0; kl < 2; ++kl) dqa[kl][0] = dqa[kl][1] = dqa[kl][2] = dqa[kl][3] = 0.f;
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+#pragma unroll
+        for (int kl = 0; kl < 2; ++kl) {
+          uint32_t pa[4], da[4];
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            const int j = 2 * kl + half, nt = 4 * qh + j;
+            float s[4], dp[4];
+            b_mma1688_z(s, ka[mt][0][0], ka[mt][0][1], qb[j]);            // S^T: rows = my keys, columns = queries
+            b_mma1688_z(dp, va[mt][0][0], va[mt][0][1], gb[j]);           // dP^T - D
+            const float2 l2 = *reinterpret_cast<const float2*>(&Ls[b][head_l][nt * 8 + 2 * t]);
+            float pw[4], ds[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              pw[i] = fast_exp2(fmaf(s[i], c, -((i & 1) ? l2.y : l2.x)));
+              if (MASK && k0 + mt * 16 + g + (i >> 1) * 8 >= N) pw[i] = 0.f;
+              ds[i] = pw[i] * dp[i];
+            }
+            pa[half * 2 + 0] = b_pack(pw[0], pw[1]); pa[half * 2 + 1] = b_pack(pw[2], pw[3]);
+            da[half * 2 + 0] = b_pack(ds[0], ds[1]); da[half * 2 + 1] = b_pack(ds[2], ds[3]);
+          }
+          b_mma16816(dv[mt], pa, gt[kl][0], gt[kl][1]);
+          b_mma16816(dk[mt], da, qt[kl][0], qt[kl][1]);
+          // dS (rows = queries) = the four 8x8 blocks of dS^T transposed: (q 0-7 | k 0-7), (q 8-15 | k 0-7), (q 0-7 | k 8-15), (q 8-15 | k 8-15)
+          uint32_t ta[4];
+          ta[0] = b_movm_trans(da[0]); ta[1] = b_movm_trans(da[2]); ta[2] = b_movm_trans(da[1]); ta[3] = b_movm_trans(da[3]);
+          b_mma16816(dqa[kl], ta, kq[mt][0], kq[mt][1]);
+        }
+      }
+      if (t < 2) {                                                    // my head's 4 dims are columns 0..3 of the 8-wide tile
+#pragma unroll
+        for (int kl = 0; kl < 2; ++kl) {
+          const int q0 = tt * BW_T + (2 * qh + kl) * 16 + g;
+          float2* r0 = reinterpret_cast<float2*>(&dq_s[(size_t)q0 * FB_QP + cbase + 2 * t]);
+          float2* r1 = reinterpret_cast<float2*>(&dq_s[(size_t)(q0 + 8) * FB_QP + cbase + 2 * t]);
+          float2 v0 = *r0, v1 = *r1;
+          v0.x += dqa[kl][0]; v0.y += dqa[kl][1]; v1.x += dqa[kl][2]; v1.y += dqa[kl][3];
+          *r0 = v0; *r1 = v1;
+        }
+      }
+    };
+    if (tail_block) { for (int tt = 0; tt < T; ++tt) tile_body(std::true_type{}, tt); }
+    else { for (int tt = 0; tt < T; ++tt) tile_body(std::false_type{}, tt); }
+    // ---- dK, dV of this key block: sum the two query halves, write ----
+    float* myred = red + ((size_t)(head_l * 2) * 32 + lane) * 8;
+    if (qh == 1) {
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        float* r = myred + (size_t)mt * 32 * 8;
+        *reinterpret_cast<float4*>(r) = make_float4(dk[mt][0], dk[mt][1], dk[mt][2], dk[mt][3]);
+        *reinterpret_cast<float4*>(r + 4) = make_float4(dv[mt][0], dv[mt][1], dv[mt][2], dv[mt][3]);
+      }
+    }
+    __syncthreads();
+    if (qh == 0 && 2 * t >= first && 2 * t < first + 4) {
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        const float* r = myred + (size_t)mt * 32 * 8;
+        const float4 a = *reinterpret_cast<const float4*>(r), bq = *reinterpret_cast<const float4*>(r + 4);
+        const float k4[4] = {dk[mt][0] + a.x, dk[mt][1] + a.y, dk[mt][2] + a.z, dk[mt][3] + a.w};
+        const float v4[4] = {dv[mt][0] + bq.x, dv[mt][1] + bq.y, dv[mt][2] + bq.z, dv[mt][3] + bq.w};
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+          const int kn = k0 + mt * 16 + g + h2 * 8;
+          if (kn >= N) continue;
+          bf16* base = dqkv + (tok_base + (int64_t)kn * tok_stride) * p.ldq + slab * CS + (cbase & ~7) + 2 * t;
+          *reinterpret_cast<uint32_t*>(base + p.C) = b_pack(k4[h2 * 2] * p.scale, k4[h2 * 2 + 1] * p.scale);
+          *reinterpret_cast<uint32_t*>(base + 2 * p.C) = b_pack(v4[h2 * 2], v4[h2 * 2 + 1]);
+        }
+      }
+    }
+  }
+  b_cp_wait<0>();
+  __syncthreads();
+  // ---- dq = scale * accumulator ----
+  for (int i = tid; i < N * CPT; i += FB_THREADS) {
+    const int q = i >> 2, chunk = i & 3;
+    const float4 a = *reinterpret_cast<const float4*>(&dq_s[(size_t)q * FB_QP + chunk * 8]);
+    const float4 bq = *reinterpret_cast<const float4*>(&dq_s[(size_t)q * FB_QP + chunk * 8 + 4]);
+    uint4 o;
+    o.x = b_pack(a.x * p.scale, a.y * p.scale); o.y = b_pack(a.z * p.scale, a.w * p.scale);
+    o.z = b_pack(bq.x * p.scale, bq.y * p.scale); o.w = b_pack(bq.z * p.scale, bq.w * p.scale);
+    *reinterpret_cast<uint4*>(dqkv + (tok_base + (int64_t)q * tok_stride) * p.ldq + slab * CS + chunk * 8) = o;
+  }
+}
+
+static int launch_bwd_fused4(const AttnParams& p, cudaStream_t st) {
+  const int N = p.geom == TFSWA_GEOM_TSA ? p.H : p.W;
+  const int rows = p.geom == TFSWA_GEOM_TSA ? p.B * p.W : p.B * p.H;
+  const int smem = fb_smem_bytes(N);
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(attn_bwd_fused4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+      set_error("attn_bwd_fused: cudaFuncSetAttribute failed");
+      return TFSWA_ECUDA;
+    }
+    attr_set = true;
+  }
+  const int64_t M = (int64_t)p.B * p.H * p.W;
+  const int64_t work = M * (p.C / 8);
+  const unsigned dgrid = (unsigned)((work + 255) / 256 < 148 * 16 ? (work + 255) / 256 : 148 * 16);
+  attn_bwd_delta4_kernel<<<dgrid, 256, 0, st>>>((const bf16*)p.dout, (const bf16*)p.o, p.ldo, p.dsum, M, p.C, p.heads);
+  attn_bwd_fused4_kernel<<<dim3(rows, p.heads / 8), FB_THREADS, smem, st>>>(p);
+  return check_launch("attn_bwd_fused");
+}
+
 template <int D, bool WIN>
 static int launch_bwd_mma(const AttnParams& p, cudaStream_t st) {
   static bool attr_set = false;
@@ -518,6 +782,12 @@ int attn_bwd_mma_bf16(const AttnParams& p, cudaStream_t st) {
   if (p.heads % 8 != 0 || (D != 4 && D != 8 && D != 16)) return 1;
   if (win ? (p.ws != 8) : (rows > 65535)) return 1;
   if ((p.ldq % 8) || (p.ldo % 8) || (((uintptr_t)p.qkv | (uintptr_t)p.dqkv | (uintptr_t)p.dout) & 15) || (((uintptr_t)p.o) & 3)) return 1;
+  // head_dim 4, axial: one-pass kernel (P computed once) when the sequence's fp32 dQ accumulator fits in shared memory
+  const char* fe = getenv("TFSWA_ATTN_BWD_FUSED");               // "0": keep the dq + dkv pair (A/B, tests)
+  const bool fused = !(fe && fe[0] == '0');
+  if (!win && D == 4 && fused && p.C % 32 == 0 && (((uintptr_t)p.o) & 15) == 0 &&
+      fb_smem_bytes(p.geom == TFSWA_GEOM_TSA ? p.H : p.W) <= 227 * 1024)
+    return launch_bwd_fused4(p, st);
   if (win) {
     if (D == 4) return launch_bwd_mma<4, true>(p, st);
     if (D == 8) return launch_bwd_mma<8, true>(p, st);
