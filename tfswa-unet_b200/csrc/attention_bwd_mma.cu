@@ -56,6 +56,9 @@ constexpr uint32_t B_ONES2 = 0x3F803F80u;        // bf16 (1, 1)
 __device__ __forceinline__ void b_cp_async16(void* smem_dst, const void* gsrc) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
 }
+__device__ __forceinline__ void b_cp_async4(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
 __device__ __forceinline__ void b_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void b_cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
@@ -342,13 +345,13 @@ __global__ void __launch_bounds__(BW_THREADS, WIN ? bw_win_ctas<D>() : 2) attn_b
       }
       for (int v = tid; v < BW_T * 8; v += BW_THREADS) {                 // lse / D of the tile's queries, all 8 heads
         const int j = v >> 3, h = v & 7;
-        float l = CUDART_INF_F, d = 0.f;                                 // +inf -> p = 0 for absent queries
         int64_t tok; bool real;
         if (seq_token<WIN>(s_wtok, tt * BW_T + j, N, tok_base, tok_stride, tok, real) && real) {
-          l = p.lse[tok * p.heads + slab * 8 + h];
-          d = p.dsum[tok * p.heads + slab * 8 + h];
+          b_cp_async4(&Ls[b][h][j], p.lse + tok * p.heads + slab * 8 + h);      // asynchronous: no load-to-store stall per tile
+          b_cp_async4(&Ds[b][h][j], p.dsum + tok * p.heads + slab * 8 + h);
+        } else {
+          Ls[b][h][j] = CUDART_INF_F; Ds[b][h][j] = 0.f;                 // +inf -> p = 0 for absent queries
         }
-        Ls[b][h][j] = l; Ds[b][h][j] = d;
       }
     }
     b_cp_commit();
@@ -556,39 +559,50 @@ __global__ void __launch_bounds__(FB_THREADS, 1) attn_bwd_fused4_kernel(const At
 
   for (int i = tid; i < T * BW_T * FB_QP; i += FB_THREADS) dq_s[i] = 0.f;
 
+  // Staging state kept incrementally (one add per tile instead of 64-bit multiplies, a modulo by T and a modulo by 3 per
+  // tile: the index arithmetic was ~45 % of this kernel's instructions in its first version).  Thread -> (row j, part, chunk)
+  // of the Q | dO copy and (row j, head h) of the lse | D copy are fixed; per tile only the query index advances.
   const int total = KSTEPS * T;                                     // the query tiles are streamed once per key block
-  auto stage = [&](int gi, int b) {
-    if (gi < total) {
-      const int tt = gi % T;
-      {
-        const int j = tid >> 3, rem = tid & 7, part = rem >> 2, chunk = rem & 3;   // 64 rows x (Q | dO) x 4 chunks = 512 copies
-        const int qn = tt * BW_T + j;
-        bf16* dst = part ? &Gs[b][j][chunk * 8] : &Qs[b][j][chunk * 8];
-        if (qn < N) {
-          const int64_t tok = tok_base + (int64_t)qn * tok_stride;
-          b_cp_async16(dst, part ? dout + tok * p.ldo + slab * CS + chunk * 8 : qkv + tok * p.ldq + slab * CS + chunk * 8);
-        } else {
-          *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
-        }
+  const int sj = tid >> 3, srem = tid & 7, spart = srem >> 2, schunk = srem & 3;
+  const bf16* s_src0 = (spart ? dout + tok_base * p.ldo : qkv + tok_base * p.ldq) + slab * CS + schunk * 8
+                       + (int64_t)sj * tok_stride * (spart ? p.ldo : p.ldq);
+  const int64_t s_src_step = (int64_t)BW_T * tok_stride * (spart ? p.ldo : p.ldq);          // elements per 64-query tile
+  const float* s_lse0 = p.lse + (tok_base + (int64_t)sj * tok_stride) * p.heads + slab * 8 + srem;
+  const float* s_dsm0 = p.dsum + (tok_base + (int64_t)sj * tok_stride) * p.heads + slab * 8 + srem;
+  const int64_t s_stat_step = (int64_t)BW_T * tok_stride * p.heads;
+  const uint32_t s_dst0 = (uint32_t)__cvta_generic_to_shared(spart ? &Gs[0][sj][schunk * 8] : &Qs[0][sj][schunk * 8]);
+  int s_gi = 0, s_tt = 0, s_slot = 0;                                // next tile to stage, its query tile and ring slot
+  const bf16* s_src = s_src0; const float* s_lse = s_lse0; const float* s_dsm = s_dsm0;
+  // Two halves: `stage_issue` starts the Q | dO copy (cp.async) and the lse | D loads into two registers, `stage_finish`
+  // parks those registers in shared memory.  The consumer calls them before and after a tile's math, so the loads' latency
+  // hides under the MMAs instead of stalling every warp right after the barrier (4-byte cp.async for them was slower: the
+  // shared-memory instruction queue is the busiest unit of this kernel).
+  float s_l = CUDART_INF_F, s_d = 0.f;
+  float* s_lsp = &Ls[0][srem][sj]; float* s_dsp = &Ds[0][srem][sj];
+  auto stage_issue = [&]() {
+    s_l = CUDART_INF_F; s_d = 0.f;                                   // +inf -> p = 0 for absent queries
+    s_lsp = &Ls[s_slot][srem][sj]; s_dsp = &Ds[s_slot][srem][sj];
+    if (s_gi < total) {
+      const uint32_t dst = s_dst0 + (uint32_t)s_slot * (BW_T * FB_PITCH * 2);
+      if (s_tt * BW_T + sj < N) {
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(s_src) : "memory");
+        s_l = *s_lse; s_d = *s_dsm;
+      } else {
+        asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(dst), "r"(0u) : "memory");
       }
-      {
-        const int j = tid >> 3, h = tid & 7;                           // lse / D of the tile's queries, 8 heads
-        const int qn = tt * BW_T + j;
-        float l = CUDART_INF_F, d = 0.f;                               // +inf -> p = 0 for absent queries
-        if (qn < N) {
-          const int64_t tok = tok_base + (int64_t)qn * tok_stride;
-          l = p.lse[tok * p.heads + slab * 8 + h];
-          d = p.dsum[tok * p.heads + slab * 8 + h];
-        }
-        Ls[b][h][j] = l; Ds[b][h][j] = d;
-      }
+      ++s_gi; s_slot = s_slot == 2 ? 0 : s_slot + 1;
+      if (++s_tt == T) { s_tt = 0; s_src = s_src0; s_lse = s_lse0; s_dsm = s_dsm0; }
+      else { s_src += s_src_step; s_lse += s_stat_step; s_dsm += s_stat_step; }
     }
     b_cp_commit();
   };
-  stage(0, 0);
-  stage(1, 1);
+  auto stage_finish = [&]() { *s_lsp = s_l; *s_dsp = s_d; };
+  stage_issue(); stage_finish();
+  stage_issue(); stage_finish();
+  int cslot = 0;                                                      // ring slot of the tile being consumed
 
   bf16* dqkv = (bf16*)p.dqkv;
+  float* const dq_mine = dq_s + (2 * qh * 16 + g) * FB_QP + cbase + 2 * t;   // my first accumulator row of a tile, my columns
   for (int ko = 0; ko < KSTEPS; ++ko) {
     const int k0 = ko * FB_KB;
     // ---- my keys: K, V as A operands (rows = keys), K once more as the B operand of dQ += dS K ----
@@ -621,11 +635,11 @@ __global__ void __launch_bounds__(FB_THREADS, 1) attn_bwd_fused4_kernel(const At
     const bool tail_block = k0 + FB_KB > N;
     auto tile_body = [&](auto masked, int tt) {
       constexpr bool MASK = decltype(masked)::value;
-      const int gi = ko * T + tt;
       b_cp_wait<1>();
       __syncthreads();
-      stage(gi + 2, (gi + 2) % 3);
-      const int b = gi % 3;
+      stage_issue();
+      const int b = cslot;
+      cslot = cslot == 2 ? 0 : cslot + 1;
       // my four query n-tiles of this tile: Q and dO as "n = query" operands; the two 16-query blocks as "k = query" operands
       uint32_t qb[4], gb[4], qt[2][2], gt[2][2];
 #pragma unroll
@@ -677,14 +691,14 @@ __global__ void __launch_bounds__(FB_THREADS, 1) attn_bwd_fused4_kernel(const At
       if (t < 2) {                                                    // my head's 4 dims are columns 0..3 of the 8-wide tile
 #pragma unroll
         for (int kl = 0; kl < 2; ++kl) {
-          const int q0 = tt * BW_T + (2 * qh + kl) * 16 + g;
-          float2* r0 = reinterpret_cast<float2*>(&dq_s[(size_t)q0 * FB_QP + cbase + 2 * t]);
-          float2* r1 = reinterpret_cast<float2*>(&dq_s[(size_t)(q0 + 8) * FB_QP + cbase + 2 * t]);
+          float2* r0 = reinterpret_cast<float2*>(dq_mine + (tt * BW_T + kl * 16) * FB_QP);
+          float2* r1 = r0 + 8 * FB_QP / 2;
           float2 v0 = *r0, v1 = *r1;
           v0.x += dqa[kl][0]; v0.y += dqa[kl][1]; v1.x += dqa[kl][2]; v1.y += dqa[kl][3];
           *r0 = v0; *r1 = v1;
         }
       }
+      stage_finish();
     };
     if (tail_block) { for (int tt = 0; tt < T; ++tt) tile_body(std::true_type{}, tt); }
     else { for (int tt = 0; tt < T; ++tt) tile_body(std::false_type{}, tt); }
