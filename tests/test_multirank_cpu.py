@@ -208,3 +208,13 @@ def test_flat_arena_inplace_allreduce_world2():
     assert all(p.exitcode == 0 for p in procs)
     for rank, err in res:
         assert err < 1e-6, f"rank {rank}: arena-averaged gradients differ from the single-process reference by {err}"
+
+
+def test_flat_arena_detects_parameters_that_left_it():
+    from tfswa_unet_b200.train_step import FlatArena
+    model = _tiny_model()
+    arena = FlatArena(model)
+    arena.check()
+    model.double()                                   # re-allocates every parameter outside the arena
+    with pytest.raises(RuntimeError, match="no longer lives in the arena"):
+        arena.check()

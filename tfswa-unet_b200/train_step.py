@@ -82,6 +82,15 @@ class FlatArena:
         for p, o in zip(self.params, self.offsets):
             p.grad = self.flat_g[o:o + p.numel()].view(p.shape)
 
+    def check(self) -> None:
+        """The arena is only as good as the views: ``model.to(...)``, ``.half()`` or assigning ``p.data`` re-allocates the
+        parameters outside it, after which the fused optimiser would update memory the model no longer reads."""
+        for i in (0, len(self.params) // 2, len(self.params) - 1):
+            p, o = self.params[i], self.offsets[i]
+            if p.data_ptr() != self.flat_p[o:].data_ptr() or p.dtype != torch.float32:
+                raise RuntimeError("FlatArena: a parameter no longer lives in the arena (model.to()/.half() after TrainStep "
+                                   "was built?) - rebuild the TrainStep / FlatArena after moving the model")
+
     def zero_grad(self) -> None:
         """One memset.  (``optimizer.zero_grad(set_to_none=True)`` would detach the views: ``adopt_grads`` repairs that.)"""
         self.flat_g.zero_()
@@ -162,6 +171,7 @@ class FusedClipAdamW:
         the total gradient norm before clipping (what ``clip_grad_norm_`` returns); nothing synchronises with the host."""
         from . import ops
         a = self.arena
+        a.check()
         scale = a.finish()
         self.step_count += 1
         st = torch.cuda.current_stream().cuda_stream
