@@ -230,11 +230,12 @@ __global__ void __launch_bounds__(256) attn_kext_kernel(const AttnParams p) {
 // softmax warps); warp 8 ("issuer") does nothing but wait on mbarriers and issue tcgen05.mma.  There is no CTA-wide
 // barrier in the key loop:
 //   bar_s   (1)  S(t) complete in TMEM                          issuer commit  -> softmax
-//   bar_a   (8)  S(t-1) pulled into registers (8 softmax warps)     softmax  -> issuer (may overwrite S with S(t))
-//   bar_k[2](1)  operands(t) staged in Ks[t&1] / Vs[t%3]            producer -> issuer; one barrier per parity of t because
-//                the producer runs up to two tiles ahead.  (The two sources shared one 9-arrival barrier at first: a
-//                producer that was a tile ahead then stood in for a softmax warp that had not pulled its rows of S(t-1)
-//                yet, S(t) overwrote them, and about one launch in ten returned 32 wrong rows in one CTA.)
+//   bar_a   (9)  S(t-1) pulled into registers (8 softmax warps) + operands(t) staged (producer) -> issuer (may issue S(t)).
+//                Every source arrives exactly ONCE per phase: a softmax warp's arrival for S(t-1) needs S(t-1), i.e. phase
+//                t-1 over, and the producer - which stages up to two tiles ahead - holds its arrival for tile t until
+//                bar_s says S(t-1) has completed.  (Without that hold a producer that was a tile ahead stood in for a softmax
+//                warp that had not pulled its rows of S(t-1) yet, S(t) overwrote them, and about one full-size launch in ten
+//                returned 32 wrong rows in one CTA.  Two separate barriers fix it too, at +1.8 %; the hold is free.)
 //   bar_free(1)  S(t) and PV(t-1) complete: Ks[t&1], Vs[(t-1)%3] may be overwritten    softmax warp 0 -> producer
 //   bar_b   (8)  P(t) written to TMEM                                 softmax  -> issuer (may issue PV(t))
 //   bar_pv  (1)  PV(t) complete: P columns and V' buffer t%3 free     issuer commit -> softmax
@@ -251,7 +252,7 @@ __global__ void __launch_bounds__(TA_NTHREADS, 2) tc_attn_axial_kernel(const Att
   constexpr int TA_PS = ps_off<D>();
   constexpr int VSB = vs_bytes<D>();
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ __align__(8) uint64_t bar_s, bar_a, bar_k[2], bar_b, bar_pv, bar_free, bar_sx[2], bar_ax[2];
+  __shared__ __align__(8) uint64_t bar_s, bar_a, bar_b, bar_pv, bar_free, bar_sx[2], bar_ax[2];
   __shared__ uint32_t s_tmem;
   __shared__ float s_kext[2][16];        // per channel of the quad: min / max of k over the whole sequence
 
@@ -274,8 +275,7 @@ __global__ void __launch_bounds__(TA_NTHREADS, 2) tc_attn_axial_kernel(const Att
   for (int i = tid; i < (TA_PS - TA_KS) / 16; i += TA_NTHREADS) reinterpret_cast<uint4*>(smem + TA_KS)[i] = make_uint4(0, 0, 0, 0);
   if (warp == 0) {
     if (lane == 0) {
-      mbar_init(&bar_s, 1); mbar_init(&bar_a, 8); mbar_init(&bar_b, 8); mbar_init(&bar_pv, 1); mbar_init(&bar_free, 1);
-      mbar_init(&bar_k[0], 1); mbar_init(&bar_k[1], 1);
+      mbar_init(&bar_s, 1); mbar_init(&bar_a, 9); mbar_init(&bar_b, 8); mbar_init(&bar_pv, 1); mbar_init(&bar_free, 1);
 #pragma unroll
       for (int i = 0; i < 2; ++i) { mbar_init(&bar_sx[i], 1); mbar_init(&bar_ax[i], 8); }
       fence_barrier_init();
@@ -321,7 +321,7 @@ __global__ void __launch_bounds__(TA_NTHREADS, 2) tc_attn_axial_kernel(const Att
   const uint32_t tmem = s_tmem;
   const uint32_t my_taddr = tmem + ((uint32_t)(quarter * 32) << 16);
   // barrier completions consumed so far by this thread (wait parity = count & 1)
-  uint32_t n_s = 0, n_a = 0, n_k0 = 0, n_k1 = 0, n_b = 0, n_pv = 0, n_free = 0, n_sx[2] = {0u, 0u}, n_ax[2] = {0u, 0u};
+  uint32_t n_s = 0, n_a = 0, n_b = 0, n_pv = 0, n_free = 0, n_sx[2] = {0u, 0u}, n_ax[2] = {0u, 0u};
 
   // row-max upper bound per head: s_ij = sum_d q_d k_jd <= sum_d max(q_d kmax_d, q_d kmin_d)   (raw score units)
   float m[HPT];
@@ -418,10 +418,7 @@ __global__ void __launch_bounds__(TA_NTHREADS, 2) tc_attn_axial_kernel(const Att
     if (issuer) {
       const uint32_t idesc_pv = umma_idesc_bf16(128, NV);
       for (int t = 0; t <= T; ++t) {
-        mbar_wait(&bar_a, n_a & 1); ++n_a;                            // S(t-1) consumed by all eight softmax warps
-        if (t < T) {                                                  // operands(t) staged
-          if (t & 1) { mbar_wait(&bar_k[1], n_k1 & 1); ++n_k1; } else { mbar_wait(&bar_k[0], n_k0 & 1); ++n_k0; }
-        }
+        mbar_wait(&bar_a, n_a & 1); ++n_a;                            // S(t-1) consumed, operands(t) staged
         if (t < T && lane == 0) {
           tc_fence_after();
           umma_bf16_ss(tmem, qdesc, umma_smem_desc_ns(sbase + TA_KS + (t & 1) * 8192, 128, 256), idesc_s, 0u);
@@ -447,13 +444,17 @@ __global__ void __launch_bounds__(TA_NTHREADS, 2) tc_attn_axial_kernel(const Att
         __syncwarp();
       }
     } else if (producer) {
-      // operands(k) for k = 0..T-1 (k >= 2 waits until tile k-2 released its buffers), one arrival on bar_k[k & 1] each
-      for (int k = 0; k < T; ++k) {
-        if (k >= 2) { mbar_wait(&bar_free, n_free & 1); ++n_free; }
-        stage_tile<D, KT>(p, tok_base, tok_stride, k * KT, N, quad, smem + TA_KS + (k & 1) * 8192, smem + TA_VS + (k % 3) * VSB, lane);
-        fence_async_smem();
+      // operands(k) for k = 0..T-1 (k >= 2 waits until tile k-2 released its buffers); one arrival per bar_a phase, held until
+      // S(k-1) has completed so that it can never land in phase k-1 (see the barrier table above)
+      for (int k = 0; k <= T; ++k) {
+        if (k < T) {
+          if (k >= 2) { mbar_wait(&bar_free, n_free & 1); ++n_free; }
+          stage_tile<D, KT>(p, tok_base, tok_stride, k * KT, N, quad, smem + TA_KS + (k & 1) * 8192, smem + TA_VS + (k % 3) * VSB, lane);
+          fence_async_smem();
+        }
+        if (k >= 1) { mbar_wait(&bar_s, n_s & 1); ++n_s; }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&bar_k[k & 1]);
+        if (lane == 0) mbar_arrive(&bar_a);
       }
     } else {
       __syncwarp();
