@@ -1,4 +1,4 @@
-"""GPU (-m gpu): the one-pass head_dim-4 attention backward (attn_bwd_fused4_kernel: P computed once, dQ accumulated in
+"""GPU (-m gpu): the one-pass head_dim-4 / 8 attention backward (attn_bwd_fused_kernel<D>: P computed once, dQ accumulated in
 shared memory) against the two-kernel warp-MMA path (TFSWA_ATTN_BWD_FUSED=0), the CUDA-core path (TFSWA_ATTN_BWD_SIMT=1)
 and torch autograd of the same op in fp32."""
 import os
@@ -30,6 +30,10 @@ def _torch_ref(qkv, dout, B, H, W, C, heads, geom):
     (1, 64, 4, 32, 8, 0), (1, 4, 96, 32, 8, 1),            # exact multiples of the tile sizes
     (1, 1025, 2, 32, 8, 0), (1, 2, 517, 32, 8, 1),         # the C3 stage-1 sequence lengths
     (1, 70, 3, 64, 16, 0),                                 # two 8-head slabs
+    (1, 37, 5, 64, 8, 0), (1, 5, 37, 64, 8, 1),            # head_dim 8: ragged tile / key block
+    (2, 129, 3, 64, 8, 0), (1, 3, 300, 64, 8, 1),
+    (1, 512, 2, 64, 8, 0), (1, 2, 258, 64, 8, 1),          # the C3 stage-2 sequence lengths
+    (1, 70, 3, 128, 16, 1),                                # head_dim 8, two slabs
 ])
 def test_fused_attention_backward_matches_other_paths(B, H, W, C, heads, geom):
     from tfswa_unet_b200 import ops

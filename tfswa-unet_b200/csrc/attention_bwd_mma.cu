@@ -492,7 +492,7 @@ __global__ void __launch_bounds__(BW_THREADS, WIN ? bw_win_ctas<D>() : 2) attn_b
 }
 
 // ------------------------------------------------------------------------------------------------
-// One-pass backward for head_dim 4 (TSA / FSA): the dq / dkv pair above computes every P_ij twice, and at head_dim 4 the
+// One-pass backward for head_dim 4 and 8 (TSA / FSA): the dq / dkv pair above computes every P_ij twice, and at head_dim 4 the
 // exponentials and the instructions around them are the whole cost.  Here each (key block, query tile) pair is visited
 // once: S^T, dP^T, P^T and dS^T are formed in the dkv orientation (rows = keys), dV += P^T dO and dK += dS^T Q accumulate in
 // registers over the query loop, and dQ += dS K uses the SAME dS^T fragments, transposed in registers with movmatrix, into
@@ -503,11 +503,11 @@ __global__ void __launch_bounds__(BW_THREADS, WIN ? bw_win_ctas<D>() : 2) attn_b
 // ------------------------------------------------------------------------------------------------
 constexpr int FB_THREADS = 512;
 constexpr int FB_KB = 32;                 // keys per outer step: two 16-key m-tiles per warp
-constexpr int FB_QP = 36;                 // fp32 pitch of a dQ accumulator row (32 channels + 4)
-constexpr int FB_PITCH = 40;              // bf16 pitch of the Q / dO tiles (32 channels + 8)
-__host__ __device__ inline int fb_smem_bytes(int N) {
+template <int D> __host__ __device__ constexpr int fb_qp() { return 8 * D + 4; }      // fp32 pitch of a dQ accumulator row
+template <int D> __host__ __device__ constexpr int fb_pitch() { return 8 * D + 8; }   // bf16 pitch of the Q / dO tiles
+template <int D> __host__ __device__ inline int fb_smem_bytes(int N) {
   const int T = (N + BW_T - 1) / BW_T;
-  return T * BW_T * FB_QP * 4 + 3 * 2 * BW_T * FB_PITCH * 2 + 2 * 3 * 8 * BW_T * 4 + 8 * 2 * 32 * 8 * 4;
+  return T * BW_T * fb_qp<D>() * 4 + 3 * 2 * BW_T * fb_pitch<D>() * 2 + 2 * 3 * 8 * BW_T * 4 + 8 * 2 * 32 * 8 * 4;
 }
 
 __device__ __forceinline__ uint32_t b_movm_trans(uint32_t a) {
@@ -516,8 +516,9 @@ __device__ __forceinline__ uint32_t b_movm_trans(uint32_t a) {
   return d;
 }
 
-// D_i = dO_i . O_i per (token, head), head_dim 4: one thread per 8 channels = two heads
-__global__ void __launch_bounds__(256) attn_bwd_delta4_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ o, int64_t ldo,
+// D_i = dO_i . O_i per (token, head), head_dim 4 or 8: one thread per 8 channels = two heads or one
+template <int D>
+__global__ void __launch_bounds__(256) attn_bwd_delta_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ o, int64_t ldo,
                                                               float* __restrict__ dsum, int64_t M, int C, int heads) {
   const int cpt = C / 8;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < M * cpt; i += (int64_t)gridDim.x * blockDim.x) {
@@ -526,13 +527,17 @@ __global__ void __launch_bounds__(256) attn_bwd_delta4_kernel(const bf16* __rest
     float a[8], b[8];
     load8(dout + tok * ldo + c8 * 8, a);
     load8(o + tok * ldo + c8 * 8, b);
-    dsum[tok * heads + 2 * c8] = a[0] * b[0] + a[1] * b[1] + a[2] * b[2] + a[3] * b[3];
-    dsum[tok * heads + 2 * c8 + 1] = a[4] * b[4] + a[5] * b[5] + a[6] * b[6] + a[7] * b[7];
+    const float lo = a[0] * b[0] + a[1] * b[1] + a[2] * b[2] + a[3] * b[3];
+    const float hi = a[4] * b[4] + a[5] * b[5] + a[6] * b[6] + a[7] * b[7];
+    if (D == 4) { dsum[tok * heads + 2 * c8] = lo; dsum[tok * heads + 2 * c8 + 1] = hi; }
+    else dsum[tok * heads + c8] = lo + hi;
   }
 }
 
-__global__ void __launch_bounds__(FB_THREADS, 1) attn_bwd_fused4_kernel(const AttnParams p) {
-  constexpr int D = 4, CS = 32, CPT = 4;
+template <int D>
+__global__ void __launch_bounds__(FB_THREADS, 1) attn_bwd_fused_kernel(const AttnParams p) {
+  constexpr int CS = 8 * D, CPT = D, FB_QP = fb_qp<D>(), FB_PITCH = fb_pitch<D>();
+  constexpr int SROWS = FB_THREADS / (2 * CPT), SPASS = BW_T / SROWS;      // rows covered by one staging pass / passes per tile
   extern __shared__ __align__(16) uint8_t fb_smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
   const int head_l = warp & 7, qh = warp >> 3;
@@ -563,12 +568,15 @@ __global__ void __launch_bounds__(FB_THREADS, 1) attn_bwd_fused4_kernel(const At
   // tile: the index arithmetic was ~45 % of this kernel's instructions in its first version).  Thread -> (row j, part, chunk)
   // of the Q | dO copy and (row j, head h) of the lse | D copy are fixed; per tile only the query index advances.
   const int total = KSTEPS * T;                                     // the query tiles are streamed once per key block
-  const int sj = tid >> 3, srem = tid & 7, spart = srem >> 2, schunk = srem & 3;
+  const int sj = tid / (2 * CPT), srem = tid % (2 * CPT), spart = srem / CPT, schunk = srem % CPT;   // Q | dO copy: row sj (+ SROWS per pass)
+  const int lj = tid >> 3, lh = tid & 7;                                                                 // lse | D copy: row lj, head lh
+  const int64_t s_ld = spart ? p.ldo : p.ldq;
   const bf16* s_src0 = (spart ? dout + tok_base * p.ldo : qkv + tok_base * p.ldq) + slab * CS + schunk * 8
-                       + (int64_t)sj * tok_stride * (spart ? p.ldo : p.ldq);
-  const int64_t s_src_step = (int64_t)BW_T * tok_stride * (spart ? p.ldo : p.ldq);          // elements per 64-query tile
-  const float* s_lse0 = p.lse + (tok_base + (int64_t)sj * tok_stride) * p.heads + slab * 8 + srem;
-  const float* s_dsm0 = p.dsum + (tok_base + (int64_t)sj * tok_stride) * p.heads + slab * 8 + srem;
+                       + (int64_t)sj * tok_stride * s_ld;
+  const int64_t s_src_step = (int64_t)BW_T * tok_stride * s_ld;                                 // elements per 64-query tile
+  const int64_t s_pass_step = (int64_t)SROWS * tok_stride * s_ld;                               // elements per staging pass
+  const float* s_lse0 = p.lse + (tok_base + (int64_t)lj * tok_stride) * p.heads + slab * 8 + lh;
+  const float* s_dsm0 = p.dsum + (tok_base + (int64_t)lj * tok_stride) * p.heads + slab * 8 + lh;
   const int64_t s_stat_step = (int64_t)BW_T * tok_stride * p.heads;
   const uint32_t s_dst0 = (uint32_t)__cvta_generic_to_shared(spart ? &Gs[0][sj][schunk * 8] : &Qs[0][sj][schunk * 8]);
   int s_gi = 0, s_tt = 0, s_slot = 0;                                // next tile to stage, its query tile and ring slot
@@ -578,18 +586,20 @@ __global__ void __launch_bounds__(FB_THREADS, 1) attn_bwd_fused4_kernel(const At
   // hides under the MMAs instead of stalling every warp right after the barrier (4-byte cp.async for them was slower: the
   // shared-memory instruction queue is the busiest unit of this kernel).
   float s_l = CUDART_INF_F, s_d = 0.f;
-  float* s_lsp = &Ls[0][srem][sj]; float* s_dsp = &Ds[0][srem][sj];
+  float* s_lsp = &Ls[0][lh][lj]; float* s_dsp = &Ds[0][lh][lj];
   auto stage_issue = [&]() {
     s_l = CUDART_INF_F; s_d = 0.f;                                   // +inf -> p = 0 for absent queries
-    s_lsp = &Ls[s_slot][srem][sj]; s_dsp = &Ds[s_slot][srem][sj];
+    s_lsp = &Ls[s_slot][lh][lj]; s_dsp = &Ds[s_slot][lh][lj];
     if (s_gi < total) {
       const uint32_t dst = s_dst0 + (uint32_t)s_slot * (BW_T * FB_PITCH * 2);
-      if (s_tt * BW_T + sj < N) {
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(s_src) : "memory");
-        s_l = *s_lse; s_d = *s_dsm;
-      } else {
-        asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(dst), "r"(0u) : "memory");
+#pragma unroll
+      for (int c = 0; c < SPASS; ++c) {
+        if (s_tt * BW_T + sj + c * SROWS < N)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + c * (SROWS * FB_PITCH * 2)), "l"(s_src + c * s_pass_step) : "memory");
+        else
+          asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(dst + c * (SROWS * FB_PITCH * 2)), "r"(0u) : "memory");
       }
+      if (s_tt * BW_T + lj < N) { s_l = *s_lse; s_d = *s_dsm; }
       ++s_gi; s_slot = s_slot == 2 ? 0 : s_slot + 1;
       if (++s_tt == T) { s_tt = 0; s_src = s_src0; s_lse = s_lse0; s_dsm = s_dsm0; }
       else { s_src += s_src_step; s_lse += s_stat_step; s_dsm += s_stat_step; }
@@ -615,7 +625,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1) attn_bwd_fused4_kernel(const At
       const int64_t tok0 = tok_base + (int64_t)(ok0 ? kn0 : 0) * tok_stride, tok1 = tok_base + (int64_t)(ok1 ? kn1 : 0) * tok_stride;
       load_a_frag<D>(ka[mt], qkv + p.C + slab * CS + cbase, p.ldq, tok0, tok1, ok0, ok1, t);
       load_a_frag<D>(va[mt], qkv + 2 * p.C + slab * CS + cbase, p.ldq, tok0, tok1, ok0, ok1, t);
-      if (t == 2) { va[mt][0][0] = B_ONES2; va[mt][0][1] = B_ONES2; }          // the -D_i slots of dO meet ones here
+      if (D == 4 && t == 2) { va[mt][0][0] = B_ONES2; va[mt][0][1] = B_ONES2; }   // the -D_i slots of dO meet ones here
 #pragma unroll
       for (int r = 0; r < 2; ++r) {                                   // b_r = (keys 2t, 2t+1 of the r-th 8-key half; n = g = dim)
         const int ke = k0 + mt * 16 + r * 8 + 2 * t;
@@ -645,15 +655,15 @@ __global__ void __launch_bounds__(FB_THREADS, 1) attn_bwd_fused4_kernel(const At
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int nt = 4 * qh + j;
-        qb[j] = t < 2 ? *reinterpret_cast<const uint32_t*>(&Qs[b][nt * 8 + g][cbase + 2 * t]) : 0u;
-        gb[j] = t < 2 ? *reinterpret_cast<const uint32_t*>(&Gs[b][nt * 8 + g][cbase + 2 * t]) : 0u;
-        if (t == 2) gb[j] = b_split2(-Ds[b][head_l][nt * 8 + g]);
+        qb[j] = 2 * t < D ? *reinterpret_cast<const uint32_t*>(&Qs[b][nt * 8 + g][cbase + 2 * t]) : 0u;
+        gb[j] = 2 * t < D ? *reinterpret_cast<const uint32_t*>(&Gs[b][nt * 8 + g][cbase + 2 * t]) : 0u;
+        if (D == 4 && t == 2) gb[j] = b_split2(-Ds[b][head_l][nt * 8 + g]);
       }
 #pragma unroll
       for (int kl = 0; kl < 2; ++kl) {
         const int kk = 2 * qh + kl;
-        b_ldsm_x2_trans(qt[kl][0], qt[kl][1], &Qs[b][kk * 16 + (lane & 15)][cbase & ~7]);
-        b_ldsm_x2_trans(gt[kl][0], gt[kl][1], &Gs[b][kk * 16 + (lane & 15)][cbase & ~7]);
+        b_ldsm_x2_trans(qt[kl][0], qt[kl][1], &Qs[b][kk * 16 + (lane & 15)][D >= 8 ? cbase : (cbase & ~7)]);
+        b_ldsm_x2_trans(gt[kl][0], gt[kl][1], &Gs[b][kk * 16 + (lane & 15)][D >= 8 ? cbase : (cbase & ~7)]);
       }
       float dqa[2][4];
 #pragma unroll
@@ -670,12 +680,14 @@ __global__ void __launch_bounds__(FB_THREADS, 1) attn_bwd_fused4_kernel(const At
             b_mma1688_z(s, ka[mt][0][0], ka[mt][0][1], qb[j]);            // S^T: rows = my keys, columns = queries
             b_mma1688_z(dp, va[mt][0][0], va[mt][0][1], gb[j]);           // dP^T - D
             const float2 l2 = *reinterpret_cast<const float2*>(&Ls[b][head_l][nt * 8 + 2 * t]);
+            float2 d2 = make_float2(0.f, 0.f);
+            if (D != 4) d2 = *reinterpret_cast<const float2*>(&Ds[b][head_l][nt * 8 + 2 * t]);   // head_dim 4 folds D_i into the MMA
             float pw[4], ds[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               pw[i] = fast_exp2(fmaf(s[i], c, -((i & 1) ? l2.y : l2.x)));
               if (MASK && k0 + mt * 16 + g + (i >> 1) * 8 >= N) pw[i] = 0.f;
-              ds[i] = pw[i] * dp[i];
+              ds[i] = D == 4 ? pw[i] * dp[i] : pw[i] * (dp[i] - ((i & 1) ? d2.y : d2.x));
             }
             pa[half * 2 + 0] = b_pack(pw[0], pw[1]); pa[half * 2 + 1] = b_pack(pw[2], pw[3]);
             da[half * 2 + 0] = b_pack(ds[0], ds[1]); da[half * 2 + 1] = b_pack(ds[2], ds[3]);
@@ -688,7 +700,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1) attn_bwd_fused4_kernel(const At
           b_mma16816(dqa[kl], ta, kq[mt][0], kq[mt][1]);
         }
       }
-      if (t < 2) {                                                    // my head's 4 dims are columns 0..3 of the 8-wide tile
+      if (2 * t < D) {                                                // head_dim 4: my head's dims are columns 0..3 of the 8-wide tile
 #pragma unroll
         for (int kl = 0; kl < 2; ++kl) {
           float2* r0 = reinterpret_cast<float2*>(dq_mine + (tt * BW_T + kl * 16) * FB_QP);
@@ -713,7 +725,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1) attn_bwd_fused4_kernel(const At
       }
     }
     __syncthreads();
-    if (qh == 0 && 2 * t >= first && 2 * t < first + 4) {
+    if (qh == 0 && (D >= 8 || (2 * t >= first && 2 * t < first + 4))) {
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt) {
         const float* r = myred + (size_t)mt * 32 * 8;
@@ -724,7 +736,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1) attn_bwd_fused4_kernel(const At
         for (int h2 = 0; h2 < 2; ++h2) {
           const int kn = k0 + mt * 16 + g + h2 * 8;
           if (kn >= N) continue;
-          bf16* base = dqkv + (tok_base + (int64_t)kn * tok_stride) * p.ldq + slab * CS + (cbase & ~7) + 2 * t;
+          bf16* base = dqkv + (tok_base + (int64_t)kn * tok_stride) * p.ldq + slab * CS + (D >= 8 ? cbase : (cbase & ~7)) + 2 * t;
           *reinterpret_cast<uint32_t*>(base + p.C) = b_pack(k4[h2 * 2] * p.scale, k4[h2 * 2 + 1] * p.scale);
           *reinterpret_cast<uint32_t*>(base + 2 * p.C) = b_pack(v4[h2 * 2], v4[h2 * 2 + 1]);
         }
@@ -735,7 +747,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1) attn_bwd_fused4_kernel(const At
   __syncthreads();
   // ---- dq = scale * accumulator ----
   for (int i = tid; i < N * CPT; i += FB_THREADS) {
-    const int q = i >> 2, chunk = i & 3;
+    const int q = i / CPT, chunk = i % CPT;
     const float4 a = *reinterpret_cast<const float4*>(&dq_s[(size_t)q * FB_QP + chunk * 8]);
     const float4 bq = *reinterpret_cast<const float4*>(&dq_s[(size_t)q * FB_QP + chunk * 8 + 4]);
     uint4 o;
@@ -745,13 +757,14 @@ __global__ void __launch_bounds__(FB_THREADS, 1) attn_bwd_fused4_kernel(const At
   }
 }
 
-static int launch_bwd_fused4(const AttnParams& p, cudaStream_t st) {
+template <int D>
+static int launch_bwd_fused(const AttnParams& p, cudaStream_t st) {
   const int N = p.geom == TFSWA_GEOM_TSA ? p.H : p.W;
   const int rows = p.geom == TFSWA_GEOM_TSA ? p.B * p.W : p.B * p.H;
-  const int smem = fb_smem_bytes(N);
+  const int smem = fb_smem_bytes<D>(N);
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(attn_bwd_fused4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+    if (cudaFuncSetAttribute(attn_bwd_fused_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
       set_error("attn_bwd_fused: cudaFuncSetAttribute failed");
       return TFSWA_ECUDA;
     }
@@ -760,8 +773,8 @@ static int launch_bwd_fused4(const AttnParams& p, cudaStream_t st) {
   const int64_t M = (int64_t)p.B * p.H * p.W;
   const int64_t work = M * (p.C / 8);
   const unsigned dgrid = (unsigned)((work + 255) / 256 < 148 * 16 ? (work + 255) / 256 : 148 * 16);
-  attn_bwd_delta4_kernel<<<dgrid, 256, 0, st>>>((const bf16*)p.dout, (const bf16*)p.o, p.ldo, p.dsum, M, p.C, p.heads);
-  attn_bwd_fused4_kernel<<<dim3(rows, p.heads / 8), FB_THREADS, smem, st>>>(p);
+  attn_bwd_delta_kernel<D><<<dgrid, 256, 0, st>>>((const bf16*)p.dout, (const bf16*)p.o, p.ldo, p.dsum, M, p.C, p.heads);
+  attn_bwd_fused_kernel<D><<<dim3(rows, p.heads / 8), FB_THREADS, smem, st>>>(p);
   return check_launch("attn_bwd_fused");
 }
 
@@ -799,9 +812,11 @@ int attn_bwd_mma_bf16(const AttnParams& p, cudaStream_t st) {
   // head_dim 4, axial: one-pass kernel (P computed once) when the sequence's fp32 dQ accumulator fits in shared memory
   const char* fe = getenv("TFSWA_ATTN_BWD_FUSED");               // "0": keep the dq + dkv pair (A/B, tests)
   const bool fused = !(fe && fe[0] == '0');
-  if (!win && D == 4 && fused && p.C % 32 == 0 && (((uintptr_t)p.o) & 15) == 0 &&
-      fb_smem_bytes(p.geom == TFSWA_GEOM_TSA ? p.H : p.W) <= 227 * 1024)
-    return launch_bwd_fused4(p, st);
+  const int Nseq = p.geom == TFSWA_GEOM_TSA ? p.H : p.W;
+  if (!win && fused && (((uintptr_t)p.o) & 15) == 0) {
+    if (D == 4 && fb_smem_bytes<4>(Nseq) <= 227 * 1024) return launch_bwd_fused<4>(p, st);
+    if (D == 8 && fb_smem_bytes<8>(Nseq) <= 227 * 1024) return launch_bwd_fused<8>(p, st);
+  }
   if (win) {
     if (D == 4) return launch_bwd_mma<4, true>(p, st);
     if (D == 8) return launch_bwd_mma<8, true>(p, st);
