@@ -116,8 +116,12 @@ def test_train_step_matches_stock_optimizer_loop(precision):
             tot += float((p.detach() - q.detach()).double().pow(2).sum())
             den += float(q.detach().double().pow(2).sum())
         stats["param_rel_l2"] = (tot / den) ** 0.5
-        stats["bn_running"] = max(float(((u - v).abs() / (v.abs() + 1e-2)).max())       # running means sit near zero: mixed abs/rel
-                                  for (k, u), (_, v) in zip(a.state_dict().items(), b.state_dict().items()) if "running" in k)
+        num = den = 0.0                                          # global rel-L2 over all running statistics (a per-element
+        for (k, u), (_, v) in zip(a.state_dict().items(), b.state_dict().items()):   # maximum is an extreme-value statistic of the noise)
+            if "running" in k:
+                num += float((u - v).double().pow(2).sum())
+                den += float(v.double().pow(2).sum())
+        stats["bn_running"] = (num / den) ** 0.5
         # eval after training must see the updated weights (the prepared-weight caches key on version counters, which the
         # in-place arena update has to bump): compare with a cache-free model built from the trained state_dict
         fresh = T.TFSWAUNet(4, 4, [1, 1, 1, 1], [32, 64, 128, 256], 8, 4, 8).cuda()
@@ -128,16 +132,17 @@ def test_train_step_matches_stock_optimizer_loop(precision):
         with torch.no_grad():
             ya, yf, yb = a(x), fresh(x), b(x)
         stats["eval_vs_fresh"] = float((ya - yf).abs().max())
-        stats["eval_masks"] = float((ya - yb).abs().max())
+        stats["eval_masks"] = float((ya - yb).norm() / yb.norm())
         # Both sides run the same kernels; they differ by the accumulation order of the split-M weight-gradient atomics and,
         # from the second step on, by what bf16 rounding of the activations makes of that noise (Adam normalises every
         # element's update to O(lr), so noise-dominated gradient elements move the weights by up to lr either way).
-        # bf16 floors measured between two runs of the same stock loop (tools/debug/trainstep_diff.py): running means of
-        # near-zero-mean channels and the eval masks of a barely-warmed-up BatchNorm move by a few percent
-        lim = ({"loss": 2e-3, "norm": 5e-2, "param_rel_l2": 5e-3, "bn_running": 0.2, "eval_masks": 0.2, "eval_vs_fresh": 1e-3}
+        # bf16 floors: two runs of the same stock loop differ at this level too (tools/debug/trainstep_diff.py); global
+        # relative L2 norms are used because per-element maxima are extreme-value statistics of that noise
+        lim = ({"loss": 2e-3, "norm": 5e-2, "param_rel_l2": 5e-3, "bn_running": 2e-2, "eval_masks": 4e-2, "eval_vs_fresh": 1e-3}
                if precision == "bf16" else
                {"loss": 1e-5, "norm": 2e-3, "param_rel_l2": 1e-4, "bn_running": 1e-3, "eval_masks": 1e-3, "eval_vs_fresh": 1e-5})
         bad = {k: v for k, v in stats.items() if v > lim[k.rstrip("01")]}
+        print("train-step deviations:", precision, {k: float("%.3g" % v) for k, v in stats.items()})
         assert not bad, f"{bad} (all: {stats})"
     finally:
         T.set_precision("bf16")
