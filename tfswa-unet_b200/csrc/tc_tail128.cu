@@ -192,6 +192,13 @@ tc_tail128_kernel(const __grid_constant__ CUtensorMap tm_att, const __grid_const
     for (int tile = cta; tile < p.tiles; tile += ncta, ++it) {
       const int64_t m = (int64_t)tile * 128 + r;
       // ---------------- epilogue 1: y = acc + bp + x1, statistics, LN_hat(y) -> A1 ----------------
+      // the residual does not depend on the MMA: its loads are issued before the wait so their latency hides behind it
+      uint4 rraw[4];
+      {
+        const bf16* rrow = p.res + (int64_t)z * p.res_bs + (m < p.M ? m : 0) * p.ldr + t * 32;
+#pragma unroll
+        for (int h = 0; h < 4; ++h) rraw[h] = *reinterpret_cast<const uint4*>(rrow + h * 8);
+      }
       mbar_wait(&bar_m1, n_m1 & 1); ++n_m1;
       tc_fence_after();
       float y[32];
@@ -200,13 +207,14 @@ tc_tail128_kernel(const __grid_constant__ CUtensorMap tm_att, const __grid_const
         __syncwarp();
         tmem_ld_x32(lane_addr + t * 32, raw);
         tmem_ld_wait();
-        const bf16* rrow = p.res + (int64_t)z * p.res_bs + (m < p.M ? m : 0) * p.ldr + t * 32;
 #pragma unroll
         for (int h = 0; h < 4; ++h) {
-          float res[8];
-          load8(rrow + h * 8, res);
+          const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&rraw[h]);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) y[h * 8 + j] = __uint_as_float(raw[h * 8 + j]) + s_bp[t * 32 + h * 8 + j] + res[j];
+          for (int j = 0; j < 4; ++j) {
+            y[h * 8 + 2 * j] = __uint_as_float(raw[h * 8 + 2 * j]) + s_bp[t * 32 + h * 8 + 2 * j] + __low2float(hh[j]);
+            y[h * 8 + 2 * j + 1] = __uint_as_float(raw[h * 8 + 2 * j + 1]) + s_bp[t * 32 + h * 8 + 2 * j + 1] + __high2float(hh[j]);
+          }
         }
       }
       float s = 0.f;
