@@ -119,7 +119,10 @@ int tfswa_row_stats(const void* x, int64_t ldx, int64_t x_bs, float* stats, int6
  * qkv: (M, ldq) act with q|k|v each C wide starting at column 0|C|2C of the given pointer.
  * out: (M, ldo) act, C wide.  lse (optional): (M, heads) fp32 log2-domain logsumexp for backward.
  * SWA: pad_kv = (2C) fp32 k|v of a zero-padded token (= folded qkv bias); rel_bias optional
- * (heads, ws*ws, ws*ws) fp32; use_shift_mask adds the Swin {0,-100} mask (both OFF = reference). */
+ * (heads, ws*ws, ws*ws) fp32; use_shift_mask adds the Swin {0,-100} mask (both OFF = reference).
+ * flags: bit 0 (TFSWA_ATTN_FORCE_EXACT) makes tfswa_attn_tc_fwd skip the row-maximum bound and run its exact two-pass
+ * softmax (same result up to rounding; exists so tests can exercise the fallback path). */
+#define TFSWA_ATTN_FORCE_EXACT 1
 typedef struct {
   const void* qkv; int64_t ldq;
   void* out;       int64_t ldo;
@@ -128,12 +131,14 @@ typedef struct {
   const float* rel_bias;
   int32_t B, H, W, C, heads;
   int32_t geom, ws, shift, use_shift_mask, dtype;
+  int32_t flags;
 } tfswa_attn_args;
 int tfswa_attn_fwd(const tfswa_attn_args* a, void* stream);
 
-/* Same contract for the axial geometries (TSA / FSA) at head_dim 4 and 8, bf16, on the tcgen05 tensor cores:
- * QK^T and PV as tcgen05.mma with TMEM accumulators, heads packed along the MMA K dimension, exact two-pass softmax
- * with ex2.approx.ftz.bf16x2, the denominator accumulated by the tensor core through a ones column appended to V. */
+/* Same contract for the axial geometries (TSA / FSA) at head_dim 4, 8 and 16, bf16, on the tcgen05 tensor cores:
+ * K and V tiles arrive by TMA (the permutes of attention.py:143,217 are the tensor map's strides), QK^T and PV are
+ * tcgen05.mma with TMEM accumulators, heads share the K slab through masked copies of Q, the softmax denominator is
+ * accumulated by the tensor core through a ones tile appended to V. */
 /* scratch: caller-owned device buffer of tfswa_attn_tc_scratch_bytes(a) bytes (per-sequence k extrema for the softmax
  * shift bound); contents are dead after the call. */
 int64_t tfswa_attn_tc_scratch_bytes(const tfswa_attn_args* a);

@@ -72,3 +72,29 @@ def test_reference_import_path_shim():
     assert TFSWAUNet is T.TFSWAUNet and "TFSWABlock" in TFSWABlock.__name__
     x = torch.arange(2 * 3 * 16 * 8, dtype=torch.float32).reshape(2, 3, 16, 8)
     assert torch.equal(window_reverse(window_partition(x, 8), 8, 16, 8), x)
+
+
+REFERENCE = "/root/reference"
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REFERENCE, "src")), reason="reference tree not present (GPU box)")
+def test_install_as_reference_keeps_the_reference_packages_importable():
+    """with the real reference on sys.path the shim must not shadow `src` / `src.models` with empty stub
+    packages - the unmodified Trainer / SourceSeparator have to import and must pick up the B200 model."""
+    import subprocess
+    import sys
+    code = (
+        "import sys, types\n"
+        "for m in ('soundfile', 'musdb'): sys.modules[m] = types.ModuleType(m)\n"
+        "import tfswa_unet_b200 as T\n"
+        "T.install_as_reference()\n"
+        "import src.training.trainer as tr, src.evaluation.inference as inf, src.data.stft_processor as sp\n"
+        "from src.models.tfswa_unet import TFSWAUNet\n"
+        "from src.models.blocks import TFSWABlock\n"
+        "assert TFSWAUNet is T.TFSWAUNet and inf.TFSWAUNet is T.TFSWAUNet\n"
+        "assert tr.Trainer.__module__ == 'src.training.trainer' and sp.STFTProcessor is not None\n"
+        "assert 'reference' in sys.modules['src'].__path__[0]\n"
+        "print('ok')\n")
+    env = dict(os.environ, PYTHONPATH=REFERENCE + os.pathsep + ROOT, PYTHONDONTWRITEBYTECODE="1")
+    r = subprocess.run([sys.executable, "-W", "ignore", "-c", code], capture_output=True, text=True, env=env, cwd="/tmp")
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr

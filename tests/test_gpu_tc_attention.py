@@ -72,7 +72,7 @@ def test_tc_attention_exact_two_pass_path(B, H, W, C, geom):
     la = torch.empty((M, 8), dtype=torch.float32, device="cuda")
     lb = torch.empty_like(la)
     ops.attention(qkv, a, B, H, W, C, 8, geom, lse=la)
-    ops.attention(qkv, b, B, H, W, C, 8, geom, lse=lb, use_shift_mask=True)      # test hook: force the exact path
+    ops.attention(qkv, b, B, H, W, C, 8, geom, lse=lb, force_exact=True)      # test hook: the exact two-pass path
     torch.cuda.synchronize()
     ref = _ref(qkv, B, H, W, C, 8, geom)
     scale = float(ref.abs().max())

@@ -52,7 +52,8 @@ class AttnArgs(C.Structure):
     _fields_ = [("qkv", _p), ("ldq", _i64), ("out", _p), ("ldo", _i64), ("lse", _p),
                 ("pad_kv", _p), ("rel_bias", _p),
                 ("B", _i32), ("H", _i32), ("W", _i32), ("C", _i32), ("heads", _i32),
-                ("geom", _i32), ("ws", _i32), ("shift", _i32), ("use_shift_mask", _i32), ("dtype", _i32)]
+                ("geom", _i32), ("ws", _i32), ("shift", _i32), ("use_shift_mask", _i32), ("dtype", _i32),
+                ("flags", _i32)]
 
 
 class ConvArgs(C.Structure):

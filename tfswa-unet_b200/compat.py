@@ -17,17 +17,37 @@ from torch import nn
 
 
 def install_as_reference(package: str = "src.models") -> None:
+    """Route ``<package>.attention`` / ``.blocks`` / ``.tfswa_unet`` to this package's modules.
+
+    The real packages along ``package`` (``src``, ``src.models``) are imported first when they exist, so their
+    ``__path__`` stays intact and ``src.training.trainer`` / ``src.evaluation.inference`` / ``src.data...`` keep
+    importing from the reference tree; only the three leaf modules are replaced.  Stub packages are created only
+    where the real import fails (the reference is not on ``sys.path``).  If the reference's own leaf modules were
+    already imported, names other modules bound with ``from src.models.x import Y`` before this call keep pointing
+    at the reference classes - call this before importing the trainer / separator."""
+    import importlib
+
     from . import attention, blocks, tfswa_unet
     parts = package.split(".")
     for i in range(1, len(parts) + 1):
         name = ".".join(parts[:i])
-        if name not in sys.modules:
+        if name in sys.modules:
+            continue
+        try:
+            importlib.import_module(name)
+        except ImportError:
             mod = types.ModuleType(name)
-            mod.__path__ = []          # mark as package
+            mod.__path__ = []          # mark as (empty) package
             sys.modules[name] = mod
+            if i > 1:
+                setattr(sys.modules[".".join(parts[:i - 1])], parts[i - 1], mod)
     for leaf, mod in (("attention", attention), ("blocks", blocks), ("tfswa_unet", tfswa_unet)):
         sys.modules[f"{package}.{leaf}"] = mod
         setattr(sys.modules[package], leaf, mod)
+    # convenience re-exports some callers use (`from src.models import TFSWAUNet`)
+    for name in ("TFSWAUNet",):
+        if not hasattr(sys.modules[package], name):
+            setattr(sys.modules[package], name, getattr(tfswa_unet, name))
 
 
 def convert(model: nn.Module) -> nn.Module:

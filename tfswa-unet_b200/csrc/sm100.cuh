@@ -11,6 +11,15 @@ namespace sm100 {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// one lane of the (converged) warp, chosen by the hardware: inside `if (elect_one())` ptxas knows a single thread is
+// active and moves MMA / TMA operands to uniform registers with plain R2UR; under `if (lane == 0)` it wraps every
+// tcgen05.mma in a BRA.U.ANY waterfall loop (~12 instructions each)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 // ---------------- mbarrier ----------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -27,21 +36,41 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
+#ifdef TFSWA_MBAR_SUSPEND_HINT
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)     // suspend-time hint: sleep in hardware instead of spinning
+      : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)     // suspend-time hint (round 1): TRYWAIT + NANOSLEEP.SYNCS in SASS
       : "memory");
+#else
+  // no suspend-time hint: one SYNCS.PHASECHK.TRYWAIT that blocks in hardware for a bounded time and wakes on the
+  // completing arrival.  With the hint ptxas adds a NANOSLEEP.SYNCS whose wake-up cost ~1000 cycles per hand-off in the
+  // attention pipeline (tools/debug/tma_trace.py).
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+#endif
   return ok != 0;
 }
 // Bounded wait: a protocol bug must surface as a trapped kernel (launch error), never as a hung GPU.  try_wait sleeps
-// in hardware up to the suspend hint, so the retry count stays small; the bound is on retries, not on a clock read.
+// in hardware for a bounded time, so retries are rare on the good path; every 256th retry reads the global timer and the
+// kernel traps once a single wait has lasted more than ~4 s.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
+  uint64_t t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 24)) __trap();
+    if ((++spins & 255u) == 0) {
+      uint64_t now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ull) __trap();
+    }
   }
 }
 

@@ -603,7 +603,7 @@ extern "C" int tfswa_attn_tc_fwd(const tfswa_attn_args* a, void* scratch, int64_
   TFSWA_REQUIRE(scratch && scratch_bytes >= tfswa_attn_tc_scratch_bytes(a), "attn_tc: scratch buffer too small");
   TFSWA_REQUIRE(a->C <= 128, "attn_tc: C=%d > 128 unsupported", a->C);
   p.kext = (float*)scratch;
-  p.force_exact = a->use_shift_mask;      // (the mask flag has no meaning for axial geometries) test hook: exact two-pass path
+  p.force_exact = (a->flags & TFSWA_ATTN_FORCE_EXACT) ? 1 : 0;      // test hook: exact two-pass path
   const int N = a->geom == TFSWA_GEOM_TSA ? a->H : a->W;
   const int rows = a->geom == TFSWA_GEOM_TSA ? a->B * a->W : a->B * a->H;
   // Ragged remainder: the MMA needs 128-query tiles; when the last tile would hold only a few queries (1025 = 8*128 + 1,
@@ -615,16 +615,28 @@ extern "C" int tfswa_attn_tc_fwd(const tfswa_attn_args* a, void* scratch, int64_
   TFSWA_REQUIRE(rows <= 65535, "attn_tc: more than 65535 sequences in one launch (split the batch)");
   cudaStream_t st = (cudaStream_t)stream;
   attn_kext_kernel<<<rows, 256, 0, st>>>(p);
-  // TFSWA_AXIAL_KERNEL=umma|mma selects the main kernel (A/B): "umma" = tcgen05 + TMEM (this file), "mma" = register-
-  // resident warp-level MMAs (attention_axial_mma.cu)
-  // Measured on B200 (tools/attn_bench.py, C3 stage shapes): head_dim 4: umma 1.38 / 0.81 ms vs mma 1.42 / 0.86 ms
-  // (TSA / FSA); head_dim 8: 0.226 / 0.188 vs 0.211 / 0.160; head_dim 16: 0.077 / 0.078 vs 0.063 / 0.062 -> default below.
-  static int force = -1;                              // 0 = default choice, 1 = umma, 2 = mma
-  if (force < 0) { const char* e = getenv("TFSWA_AXIAL_KERNEL"); force = !e ? 0 : (e[0] == 'm' ? 2 : 1); }
-  const bool use_mma = force == 2 || (force == 0 && D >= 8);
+  // TFSWA_AXIAL_KERNEL=tma|umma|mma selects the main kernel (A/B): "tma" = tcgen05 + TMEM with TMA-fed operands
+  // (tc_attn_tma.cu), "umma" = round 1's thread-staged tcgen05 kernel (this file), "mma" = register-resident warp-level
+  // MMAs (attention_axial_mma.cu).
+  // Measured on B200 (tools/attn_bench.py, C3 stage shapes, B=8, TSA / FSA ms): head_dim 4: tma 9.42 / 5.35, umma 10.58 / 6.26;
+  // head_dim 8: tma 1.40 / 1.13, mma 1.46 / 1.01; head_dim 16: tma 0.39 / 0.41, mma 0.36 / 0.31 -> default below.
+  static int force = -1;                              // 0 = default choice, 1 = umma, 2 = mma, 3 = tma
+  if (force < 0) { const char* e = getenv("TFSWA_AXIAL_KERNEL"); force = !e ? 0 : (e[0] == 'm' ? 2 : (e[0] == 't' ? 3 : 1)); }
+  const bool use_mma = force == 2 || (force == 0 && (D == 16 || (D == 8 && N < 384)));
   if (use_mma && a->heads % 8 == 0) {                // 16-row granularity: no separate remainder pass
     AttnParams pm = p; pm.q_begin = 0; pm.q_end = 0;
     return attn_axial_mma_bf16(pm, st);
+  }
+  if (force == 3 || force == 0) {
+    int rc = attn_axial_tma_bf16(p, st);
+    if (rc) return rc;
+    if (q_tc < N) {                                  // ragged remainder (< 32 queries per sequence), see below
+      AttnParams ps = p;
+      ps.q_begin = q_tc; ps.q_end = 0;
+      if (a->heads % 8 == 0 && N - q_tc > 2) return attn_axial_mma_bf16(ps, st);
+      return attn_simt_axial_bf16(ps, st);
+    }
+    return TFSWA_OK;
   }
   static bool attr_set = false;
   if (!attr_set) {

@@ -1,0 +1,587 @@
+// Axial (TSA / FSA) attention on tcgen05 with TMA-fed operands (round 2; head_dim 4, 8, 16, bf16).
+//
+// The token regrouping of attention.py:143 / :217 (permute(0,3,2,1) / permute(0,2,3,1)) is a TMA tensor map here: the
+// q|k|v token matrix (M, ldq) is described once per launch as a 4-D tensor (channel, w, h, b); a key tile of a TSA
+// sequence is the box (8 channels, 1, 128 keys, 1), of an FSA sequence (8, 128, 1, 1).  A box lands in shared memory
+// as [key][16 B] - which is at the same time
+//   * the canonical no-swizzle K-MAJOR operand of S = Q K^T (keys = N, 8 keys x 16 B per core matrix; the second
+//     8-channel chunk of the quad is a second box, LBO apart), and
+//   * the canonical no-swizzle MN-MAJOR operand of O = P V (channels = N, keys = K).
+// So K and V go from HBM / L2 to the tensor core without a single thread touching them; rows beyond the sequence end
+// are zero-filled by the TMA unit.  What round 1 did by staging an "expanded K" and per-head V' with a producer warp
+// (a third of one sub-partition's issue slots) is moved to the operands that are constant over the key loop:
+//   * heads share the 16-channel K slab through HPQ = 16/d MASKED COPIES OF Q (head h's copy keeps channels
+//     [d h, d h + d) and zeros the rest): S_h = Q_h K^T, one MMA (M=128, N=KT, K=16) per head writes its 128/HPQ keys
+//     into its own TMEM columns - same MMA work as the expanded-K form, operand prepared once per CTA;
+//   * the softmax denominator comes out of the PV MMA: its B operand (N = 16) is [8 v channels | 8 x ones], the second
+//     N-group being a constant all-ones tile that the descriptor's stride field (SBO) points at.  D_h = [P_h V | l_h..]:
+//     the row sum is accumulated by the tensor core from the same bf16-rounded P as the numerator; the last key block
+//     uses a second tile with zeros at the absent keys.
+// Softmax warps (0-7): S (TMEM) -> registers -> P (TMEM, bf16) with
+//   * packed fp32 arithmetic (fma/add.f32x2 -> FFMA2/FADD2: one issue slot per two elements),
+//   * MUFU.EX2 for 11 of 16 element pairs and a degree-3 Cody-Waite polynomial on the FMA pipe for the other 5:
+//     tools/mufu_bench.cu measures 16.0 ex2/clk/SM for MUFU alone (4.64e12/s) and 21.8/clk/SM (6.3e12/s) for this mix
+//     at 4 warps per sub-partition,
+//   * no running maximum (row bound from the per-channel extrema of k, see tc_attention.cu); the polynomial's exponent
+//     clamp is compiled out for warps whose rows cannot reach 2^-120 (bound minus lower bound, checked once per CTA).
+// Warp 8 issues every MMA, warp 9 (one lane) every TMA; the key loop has no CTA-wide barrier:
+//   bar_full[s]  (tx)  stage s (128 keys: K lo|hi, V lo|hi = 8 KB) landed          TMA      -> issuer
+//   bar_empty[s] (1)   every MMA reading stage s has completed                     issuer commit -> producer
+//   bar_s   (1)  S(t) complete                                                     issuer commit -> softmax
+//   bar_a   (8)  S(t) pulled into registers by all softmax warps                   softmax  -> issuer (may issue S(t+1))
+//   bar_b   (8)  P(t) written to TMEM                                              softmax  -> issuer (may issue PV(t))
+//   bar_pv  (1)  PV(t) complete: P columns free                                    issuer commit -> softmax
+// Replaces attention.py:70-85 (+ permutes :143,:162,:217,:236), bf16 activations.
+#include "attn_common.cuh"
+#include "sm100.cuh"
+#include <stdlib.h>
+
+namespace tfswa {
+
+using namespace sm100;
+
+namespace tma_attn {
+
+#ifdef TFSWA_TMA_TRACE
+__device__ long long g_trace[8][128];   // debug: clock64 per (event, tile) of one CTA
+#define TRACE(ev, t) do { if (blockIdx.x == 0 && blockIdx.y == 1000 && (t) < 128) g_trace[ev][t] = clock64(); } while (0)
+#else
+#define TRACE(ev, t) do { } while (0)
+#endif
+
+constexpr int NTHREADS = 320;          // warps 0-7 softmax, 8 MMA issuer, 9 TMA producer
+constexpr int QTILE = 128;             // queries per CTA
+constexpr int SKEYS = 128;             // keys per shared-memory stage
+constexpr int NSTAGE = 4;             // TMA runs two stages ahead of the stage in use; a fourth covers the one being drained
+constexpr uint32_t TMEM_COLS = 256;
+constexpr int BOX_BYTES = SKEYS * 16;  // one TMA box: 128 keys x 8 channels bf16
+constexpr int STAGE_BYTES = 4 * BOX_BYTES;            // K lo, K hi, V lo, V hi
+template <int D> __host__ __device__ constexpr int q_bytes() { return (16 / D) * 4096; }
+template <int D> __host__ __device__ constexpr int stage_off() { return q_bytes<D>(); }
+template <int D> __host__ __device__ constexpr int ones_off() { return stage_off<D>() + NSTAGE * STAGE_BYTES; }
+template <int D> __host__ __device__ constexpr int tail_off() { return ones_off<D>() + 2 * BOX_BYTES; }
+template <int D> __host__ __device__ constexpr int smem_bytes() { return tail_off<D>() + 2 * BOX_BYTES; }   // 48 / 40 / 36 KB
+
+#ifndef TFSWA_TMA_POLY_K
+#define TFSWA_TMA_POLY_K 3
+#endif
+#ifndef TFSWA_TMA_PIPE
+#define TFSWA_TMA_PIPE 0
+#endif
+constexpr int POLY_K = TFSWA_TMA_POLY_K;   // every POLY_K-th element PAIR takes the polynomial (0 = MUFU only); -D for A/B builds
+
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
+// kind::f16 instruction descriptor with a K-major A and an MN-major B operand (bit 16)
+__device__ __forceinline__ uint32_t idesc_bf16_bmn(uint32_t M, uint32_t N) { return umma_idesc_bf16(M, N) | (1u << 16); }
+
+__device__ __forceinline__ float ex2_f32(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) { uint32_t y; asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(y) : "f"(hi), "f"(lo)); return y; }
+__device__ __forceinline__ uint64_t pk2(float a, float b) { uint64_t r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ uint64_t pk2u(uint32_t a, uint32_t b) { uint64_t r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ void up2(uint64_t r, float& a, float& b) { asm("mov.b64 {%0,%1}, %2;" : "=f"(a), "=f"(b) : "l"(r)); }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) { uint64_t d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) { uint64_t d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) { uint64_t d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+
+// 2^x for a pair of x <= 0 on the FMA / ALU pipes: x = n + r (round to nearest through the 1.5 * 2^23 trick), degree-3
+// minimax polynomial of 2^r on [-0.5, 0.5] (7.5e-5 relative - P is rounded to bf16, 3.9e-3), exponent patched in with an
+// integer shift-add.  3 FADD2 + 3 FFMA2 + 2 LEA for two results.  CLAMP bounds n at -125 (needed only when the row's
+// bound is more than 120 binades above its smallest possible score).
+template <bool CLAMP>
+__device__ __forceinline__ void ex2_poly2(uint64_t x, float& e0, float& e1) {
+  constexpr float MAGIC = 12582912.0f;
+  if (CLAMP) { float a, b; up2(x, a, b); x = pk2(fmaxf(a, -125.0f), fmaxf(b, -125.0f)); }
+  const uint64_t t = add2(x, pk2(MAGIC, MAGIC));
+  const uint64_t u = add2(t, pk2(-MAGIC, -MAGIC));
+  const uint64_t r = sub2(x, u);
+  uint64_t p = fma2(pk2(0.0551716685f, 0.0551716685f), r, pk2(0.2426111251f, 0.2426111251f));
+  p = fma2(p, r, pk2(0.6932609677f, 0.6932609677f));
+  p = fma2(p, r, pk2(0.9999280572f, 0.9999280572f));
+  float p0, p1, t0, t1;
+  up2(p, p0, p1); up2(t, t0, t1);
+  e0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
+  e1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
+}
+
+// 16 scores sc[16*HALF ..] -> 8 packed bf16x2 probabilities pk[8*HALF ..]: p = 2^(s*c - mc)
+template <bool CLAMP, int HALF>
+__device__ __forceinline__ void softmax_half(const uint32_t (&sc)[32], uint32_t (&pk)[16], float c, float mc) {
+  const uint64_t c2 = pk2(c, c), nm = pk2(-mc, -mc);
+#pragma unroll
+  for (int i = 8 * HALF; i < 8 * HALF + 8; ++i) {
+    const uint64_t x = fma2(pk2u(sc[2 * i], sc[2 * i + 1]), c2, nm);
+    float e0, e1;
+    if (POLY_K > 0 && (i % POLY_K) == POLY_K - 1) ex2_poly2<CLAMP>(x, e0, e1);
+    else { float x0, x1; up2(x, x0, x1); e0 = ex2_f32(x0); e1 = ex2_f32(x1); }
+    pk[i] = pack_bf16x2(e0, e1);
+  }
+}
+
+// TMEM: three S/P buffers of 64 columns (S tile = HPQ heads x KT keys fp32; P overwrites the thread's own S columns as
+// bf16 pairs) + O.  A softmax warp may run up to two tiles ahead of the slowest one.
+constexpr uint32_t NBUF = 3, BUF_COLS = 64;
+constexpr uint32_t O_COL2 = NBUF * BUF_COLS;          // 192: O accumulators, HPQ x 16 columns (d = 16: 32)
+
+template <int D>
+__global__ void __launch_bounds__(NTHREADS, 2) tc_attn_tma_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
+  constexpr int HPQ = 16 / D;            // heads per CTA (one 16-channel "quad")
+  constexpr int KT = 64 / HPQ;           // keys per S tile and head: HPQ heads x KT keys = 64 TMEM columns (16 / 32 / 64)
+  constexpr int TPS = SKEYS / KT;        // S tiles per shared-memory stage (8 / 4 / 2)
+  constexpr int HPT = D == 4 ? 2 : 1;    // head slots per softmax thread (32 columns = 2 heads x 16 keys at d = 4)
+  constexpr int Q_OFF = 0, ST_OFF = stage_off<D>(), ONES_OFF = ones_off<D>(), TAIL_OFF = tail_off<D>();
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar_full[NSTAGE], bar_empty[NSTAGE], bar_s[NBUF], bar_p[NBUF], bar_done;
+  __shared__ uint32_t s_tmem;
+  __shared__ float s_kext[2][16];        // per channel of the quad: min / max of k over the whole sequence
+  __shared__ float s_xch[HPQ == 1 ? 256 : 1];   // d = 16, exact pass: the two threads of a row exchange their maxima
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool softmax = warp < 8, issuer = warp == 8, producer = warp == 9;
+  const int nquads = p.C / 16;
+  const int row = blockIdx.y, q0 = (blockIdx.x / nquads) * QTILE, quad = blockIdx.x % nquads;
+  const bool tsa = p.geom == TFSWA_GEOM_TSA;
+  const int N = tsa ? p.H : p.W;
+  const int quarter = warp & 3, half = (warp >> 2) & 1;
+  const int r = quarter * 32 + lane;                 // my query row == my TMEM lane
+  const float c = p.qscale;                          // head_dim^-0.5 * log2(e)
+  const int T = (N + KT - 1) / KT;                   // S tiles
+  const int NST = (N + SKEYS - 1) / SKEYS;           // stages (TMA loads) per pass
+  const int tail_keys = N - (NST - 1) * SKEYS;       // valid keys in the last stage (1..128)
+  // sequence `row` -> tensor coordinates: TSA row = b * W + w (keys along h), FSA row = b * H + h (keys along w)
+  const int cb = tsa ? row / p.W : row / p.H;
+  const int cf = tsa ? row - cb * p.W : row - cb * p.H;
+  int64_t tok_base, tok_stride;
+  if (tsa) { tok_base = (int64_t)cb * p.H * p.W + cf; tok_stride = p.W; }
+  else { tok_base = (int64_t)row * p.W; tok_stride = 1; }
+
+  // ---- setup ----
+  if (warp == 0) {
+    if (lane == 0) {
+#pragma unroll
+      for (int i = 0; i < NSTAGE; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 1); }
+#pragma unroll
+      for (int i = 0; i < (int)NBUF; ++i) { mbar_init(&bar_s[i], 1); mbar_init(&bar_p[i], 8); }
+      mbar_init(&bar_done, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(&s_tmem, TMEM_COLS);
+  }
+  if (producer && elect_one()) prefetch_tmap(&tm);
+  // constant PV operands: all-ones tile (2 N-groups) and the last stage's tile with zeros at the absent keys
+  for (int i = tid; i < 2 * BOX_BYTES / 16; i += NTHREADS) {
+    reinterpret_cast<uint4*>(smem + ONES_OFF)[i] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+    const uint32_t v = ((i & (SKEYS - 1)) < tail_keys) ? 0x3F803F80u : 0u;
+    reinterpret_cast<uint4*>(smem + TAIL_OFF)[i] = make_uint4(v, v, v, v);
+  }
+  bool q_valid = false;
+  int64_t q_tok = 0;
+  uint4 qa = make_uint4(0, 0, 0, 0), qb = qa;        // my row's 16 q channels
+  if (softmax) {
+    if (q0 + r < (p.q_end ? p.q_end : N)) { q_tok = tok_base + (int64_t)(q0 + r) * tok_stride; q_valid = true; }
+    if (q_valid) {
+      const uint4* src = reinterpret_cast<const uint4*>((const bf16*)p.qkv + q_tok * p.ldq + quad * 16);
+      qa = src[0]; qb = src[1];
+    }
+    // masked copies of Q (K-major, 8-row x 16-byte core matrices): copy h keeps head h's channels.  The two threads of a
+    // row split the copies.
+    const uint32_t w[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};   // 2 channels per word
+#pragma unroll
+    for (int h = 0; h < HPQ; ++h) {                  // compile-time h: the masks are immediates, no local array
+      if ((HPQ >= 2 ? h / (HPQ / 2) : 0) != half) continue;
+      uint32_t m8[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) m8[i] = (2 * i >= D * h && 2 * i < D * h + D) ? w[i] : 0u;
+      uint8_t* dst = smem + Q_OFF + h * 4096 + (r >> 3) * 256 + (r & 7) * 16;
+      *reinterpret_cast<uint4*>(dst) = make_uint4(m8[0], m8[1], m8[2], m8[3]);
+      *reinterpret_cast<uint4*>(dst + 128) = make_uint4(m8[4], m8[5], m8[6], m8[7]);
+    }
+  }
+  if (tid < 32) {   // per-channel extrema of k over the sequence (attn_kext_kernel)
+    const float* ke = p.kext + ((int64_t)row * 2 + (tid >> 4)) * p.C + quad * 16 + (tid & 15);
+    s_kext[tid >> 4][tid & 15] = *ke;
+  }
+  fence_async_smem();                    // generic-proxy writes above are read by tcgen05.mma through the async proxy
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t tmem = s_tmem;
+  const uint32_t my_taddr = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * 32);   // my 32 columns of a buffer
+
+  // my head slots: d = 4: heads 2*half, 2*half + 1 (16 keys each per tile); d = 8: head `half`; d = 16: head 0, keys half*32..
+  // row bounds per head: sum_d min/max(q_d kmax_d, q_d kmin_d) <= s_ij <= ... (raw score units)
+  float m[HPT];
+  bool wide = false;                     // some row of this warp spans more than 120 binades: polynomial needs its clamp
+#pragma unroll
+  for (int hh = 0; hh < HPT; ++hh) m[hh] = 0.f;
+  if (softmax) {
+    const uint32_t w[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+#pragma unroll
+    for (int h = 0; h < HPQ; ++h) {                  // compile-time h (no runtime-indexed register arrays)
+      float hi = 0.f, lo = 0.f;
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        const int ch = h * D + d;
+        const float qv = __uint_as_float((ch & 1) ? (w[ch >> 1] & 0xFFFF0000u) : (w[ch >> 1] << 16));   // bf16 -> fp32
+        const float a = qv * s_kext[1][ch], b = qv * s_kext[0][ch];
+        hi += fmaxf(a, b); lo += fminf(a, b);
+      }
+#pragma unroll
+      for (int hh = 0; hh < HPT; ++hh) {
+        if ((D == 4 ? half * 2 + hh : (D == 8 ? half : 0)) == h) {
+          m[hh] = hi;
+          wide = wide || !((hi - lo) * c < 120.0f);
+        }
+      }
+    }
+    wide = __any_sync(0xffffffffu, wide);
+  }
+
+  // pipeline positions, monotonic across passes: stage counter, tile counter (buffer = gt % 3, parity = (gt / 3) & 1)
+  uint32_t n_stage = 0, n_done = 0;
+  // tile t of a pass uses TMEM buffer t % 3; every role keeps the parity of the next phase it will wait for per buffer
+  // (softmax: bar_s, issuer: bar_p) in three scalars, so the 3-way unrolled loops address buffers with immediates
+  uint32_t ph0 = 0, ph1 = 0, ph2 = 0;
+  auto wait_buf = [&](uint64_t* bars, int b) {      // runtime b (prologue / rare paths)
+    const uint32_t ph = b == 0 ? ph0 : (b == 1 ? ph1 : ph2);
+    mbar_wait(&bars[b], ph);
+    if (b == 0) ph0 ^= 1; else if (b == 1) ph1 ^= 1; else ph2 ^= 1;
+  };
+
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    const bool exact = attempt == 1 || p.force_exact;
+    // pass 0 (only if exact): stream S, reduce the exact row maxima.  pass 1: P = ex2(S c - m c), O += P [V | 1].
+    for (int pass = exact ? 0 : 1; pass < 2; ++pass) {
+      const bool maxpass = pass == 0;
+      if (producer) {
+        // ---- warp 9, one lane: TMA loads, NSTAGE-1 stages ahead; a stage is reused once every MMA that read it has completed ----
+        if (elect_one()) {
+          for (int i = 0; i < NST; ++i) {
+            const uint32_t g = n_stage + i, st = g % NSTAGE;
+            if (g >= NSTAGE) mbar_wait(&bar_empty[st], ((g / NSTAGE) - 1) & 1);   // stage g - NSTAGE released (waited in order, every one)
+            uint8_t* dst = smem + ST_OFF + st * STAGE_BYTES;
+            mbar_arrive_expect_tx(&bar_full[st], STAGE_BYTES);
+            const int ck = p.C + quad * 16, cv = 2 * p.C + quad * 16, k0 = i * SKEYS;
+            if (tsa) {
+              tma_load_4d(dst, &tm, &bar_full[st], ck, cf, k0, cb);
+              tma_load_4d(dst + BOX_BYTES, &tm, &bar_full[st], ck + 8, cf, k0, cb);
+              tma_load_4d(dst + 2 * BOX_BYTES, &tm, &bar_full[st], cv, cf, k0, cb);
+              tma_load_4d(dst + 3 * BOX_BYTES, &tm, &bar_full[st], cv + 8, cf, k0, cb);
+            } else {
+              tma_load_4d(dst, &tm, &bar_full[st], ck, k0, cf, cb);
+              tma_load_4d(dst + BOX_BYTES, &tm, &bar_full[st], ck + 8, k0, cf, cb);
+              tma_load_4d(dst + 2 * BOX_BYTES, &tm, &bar_full[st], cv, k0, cf, cb);
+              tma_load_4d(dst + 3 * BOX_BYTES, &tm, &bar_full[st], cv + 8, k0, cf, cb);
+            }
+          }
+        }
+      } else if (issuer) {
+        // ---- warp 8: every MMA.  P(t) written (bar_p) -> O += P(t) [V | 1], then S(t+3) into the same TMEM buffer: the
+        // two are issued back to back by one thread and the tensor core executes a thread's MMAs in issue order, so S(t+3)
+        // cannot overtake the PV MMA that reads the columns it overwrites ----
+        const uint32_t idesc_s = umma_idesc_bf16(128, KT);
+        const uint32_t idesc_pv = idesc_bf16_bmn(128, 16);
+        auto issue_S = [&](int u, uint32_t b) {      // lane 0; S(u) -> buffer b
+          const uint32_t st = (n_stage + u / TPS) % NSTAGE;
+          const uint32_t kaddr = sbase + ST_OFF + st * STAGE_BYTES + (u % TPS) * KT * 16;
+          const uint64_t kdesc = umma_smem_desc_ns(kaddr, BOX_BYTES, 128);
+#pragma unroll
+          for (int h = 0; h < HPQ; ++h)
+            umma_bf16_ss(tmem + b * BUF_COLS + h * KT, umma_smem_desc_ns(sbase + Q_OFF + h * 4096, 128, 256), kdesc, idesc_s, 0u);
+          umma_commit(&bar_s[b]);
+          TRACE(2, u);
+        };
+        auto wait_stage = [&](int u) {               // all lanes: the stage holding tile u has landed
+          const uint32_t g = n_stage + u / TPS, st = g % NSTAGE;
+          mbar_wait(&bar_full[st], (g / NSTAGE) & 1);
+        };
+        for (int u = 0; u < (int)NBUF && u < T; ++u) {
+          if (u % TPS == 0) wait_stage(u);
+          if (elect_one()) { tc_fence_after(); issue_S(u, u); }
+          __syncwarp();
+        }
+        for (int t0 = 0; t0 < T; t0 += (int)NBUF) {
+#pragma unroll
+          for (int b = 0; b < (int)NBUF; ++b) {      // compile-time buffer index
+            const int t = t0 + b;
+            if (t >= T) break;
+            const uint32_t st = (n_stage + t / TPS) % NSTAGE;
+            const int u = t + NBUF;
+            if (u < T && u % TPS == 0) wait_stage(u);
+            uint32_t& ph = b == 0 ? ph0 : (b == 1 ? ph1 : ph2);
+            mbar_wait(&bar_p[b], ph);                                   // P(t) written over S(t) (max pass: S(t) consumed)
+            ph ^= 1;
+            if (elect_one()) {
+              tc_fence_after();
+              TRACE(3, t);
+              if (!maxpass) {
+                const uint32_t vaddr = sbase + ST_OFF + st * STAGE_BYTES + 2 * BOX_BYTES + (t % TPS) * KT * 16;
+                const bool last_stage = t / TPS == NST - 1;
+                const uint32_t oaddr = sbase + (last_stage ? TAIL_OFF : ONES_OFF) + (t % TPS) * KT * 16;
+#pragma unroll
+                for (int h = 0; h < HPQ; ++h) {
+#pragma unroll
+                  for (int kk = 0; kk < KT / 16; ++kk) {   // 16 keys per MMA = 8 P columns inside the S columns they came from
+                    const uint32_t acc = (t | kk) ? 1u : 0u;
+                    const int scol = h * KT + kk * 16;     // first S column of these 16 keys
+                    const uint32_t pcol = tmem + b * BUF_COLS + (scol / 32) * 32 + (scol % 32) / 2;
+                    if (D == 16) {
+                      // [v channels 0-7 | 8-15] and, as a second accumulator, [ones | ones]
+                      umma_bf16_ts(tmem + O_COL2, pcol, umma_smem_desc_ns(vaddr + kk * 256, 128, BOX_BYTES), idesc_pv, acc);
+                      umma_bf16_ts(tmem + O_COL2 + 16, pcol, umma_smem_desc_ns(oaddr + kk * 256, 128, BOX_BYTES), idesc_pv, acc);
+                    } else {
+                      const uint32_t va = vaddr + ((h * D) / 8) * BOX_BYTES + kk * 256;   // the 8-channel group holding head h
+                      umma_bf16_ts(tmem + O_COL2 + 16 * h, pcol, umma_smem_desc_ns(va, 128, oaddr + kk * 256 - va), idesc_pv, acc);
+                    }
+                  }
+                }
+              }
+              if (u < T) issue_S(u, b);
+              if (t % TPS == TPS - 1 || t == T - 1) umma_commit(&bar_empty[st]);   // K rows (S) and V rows (PV) of the stage are done with
+              if (!maxpass && t == T - 1) umma_commit(&bar_done);
+            }
+            __syncwarp();
+          }
+        }
+      } else if (maxpass) {
+        // ---- exact row maxima (fallback / force_exact) ----
+#pragma unroll
+        for (int i = 0; i < HPT; ++i) m[i] = -CUDART_INF_F;
+        for (int t = 0; t < T; ++t) {
+          const int b = t % (int)NBUF;
+          wait_buf(bar_s, b);
+          tc_fence_after();
+          const int kcount = min(KT, N - t * KT);      // valid keys of this tile (per head)
+          uint32_t s[32];
+          __syncwarp();
+          tmem_ld_x32(my_taddr + b * BUF_COLS, s);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int key = D == 4 ? (i & 15) : (D == 8 ? i : half * 32 + i);
+            if (key < kcount) m[D == 4 ? i / 16 : 0] = fmaxf(m[D == 4 ? i / 16 : 0], __uint_as_float(s[i]));
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bar_p[b]);                       // S(t) consumed
+        }
+      } else {
+        // ---- P = ex2(S c - m c), written over S ----
+        float mc[HPT];
+#pragma unroll
+        for (int i = 0; i < HPT; ++i) mc[i] = m[i] * c;
+        const float mc0 = mc[0], mc1 = mc[HPT - 1];
+        uint32_t sc[32], pk[16];
+#if TFSWA_TMA_PIPE >= 1
+        // software pipeline (variants 1, 2): S(t+1) is waited for / loaded before tile t's P is stored and published
+        mbar_wait(&bar_s[0], ph0); ph0 ^= 1;
+        tc_fence_after();
+        __syncwarp();
+        tmem_ld_x32(my_taddr, sc);
+#endif
+        for (int t0 = 0; t0 < T; t0 += (int)NBUF) {
+#pragma unroll
+          for (int b = 0; b < (int)NBUF; ++b) {      // compile-time buffer index: TMEM / barrier addresses are immediates
+            const int t = t0 + b;
+            if (t >= T) break;
+            const int b1 = (b + 1) % (int)NBUF;      // compile-time after unrolling
+#if TFSWA_TMA_PIPE == 0
+            {
+              uint32_t& ph = b == 0 ? ph0 : (b == 1 ? ph1 : ph2);
+              mbar_wait(&bar_s[b], ph);
+              ph ^= 1;
+              tc_fence_after();
+              if (tid == 0) TRACE(0, t);
+              __syncwarp();
+              tmem_ld_x32(my_taddr + b * BUF_COLS, sc);
+            }
+#endif
+            tmem_ld_wait();
+            if (tid == 0) TRACE(4, t);
+            const bool tail = t == T - 1 && T * KT > N;   // last tile: absent keys score 0, which may exceed the bound
+            if (tail) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) sc[i] = __float_as_uint(fminf(__uint_as_float(sc[i]), m[D == 4 ? i / 16 : 0]));
+            }
+#if TFSWA_TMA_PIPE == 0
+            if (tail || wide) { softmax_half<true, 0>(sc, pk, c, mc0); softmax_half<true, 1>(sc, pk, c, mc1); }
+            else { softmax_half<false, 0>(sc, pk, c, mc0); softmax_half<false, 1>(sc, pk, c, mc1); }
+#else
+            if (tail || wide) softmax_half<true, 0>(sc, pk, c, mc0); else softmax_half<false, 0>(sc, pk, c, mc0);
+#endif
+#if TFSWA_TMA_PIPE == 1
+            if (t + 1 < T) {
+              uint32_t& ph = b1 == 0 ? ph0 : (b1 == 1 ? ph1 : ph2);
+              mbar_wait(&bar_s[b1], ph);
+              ph ^= 1;
+              if (tid == 0) TRACE(0, t + 1);
+            }
+#endif
+#if TFSWA_TMA_PIPE != 0
+            if (tail || wide) softmax_half<true, 1>(sc, pk, c, mc1); else softmax_half<false, 1>(sc, pk, c, mc1);
+#endif
+            if (tid == 0) TRACE(5, t);
+#if TFSWA_TMA_PIPE >= 1
+            if (t + 1 < T) {
+#if TFSWA_TMA_PIPE == 2
+              uint32_t& ph = b1 == 0 ? ph0 : (b1 == 1 ? ph1 : ph2);
+              mbar_wait(&bar_s[b1], ph);
+              ph ^= 1;
+              if (tid == 0) TRACE(0, t + 1);
+#endif
+              tc_fence_after();
+              __syncwarp();
+              tmem_ld_x32(my_taddr + b1 * BUF_COLS, sc);            // S(t+1): in flight under the store / arrive below
+            }
+#endif
+            tmem_st_x16(my_taddr + b * BUF_COLS, pk);  // score pair (2i, 2i+1) -> 32-bit cell i of my own columns
+            tmem_st_wait();
+            if (tid == 0) TRACE(6, t);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_p[b]);                     // P(t) in TMEM
+            if (tid == 0) TRACE(1, t);
+          }
+        }
+        mbar_wait(&bar_done, n_done & 1); ++n_done;                    // every PV MMA has completed
+        tc_fence_after();
+      }
+      n_stage += NST;
+      if (maxpass) {
+        if (HPQ == 1 && softmax) s_xch[half * 128 + r] = m[0];
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+        if (HPQ == 1) {                                // the two threads of a row each saw half of the keys
+          if (softmax) m[0] = fmaxf(s_xch[r], s_xch[128 + r]);
+          __syncthreads();
+        }
+      }
+    }
+    // ---- epilogue: O / l.  D_h = [P_h V over the 8-channel group holding head h | l_h x 8] ----
+    const uint32_t o_taddr = tmem + ((uint32_t)(quarter * 32) << 16) + O_COL2;
+    uint32_t o[32];
+    bool bad = false;
+    if (softmax) {
+      __syncwarp();
+      if (D == 8) {
+        uint32_t t16[16];
+        tmem_ld_x16(o_taddr + 16 * half, t16);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) o[i] = t16[i];
+      } else {
+        tmem_ld_x32(o_taddr + (D == 4 ? 32 * half : 0), o);
+        tmem_ld_wait();
+      }
+      // the bound keeps every exponent <= 0; if it was so loose that a whole row underflowed (denominator ~ 0) the CTA
+      // repeats the computation with the exact maximum
+      if (D == 16) bad = q_valid && !(__uint_as_float(o[16]) > 1e-30f);
+      else {
+#pragma unroll
+        for (int hh = 0; hh < HPT; ++hh) bad = bad || (q_valid && !(__uint_as_float(o[hh * 16 + 8]) > 1e-30f));
+      }
+    }
+    tc_fence_before();
+    const bool redo = attempt == 0 && !p.force_exact && __syncthreads_or(bad);
+    if (redo) continue;
+    if (softmax && q_valid) {
+      if (D == 16) {                                 // both threads of the row hold the same 32 columns: split the 16 dims
+        const float l = __uint_as_float(o[16]);
+        const float inv = 1.0f / l;
+        float v[8];
+#pragma unroll
+        for (int d = 0; d < 8; ++d) v[d] = __uint_as_float(half ? o[8 + d] : o[d]) * inv;
+        store8((bf16*)p.out + q_tok * p.ldo + quad * 16 + half * 8, v);
+        if (p.lse && half == 0) p.lse[q_tok * p.heads + quad] = m[0] * c + log2f(l);
+      } else {
+#pragma unroll
+        for (int hh = 0; hh < HPT; ++hh) {
+          const int head = half * HPT + hh;          // head within the quad
+          const int off = hh * 16 + ((D == 4) ? (hh & 1) * 4 : 0);   // head h's dims start at (h*D) % 8 inside its group
+          const float l = __uint_as_float(o[hh * 16 + 8]);
+          const float inv = 1.0f / l;
+          bf16* op = (bf16*)p.out + q_tok * p.ldo + quad * 16 + head * D;
+          if (D == 4) {
+            float v[4];
+#pragma unroll
+            for (int d = 0; d < 4; ++d) v[d] = __uint_as_float(o[off + d]) * inv;
+            store4(op, v);
+          } else {
+            float v[8];
+#pragma unroll
+            for (int d = 0; d < 8; ++d) v[d] = __uint_as_float(o[off + d]) * inv;
+            store8(op, v);
+          }
+          if (p.lse) p.lse[q_tok * p.heads + quad * HPQ + head] = m[hh] * c + log2f(l);
+        }
+      }
+    }
+    break;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);
+}
+
+}  // namespace tma_attn
+
+// 4-D view of the q|k|v token matrix: (channel, w, h, b); box = 8 channels x 128 keys along the attended axis
+static int make_tmap_qkv(CUtensorMap* out, const AttnParams& p) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return TFSWA_ECUDA; }
+  const bool tsa = p.geom == TFSWA_GEOM_TSA;
+  cuuint64_t dims[4] = {(cuuint64_t)(3 * p.C), (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.B};
+  cuuint64_t strides[3] = {(cuuint64_t)p.ldq * 2, (cuuint64_t)p.W * p.ldq * 2, (cuuint64_t)p.H * p.W * p.ldq * 2};
+  cuuint32_t box[4] = {8, tsa ? 1u : (cuuint32_t)tma_attn::SKEYS, tsa ? (cuuint32_t)tma_attn::SKEYS : 1u, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  if (((uintptr_t)p.qkv & 15) || (strides[0] & 15)) { set_error("attn_tc: q|k|v base / row stride must be 16-byte aligned"); return TFSWA_EINVAL; }
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(p.qkv), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("attn_tc: cuTensorMapEncodeTiled failed (CUresult %d)", (int)r); return TFSWA_ECUDA; }
+  return TFSWA_OK;
+}
+
+// queries [0, p.q_end) of every sequence (q_end = 0: all); needs p.kext filled by attn_kext_kernel
+int attn_axial_tma_bf16(const AttnParams& p, cudaStream_t st) {
+  using namespace tma_attn;
+  const int D = p.C / p.heads;
+  const int N = p.geom == TFSWA_GEOM_TSA ? p.H : p.W;
+  const int rows = p.geom == TFSWA_GEOM_TSA ? p.B * p.W : p.B * p.H;
+  const int q_end = p.q_end ? p.q_end : N;
+  CUtensorMap tm;
+  int rc = make_tmap_qkv(&tm, p);
+  if (rc) return rc;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  static bool attr_set[64] = {};
+  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+    cudaError_t e1 = cudaFuncSetAttribute(tc_attn_tma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<4>());
+    cudaError_t e2 = cudaFuncSetAttribute(tc_attn_tma_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<8>());
+    cudaError_t e3 = cudaFuncSetAttribute(tc_attn_tma_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<16>());
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) { set_error("attn_tc: cudaFuncSetAttribute failed"); return TFSWA_ECUDA; }
+    attr_set[dev] = true;
+  }
+  dim3 grid(((q_end + QTILE - 1) / QTILE) * (p.C / 16), rows, 1);
+  if (D == 4) tc_attn_tma_kernel<4><<<grid, NTHREADS, smem_bytes<4>(), st>>>(tm, p);
+  else if (D == 8) tc_attn_tma_kernel<8><<<grid, NTHREADS, smem_bytes<8>(), st>>>(tm, p);
+  else tc_attn_tma_kernel<16><<<grid, NTHREADS, smem_bytes<16>(), st>>>(tm, p);
+  return check_launch("attn_tc(tma)");
+}
+
+}  // namespace tfswa
+
+#ifdef TFSWA_TMA_TRACE
+// debug builds only (tools/build_variant.sh trace tc_attn_tma.cu -DTFSWA_TMA_TRACE): copy the per-tile clock samples out
+extern "C" int tfswa_dbg_tma_trace(long long* host) {
+  return (int)cudaMemcpyFromSymbol(host, tfswa::tma_attn::g_trace, sizeof(long long) * 8 * 128);
+}
+#endif

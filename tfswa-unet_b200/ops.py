@@ -243,7 +243,7 @@ def row_stats(x: Tensor) -> Tensor:
 
 def attention(qkv: Tensor, out: Tensor, B: int, H: int, W: int, C_: int, heads: int, geom: int, *, ws: int = 8,
               shift: int = 0, pad_kv: Optional[Tensor] = None, rel_bias: Optional[Tensor] = None,
-              use_shift_mask: bool = False, lse: Optional[Tensor] = None) -> Tensor:
+              use_shift_mask: bool = False, lse: Optional[Tensor] = None, force_exact: bool = False) -> Tensor:
     """qkv: (M, >=3C) view with q|k|v at columns 0|C|2C; out: (M, C) view (both row-strided, dense rows)."""
     _cuda(qkv, out)
     if qkv.dim() != 2 or out.dim() != 2 or qkv.stride(1) != 1 or out.stride(1) != 1:
@@ -256,6 +256,7 @@ def attention(qkv: Tensor, out: Tensor, B: int, H: int, W: int, C_: int, heads: 
     a.lse, a.pad_kv, a.rel_bias = _p(lse), _p(pad_kv), _p(rel_bias)
     a.B, a.H, a.W, a.C, a.heads = B, H, W, C_, heads
     a.geom, a.ws, a.shift, a.use_shift_mask, a.dtype = geom, ws, shift, int(use_shift_mask), _dt(qkv)
+    a.flags = 1 if force_exact else 0          # TFSWA_ATTN_FORCE_EXACT (tests)
     d = C_ // heads
     tc = USE_TC_ATTENTION and qkv.dtype == torch.bfloat16 and geom != L.GEOM_SWA and d in (4, 8, 16) and heads * d == C_ and C_ <= 128
     if tc:
