@@ -249,10 +249,13 @@ int tfswa_grad_sumsq(const float* g, int64_t n, double* sumsq, void* stream);
  *         grad_scale = 1/world when g holds the all-reduced SUM of the per-rank gradients)
  * p *= 1 - lr*weight_decay;  m = beta1 m + (1-beta1) g_eff;  v = beta2 v + (1-beta2) g_eff^2;
  * p -= lr/(1-beta1^step) * m / (sqrt(v)/sqrt(1-beta2^step) + eps)                 (torch.optim.AdamW, step >= 1)
- * norm_out (optional, device) receives the unclipped total norm; a non-finite norm skips the update. */
+ * norm_out (optional, device) receives the unclipped total norm; a non-finite norm skips the update.
+ * skipped (optional, device int64, caller-zeroed once): number of skipped updates so far.  A skipped update increments
+ * it and the bias corrections use step - *skipped, so a skipped step does not advance the optimiser state (the
+ * semantics of GradScaler.step around torch.optim.AdamW, trainer.py:215-216). */
 int tfswa_adamw_clip_step(float* p, const float* g, float* m, float* v, int64_t n, const double* sumsq, float* norm_out,
                           float grad_scale, float max_norm, float lr, float beta1, float beta2, float eps, float weight_decay,
-                          int64_t step, void* stream);
+                          int64_t step, long long* skipped, void* stream);
 
 #ifdef __cplusplus
 }

@@ -132,20 +132,76 @@ def test_unet_forward_golden(golden, name, precision):
         assert float((masks.cpu() - case["y"]).abs().max()) <= 2e-2
 
 
-def test_unet_config0_shape_vs_oracle():
+_CONFIG0_REF = {}
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_unet_config0_shape_vs_oracle(precision):
     """BASELINE.json configs[0] (the reference's tests/test_model.py forward): TFSWA-UNet 15.4 M params, input
-    (2,2,256,512) fp32 - fp32 kernels against the CPU oracle on the same seeded weights and input."""
+    (2,2,256,512) - the fp32 kernels AND the bf16 tensor-core path against the CPU oracle (fp32, computed once) on the
+    same seeded weights and input."""
     T = _T()
-    T.set_precision("fp32")
-    m, sd = _filled("unet", 32, 5, gain=0.7, cin=2, cout=2)
-    m.eval().cuda()
-    assert sum(p.numel() for p in m.parameters()) == 15404834
-    x = seeded((2, 2, 256, 512), 6)
-    with torch.no_grad():
-        masks = m(x.cuda())
-        ref = O.unet_forward(x, sd)
-    assert masks.shape == (2, 2, 256, 512) and masks.dtype == torch.float32
-    assert_close("config0.masks", masks, ref, 2e-4)
+    try:
+        T.set_precision(precision)
+        m, sd = _filled("unet", 32, 5, gain=0.7, cin=2, cout=2)
+        m.eval().cuda()
+        assert sum(p.numel() for p in m.parameters()) == 15404834
+        x = seeded((2, 2, 256, 512), 6)
+        if "ref" not in _CONFIG0_REF:
+            with torch.no_grad():
+                _CONFIG0_REF["ref"] = O.unet_forward(x, sd, return_logits=True)
+        ref_masks, ref_logits = _CONFIG0_REF["ref"]
+        with torch.no_grad():
+            masks, logits = m(x.cuda(), return_logits=True)
+        assert masks.shape == (2, 2, 256, 512) and masks.dtype == torch.float32
+        if precision == "fp32":
+            assert_close("config0.masks", masks, ref_masks, 2e-4)
+            assert_close("config0.logits", logits, ref_logits, 2e-4)
+        else:
+            e = rel_l2(logits.float(), ref_logits)
+            assert e <= BF16_L2, f"config0 bf16 logits rel-L2 {e:.3e}"
+            assert float((masks.cpu() - ref_masks).abs().max()) <= 2e-2
+    finally:
+        T.set_precision("bf16")
+
+
+def test_gradient_checkpointing_over_tfswa_blocks():
+    """the reference's enable_gradient_checkpointing (src/optimization/gradient_checkpoint.py:44-69) finds
+    modules whose class name contains 'TFSWABlock', replaces their instance `forward` with
+    torch.utils.checkpoint.checkpoint(original_forward, ..., use_reentrant=False) in training mode.  The same patch applied
+    to the product model must give the same loss and gradients as the unpatched model (recompute = same kernels)."""
+    from torch.utils.checkpoint import checkpoint
+    T = _T()
+    try:
+        T.set_precision("fp32")
+        x = seeded((1, 2, 40, 24), 91).cuda()
+        wgt = seeded((1, 2, 40, 24), 92).cuda()
+        res = {}
+        for mode in ("plain", "checkpointed"):
+            m, _ = _filled("unet", 32, 5, gain=0.7, cin=2, cout=2)
+            m.train().cuda()
+            patched = 0
+            if mode == "checkpointed":
+                for mod in m.modules():
+                    if "TFSWABlock" in type(mod).__name__:
+                        orig = mod.forward
+
+                        def fwd(*a, _orig=orig, _mod=mod, **kw):
+                            return checkpoint(_orig, *a, **kw, use_reentrant=False) if _mod.training else _orig(*a, **kw)
+                        mod.forward = fwd
+                        patched += 1
+                assert patched == 22
+            y = m(x)
+            loss = (y * wgt).sum()
+            loss.backward()
+            torch.cuda.synchronize()
+            res[mode] = (loss.detach(), {k: p.grad.detach().clone() for k, p in m.named_parameters()})
+        (l0, g0), (l1, g1) = res["plain"], res["checkpointed"]
+        assert abs(float(l0) - float(l1)) <= 1e-5 * abs(float(l0)) + 1e-6
+        for k in g0:
+            assert_close(f"ckpt.{k}", g1[k], g0[k], 1e-4, atol=1e-6)
+    finally:
+        T.set_precision("bf16")
 
 
 @pytest.mark.parametrize("shape,C,shift", [((1, 32, 65, 41), 32, 4), ((2, 64, 33, 50), 64, 4), ((1, 128, 24, 40), 128, 0),

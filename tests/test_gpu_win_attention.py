@@ -1,11 +1,33 @@
 """GPU (-m gpu): register-resident SW-MSA window attention (tfswa_attn_win_tc_fwd, warp-level MMAs) against the fp32-math
-SIMT kernel on the same bf16 q|k|v, for every head_dim of the model, padded windows and cyclic shift."""
+SIMT kernel on the same bf16 q|k|v AND against a torch fp32 restatement of attention.py:358-401, for every head_dim of the
+model, padded windows and cyclic shift."""
 import pytest
 import torch
 
 from helpers import seeded
 
 pytestmark = pytest.mark.gpu
+
+
+def _ref_windows(qkv, B, H, W, C, heads, ws, shift, pad_kv):
+    """torch fp32 restatement of attention.py:358-401 on q|k|v tokens: zero-padded tokens are real keys whose k|v are
+    `pad_kv` (= the folded qkv bias of a LayerNorm'ed zero token), roll(-shift), 8x8 windows, softmax(QK^T/sqrt(d)) V,
+    reverse, roll back, crop."""
+    d = C // heads
+    Hp, Wp = -(-H // ws) * ws, -(-W // ws) * ws
+    t = qkv.float().view(B, H, W, 3 * C)
+    full = torch.zeros((B, Hp, Wp, 3 * C), device=qkv.device)
+    full[..., C:] = pad_kv.view(1, 1, 1, 2 * C)
+    full[:, :H, :W] = t
+    if shift:
+        full = torch.roll(full, shifts=(-shift, -shift), dims=(1, 2))
+    win = full.view(B, Hp // ws, ws, Wp // ws, ws, 3 * C).permute(0, 1, 3, 2, 4, 5).reshape(-1, ws * ws, 3, heads, d)
+    q, k, v = win[:, :, 0].transpose(1, 2), win[:, :, 1].transpose(1, 2), win[:, :, 2].transpose(1, 2)     # (nW, h, 64, d)
+    o = torch.softmax((q @ k.transpose(-1, -2)) * d ** -0.5, -1) @ v
+    o = o.transpose(1, 2).reshape(B, Hp // ws, Wp // ws, ws, ws, C).permute(0, 1, 3, 2, 4, 5).reshape(B, Hp, Wp, C)
+    if shift:
+        o = torch.roll(o, shifts=(shift, shift), dims=(1, 2))
+    return o[:, :H, :W].reshape(B * H * W, C)
 
 
 @pytest.mark.parametrize("B,H,W,C,shift", [
@@ -49,6 +71,13 @@ def test_window_attention_matches_simt(B, H, W, C, shift):
     err = float((out_tc.float() - out_s.float()).abs().max())
     assert err <= 2e-2 * scale, f"window tc vs simt: {err:.3e} (scale {scale:.3e})"
     assert float((lse_tc - lse_s).abs().max()) <= 3e-2, "log-sum-exp mismatch"
+    # and against a torch fp32 restatement of the same op (not only CUDA against CUDA)
+    ref = _ref_windows(qkv.contiguous(), B, H, W, C, heads, 8, shift, pad_kv)
+    rscale = float(ref.abs().max())
+    e_tc = float((out_tc.float() - ref).abs().max())
+    e_s = float((out_s.float() - ref).abs().max())
+    assert e_tc <= 2e-2 * rscale, f"window tc vs torch fp32: {e_tc:.3e} (scale {rscale:.3e})"
+    assert e_s <= 1e-2 * rscale, f"window simt vs torch fp32: {e_s:.3e}"
 
 
 def test_window_features_stay_on_simt():

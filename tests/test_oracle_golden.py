@@ -143,3 +143,33 @@ def test_product_flop_model_equals_the_checker():
     for args in [(1, 2, 2, 64, 96), (8, 2, 2, 1025, 517), (8, 4, 4, 1025, 517)]:
         assert flops.model_flops(*args) == O.count_model_flops(*args)
     assert flops.model_flops(1, 2, 2, 64, 96) == 13127385088
+
+
+def test_product_window_helpers_and_mask_buffer_match_reference():
+    """the PRODUCT's window_partition / window_reverse and the attn_mask buffer its ShiftedWindowAttention
+    registers, against outputs of the live reference (tests/golden/make_golden_windows.py) - not only the oracle's."""
+    import os
+    import tfswa_unet_b200 as T
+    from tfswa_unet_b200.attention import window_partition, window_reverse
+    from helpers import seeded
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "golden_windows_v1.pt"), weights_only=False)
+    for case in g["cases"]:
+        x = seeded(case["shape"], case["seed"])
+        win = window_partition(x, case["ws"])
+        assert torch.equal(win, case["windows"]), case["shape"]
+        assert torch.equal(window_reverse(win, case["ws"], case["shape"][2], case["shape"][3]), x)
+        assert torch.equal(O.window_partition(x, case["ws"]), case["windows"])          # and the checker's own
+    for (ws, shift), ref in g["masks"].items():
+        m = T.ShiftedWindowAttention(32, ws, 8, shift_size=shift)
+        if ref is None:
+            assert m.attn_mask is None and "attn_mask" not in m.state_dict()
+        else:
+            assert m.attn_mask.dtype == torch.float32 and tuple(m.attn_mask.shape) == tuple(ref.shape)
+            assert torch.equal(m.attn_mask.to(torch.int8), ref), (ws, shift)
+            assert "attn_mask" in m.state_dict()
+
+
+def test_product_attn_mask_matches_main_golden(golden):
+    import tfswa_unet_b200 as T
+    m = T.ShiftedWindowAttention(32, 8, 8, shift_size=4)
+    assert torch.equal(m.attn_mask.to(torch.int8), golden["attn_mask_ws8_s4"])

@@ -96,7 +96,7 @@ SIGNATURES = {
     "tfswa_head_tail_bwd": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _p]),
     # optimiser step over the flat arena
     "tfswa_grad_sumsq": (C.c_int, [_p, _i64, _p, _p]),
-    "tfswa_adamw_clip_step": (C.c_int, [_p, _p, _p, _p, _i64, _p, _p, _f, _f, _f, _f, _f, _f, _f, _i64, _p]),
+    "tfswa_adamw_clip_step": (C.c_int, [_p, _p, _p, _p, _i64, _p, _p, _f, _f, _f, _f, _f, _f, _f, _i64, _p, _p]),
 }
 
 _lib = None

@@ -321,11 +321,11 @@ __global__ void __launch_bounds__(AX_THREADS, MINB) attn_axial_mma_kernel(const 
 
 template <int D, int MT, int MINB>
 static int launch_axial(const AttnParams& p, int q_count, int rows, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_once;
+  if (attr_once.needed()) {
     cudaError_t e = cudaFuncSetAttribute(attn_axial_mma_kernel<D, MT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, ax_smem_bytes<D>());
     if (e != cudaSuccess) { set_error("attn_axial_mma: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return TFSWA_ECUDA; }
-    attr_set = true;
+    attr_once.done();
   }
   dim3 grid((q_count + 16 * MT - 1) / (16 * MT), rows, p.heads / 8);
   attn_axial_mma_kernel<D, MT, MINB><<<grid, AX_THREADS, ax_smem_bytes<D>(), st>>>(p);

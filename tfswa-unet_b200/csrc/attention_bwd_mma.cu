@@ -762,13 +762,13 @@ static int launch_bwd_fused(const AttnParams& p, cudaStream_t st) {
   const int N = p.geom == TFSWA_GEOM_TSA ? p.H : p.W;
   const int rows = p.geom == TFSWA_GEOM_TSA ? p.B * p.W : p.B * p.H;
   const int smem = fb_smem_bytes<D>(N);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_once;
+  if (attr_once.needed()) {
     if (cudaFuncSetAttribute(attn_bwd_fused_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
       set_error("attn_bwd_fused: cudaFuncSetAttribute failed");
       return TFSWA_ECUDA;
     }
-    attr_set = true;
+    attr_once.done();
   }
   const int64_t M = (int64_t)p.B * p.H * p.W;
   const int64_t work = M * (p.C / 8);
@@ -780,12 +780,12 @@ static int launch_bwd_fused(const AttnParams& p, cudaStream_t st) {
 
 template <int D, bool WIN>
 static int launch_bwd_mma(const AttnParams& p, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_once;
+  if (attr_once.needed()) {
     cudaError_t e1 = cudaFuncSetAttribute(attn_bwd_dq_mma_kernel<D, WIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, bw_smem_bytes<D>());
     cudaError_t e2 = cudaFuncSetAttribute(attn_bwd_dkv_mma_kernel<D, WIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, bw_smem_bytes<D>());
     if (e1 != cudaSuccess || e2 != cudaSuccess) { set_error("attn_bwd_mma: cudaFuncSetAttribute failed"); return TFSWA_ECUDA; }
-    attr_set = true;
+    attr_once.done();
   }
   const int per_cta = 16 * bw_mt<D>();
   dim3 grid;

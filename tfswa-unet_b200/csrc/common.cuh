@@ -150,4 +150,17 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// One-time-per-DEVICE set-up guard for launchers (cudaFuncSetAttribute is a per-device property; a process-wide bool
+// would leave the second GPU of a multi-device process without the attribute).  The guarded body must be idempotent:
+// two host threads may both run it, which is harmless.
+struct DeviceOnce {
+  unsigned long long mask = 0;          // bit d = done on device d (devices >= 64: always redo)
+  int dev = 0;
+  bool needed() {
+    if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+    return dev >= 64 || !((__atomic_load_n(&mask, __ATOMIC_ACQUIRE) >> dev) & 1ull);
+  }
+  void done() { if (dev < 64) __atomic_fetch_or(&mask, 1ull << dev, __ATOMIC_RELEASE); }
+};
+
 }  // namespace tfswa

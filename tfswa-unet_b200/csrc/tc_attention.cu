@@ -638,14 +638,14 @@ extern "C" int tfswa_attn_tc_fwd(const tfswa_attn_args* a, void* scratch, int64_
     }
     return TFSWA_OK;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_once;
+  if (attr_once.needed()) {
     cudaError_t e1 = cudaFuncSetAttribute(tc_attn_axial_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<4>());
     cudaError_t e2 = cudaFuncSetAttribute(tc_attn_axial_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<8>());
     if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(tc_attn_axial_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<16>());
     cudaFuncSetAttribute(tc_attn_axial_kernel<16>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     if (e1 != cudaSuccess || e2 != cudaSuccess) { set_error("attn_tc: cudaFuncSetAttribute failed"); return TFSWA_ECUDA; }
-    attr_set = true;
+    attr_once.done();
   }
   if (D == 4) tc_attn_axial_kernel<4><<<grid, TA_NTHREADS, smem_bytes<4>(), st>>>(p);
   else if (D == 8) tc_attn_axial_kernel<8><<<grid, TA_NTHREADS, smem_bytes<8>(), st>>>(p);

@@ -560,15 +560,13 @@ int attn_axial_tma_bf16(const AttnParams& p, cudaStream_t st) {
   CUtensorMap tm;
   int rc = make_tmap_qkv(&tm, p);
   if (rc) return rc;
-  int dev = 0;
-  cudaGetDevice(&dev);
-  static bool attr_set[64] = {};
-  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+  static DeviceOnce attr_once;
+  if (attr_once.needed()) {
     cudaError_t e1 = cudaFuncSetAttribute(tc_attn_tma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<4>());
     cudaError_t e2 = cudaFuncSetAttribute(tc_attn_tma_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<8>());
     cudaError_t e3 = cudaFuncSetAttribute(tc_attn_tma_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<16>());
     if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) { set_error("attn_tc: cudaFuncSetAttribute failed"); return TFSWA_ECUDA; }
-    attr_set[dev] = true;
+    attr_once.done();
   }
   dim3 grid(((q_end + QTILE - 1) / QTILE) * (p.C / 16), rows, 1);
   if (D == 4) tc_attn_tma_kernel<4><<<grid, NTHREADS, smem_bytes<4>(), st>>>(tm, p);

@@ -267,11 +267,11 @@ extern "C" int tfswa_conv_tc_fwd(const tfswa_conv_args* a, const void* w_bf16, v
   size_t smem = (size_t)p.stages * stage_bytes;
   if (smem < (size_t)CV_BM * p.BN * 2) smem = (size_t)CV_BM * p.BN * 2;
   smem += 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_once;
+  if (attr_once.needed()) {
     cudaError_t e = cudaFuncSetAttribute(tc_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) { set_error("conv_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return TFSWA_ECUDA; }
-    attr_set = true;
+    attr_once.done();
   }
   dim3 grid((unsigned)ceil_div64(p.M, CV_BM), a->Cout / p.BN, zdim);
   tc_conv_kernel<<<grid, CV_THREADS, smem, (cudaStream_t)stream>>>(tmw, tmy, p);

@@ -242,15 +242,15 @@ static int launch_head(const tfswa_head_args* a, cudaStream_t st) {
   rc = make_tmap_bf16_3d(&tm_q, a->qkv, 9 * C, a->M, 1, a->ldq, 0, C, 128);
   if (rc) return rc;
   static int sms = 0;
-  static bool attr_set = false;
+  static DeviceOnce attr_once;
   const size_t smem = Cfg::BYTES + 1024;
-  if (!attr_set) {
+  if (attr_once.needed()) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaError_t e = cudaFuncSetAttribute(tc_head_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess || sms <= 0) { set_error("block_head_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return TFSWA_ECUDA; }
-    attr_set = true;
+    attr_once.done();
   }
   HeadParams p = {};
   p.bi = a->bi; p.bq = a->bq; p.x1 = (bf16*)a->x1; p.ld1 = a->ld1; p.M = a->M; p.eps = a->eps;

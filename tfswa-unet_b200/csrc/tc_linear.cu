@@ -321,11 +321,11 @@ extern "C" int tfswa_linear_tc_fwd(const tfswa_linear_args* a, const void* w_bf1
   size_t smem = (size_t)p.stages * stage_bytes;
   if (smem < (size_t)TC_BM * p.BN * 2) smem = (size_t)TC_BM * p.BN * 2;     // the output tile is staged in the same memory
   smem += 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_once;
+  if (attr_once.needed()) {
     cudaError_t e = cudaFuncSetAttribute(tc_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) { set_error("linear_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return TFSWA_ECUDA; }
-    attr_set = true;
+    attr_once.done();
   }
   dim3 grid((unsigned)ceil_div64(a->M, TC_BM), a->N / p.BN, a->batch);
   tc_linear_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(tmx, tmw, tmy, p);

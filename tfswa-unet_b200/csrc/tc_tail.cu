@@ -285,15 +285,15 @@ static int launch_tail(const tfswa_tail_args* a, cudaStream_t st) {
   rc = make_tmap_bf16_3d(&tm_out, a->out, C, a->M, nb, a->ldo, a->out_bs, C, 128);
   if (rc) return rc;
   static int sms = 0;
-  static bool attr_set = false;
+  static DeviceOnce attr_once;
   const size_t smem = Cfg::BYTES + 1024;
-  if (!attr_set) {
+  if (attr_once.needed()) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaError_t e = cudaFuncSetAttribute(tc_tail_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess || sms <= 0) { set_error("branch_tail_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return TFSWA_ECUDA; }
-    attr_set = true;
+    attr_once.done();
   }
   TailParams p = {};
   p.bp = a->bp; p.b1 = a->b1; p.b2 = a->b2; p.M = a->M; p.nb = nb; p.res_batched = res_batched ? 1 : 0; p.eps = a->eps;

@@ -318,15 +318,15 @@ int launch_tail128(const tfswa_tail_args* a, cudaStream_t st) {
   rc = make_tmap_bf16_3d(&tm_out, a->out, T8_C, a->M, nb, a->ldo, a->out_bs, 64, 128);
   if (rc) return rc;
   static int sms = 0;
-  static bool attr_set = false;
+  static DeviceOnce attr_once;
   const size_t smem = T8_BYTES + 1024;
-  if (!attr_set) {
+  if (attr_once.needed()) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaError_t e = cudaFuncSetAttribute(tc_tail128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess || sms <= 0) { set_error("branch_tail_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return TFSWA_ECUDA; }
-    attr_set = true;
+    attr_once.done();
   }
   Tail128Params p = {};
   p.bp = a->bp; p.b1 = a->b1; p.b2 = a->b2; p.res = (const bf16*)a->res; p.ldr = a->ldr;

@@ -222,13 +222,13 @@ int wgrad_mma_bf16(const tfswa_linear_args* a, const void* g, int64_t ldg, int64
   p.rows_per_cta = ((p.M + want - 1) / want + WM_MC - 1) / WM_MC * WM_MC;
   p.msplit = (int)((p.M + p.rows_per_cta - 1) / p.rows_per_cta);
   dim3 grid(kt, nt, a->batch * p.msplit);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_once;
+  if (attr_once.needed()) {
     if (cudaFuncSetAttribute(wgrad_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, WM_SMEM) != cudaSuccess) {
       set_error("wgrad_mma: cudaFuncSetAttribute failed");
       return TFSWA_ECUDA;
     }
-    attr_set = true;
+    attr_once.done();
   }
   wgrad_mma_kernel<false><<<grid, WM_THREADS, WM_SMEM, st>>>(p);
   return check_launch("linear_wgrad");
@@ -257,13 +257,13 @@ int conv_wgrad_mma_bf16(const tfswa_conv_args* a, const void* g, float* dw, floa
   p.rows_per_cta = ((p.M + want - 1) / want + WM_MC - 1) / WM_MC * WM_MC;
   p.msplit = (int)((p.M + p.rows_per_cta - 1) / p.rows_per_cta);
   dim3 grid(kt, nt, zdim * p.msplit);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_once;
+  if (attr_once.needed()) {
     if (cudaFuncSetAttribute(wgrad_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WM_SMEM) != cudaSuccess) {
       set_error("conv_wgrad_mma: cudaFuncSetAttribute failed");
       return TFSWA_ECUDA;
     }
-    attr_set = true;
+    attr_once.done();
   }
   wgrad_mma_kernel<true><<<grid, WM_THREADS, WM_SMEM, st>>>(p);
   return check_launch("conv_wgrad");

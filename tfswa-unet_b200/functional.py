@@ -55,9 +55,11 @@ class LinW:
 def _bf16_of(w: Tensor) -> Tensor:
     """bf16 copy of a prepared (cached, immutable) weight tensor.  The copy hangs on the tensor OBJECT (not on its
     address: the caching allocator hands a freed weight's address to the next rebuilt one) and is tied to its version."""
+    # inference tensors (prepared under torch.inference_mode()) have no version counter and cannot be modified in place
+    ver = -1 if torch.is_inference(w) else w._version
     hit = getattr(w, "_tfswa_bf16", None)
-    if hit is None or hit[0] != w._version:
-        hit = (w._version, w.detach().to(torch.bfloat16).contiguous())
+    if hit is None or hit[0] != ver:
+        hit = (ver, w.detach().to(torch.bfloat16).contiguous())
         w._tfswa_bf16 = hit
     return hit[1]
 

@@ -16,8 +16,12 @@ from . import _lib as L
 Tensor = torch.Tensor
 
 
+_DEV = None      # device of the tensors of the op being launched (set by _cuda at the top of every wrapper)
+
+
 def _stream() -> int:
-    return torch.cuda.current_stream().cuda_stream
+    """current stream of the TENSORS' device (not of the process-wide current device)"""
+    return torch.cuda.current_stream(_DEV).cuda_stream
 
 
 USE_TC_ATTENTION = True   # tcgen05 attention for axial geometries at head_dim 4/8 (bf16); False forces the SIMT kernel
@@ -53,6 +57,9 @@ def collect_timing():
 
 def _call(name: str, *args, tag: str = None, work: dict = None) -> None:
     global LAUNCHES
+    if _DEV is not None and _DEV.index is not None and _DEV.index != torch.cuda.current_device():
+        with torch.cuda.device(_DEV):       # a model on cuda:1 in a process whose current device is cuda:0
+            return _call(name, *args, tag=tag, work=work)
     fn = getattr(L.lib(), name)
     if _TIMING is not None:
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -75,9 +82,18 @@ def _dt(t: Tensor) -> int:
 
 
 def _cuda(*ts) -> None:
+    global _DEV
+    dev = None
     for t in ts:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise RuntimeError("tfswa_unet_b200 runs on CUDA (sm_100a) tensors only - there is no CPU fallback")
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise RuntimeError(f"tfswa_unet_b200: tensors on different devices ({dev} vs {t.device})")
+    _DEV = dev
 
 
 def _p(t: Optional[Tensor]):
@@ -260,10 +276,10 @@ def attention(qkv: Tensor, out: Tensor, B: int, H: int, W: int, C_: int, heads: 
     d = C_ // heads
     tc = USE_TC_ATTENTION and qkv.dtype == torch.bfloat16 and geom != L.GEOM_SWA and d in (4, 8, 16) and heads * d == C_ and C_ <= 128
     if tc:
-        # the tensor-core kernel works on 128-query x (128*d/16)-key tiles; short sequences that fill them badly
-        # (e.g. 129 tokens -> 25 % useful work) stay on the SIMT kernel, which has no padding
+        # the tensor-core kernels work on 128-query tiles (keys in tiles of 4*d, zero-filled by TMA); short sequences that
+        # fill the query tiles badly (e.g. 129 tokens -> 25 % useful work) stay on the SIMT kernel, which has no padding
         n = H if geom == L.GEOM_TSA else W
-        kt = 128 * d // 16
+        kt = 4 * d
         rem = n % 128
         nq = n - rem if (n >= 128 and 0 < rem < 32) else n       # a short remainder goes to the key-split warp kernel
         fill = (nq / (-(-nq // 128) * 128)) * (n / (-(-n // kt) * kt))

@@ -161,7 +161,8 @@ class FusedClipAdamW:
         self.exp_avg_sq = torch.zeros_like(arena.flat_p)
         self._sumsq = torch.zeros(1, dtype=torch.float64, device=arena.flat_p.device)
         self.grad_norm = torch.zeros(1, dtype=torch.float32, device=arena.flat_p.device)   # unclipped total norm, on device
-        self.step_count = 0
+        self.step_count = 0          # host count of step() calls
+        self._skipped = torch.zeros(1, dtype=torch.int64, device=arena.flat_p.device)   # device count of skipped (non-finite) updates
 
     def zero_grad(self) -> None:
         self.arena.zero_grad()
@@ -179,7 +180,7 @@ class FusedClipAdamW:
         ops._call("tfswa_adamw_clip_step", a.flat_p.data_ptr(), a.flat_g.data_ptr(), self.exp_avg.data_ptr(),
                   self.exp_avg_sq.data_ptr(), a.numel, self._sumsq.data_ptr(), self.grad_norm.data_ptr(), scale,
                   float(self.max_grad_norm or 0.0), float(self.lr if lr is None else lr), self.betas[0], self.betas[1], self.eps,
-                  self.weight_decay, self.step_count, st)
+                  self.weight_decay, self.step_count, self._skipped.data_ptr(), st)
         torch.autograd.graph.increment_version(a.params)     # prepared-weight caches key on the version counters
         return self.grad_norm
 
