@@ -150,7 +150,8 @@ def test_unet_config0_shape_vs_oracle(precision):
         if "ref" not in _CONFIG0_REF:
             with torch.no_grad():
                 _CONFIG0_REF["ref"] = O.unet_forward(x, sd, return_logits=True)
-        ref_masks, ref_logits = _CONFIG0_REF["ref"]
+        ref_logits = _CONFIG0_REF["ref"]
+        ref_masks = torch.sigmoid(ref_logits)
         with torch.no_grad():
             masks, logits = m(x.cuda(), return_logits=True)
         assert masks.shape == (2, 2, 256, 512) and masks.dtype == torch.float32
@@ -199,7 +200,8 @@ def test_gradient_checkpointing_over_tfswa_blocks():
         (l0, g0), (l1, g1) = res["plain"], res["checkpointed"]
         assert abs(float(l0) - float(l1)) <= 1e-5 * abs(float(l0)) + 1e-6
         for k in g0:
-            assert_close(f"ckpt.{k}", g1[k], g0[k], 1e-4, atol=1e-6)
+            # atol: a conv bias that feeds a train-mode BatchNorm has an analytically zero gradient (fp32 noise ~1e-6)
+            assert_close(f"ckpt.{k}", g1[k], g0[k], 1e-4, atol=3e-5)
     finally:
         T.set_precision("bf16")
 

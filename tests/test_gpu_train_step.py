@@ -61,6 +61,29 @@ def test_nonfinite_gradient_skips_update():
     assert not torch.isfinite(norm).item() and torch.equal(arena.flat_p, before) and float(opt.exp_avg.abs().max()) == 0.0
 
 
+def test_skipped_step_does_not_advance_the_optimizer_state():
+    """a skipped (non-finite) update must not advance the bias corrections - after one skipped and one good step
+    the parameters equal those of a stock AdamW that only saw the good step (GradScaler.step semantics, trainer.py:215)."""
+    from tfswa_unet_b200.train_step import FlatArena, FusedClipAdamW
+    model, ref = _mlp(), _mlp()
+    arena = FlatArena(model)
+    opt = FusedClipAdamW(arena, lr=3e-3, weight_decay=0.05, max_grad_norm=0.0)
+    ropt = torch.optim.AdamW(ref.parameters(), lr=3e-3, weight_decay=0.05)
+    x = torch.randn(16, 37, device="cuda")
+    tgt = torch.randn(16, 19, device="cuda")
+    opt.zero_grad()
+    arena.flat_g.fill_(float("nan"))
+    opt.step()                                                   # skipped
+    opt.zero_grad()
+    (model(x) - tgt).pow(2).mean().backward()
+    (ref(x) - tgt).pow(2).mean().backward()
+    opt.step()
+    ropt.step()
+    for p, q in zip(model.parameters(), ref.parameters()):
+        assert float((p.detach() - q.detach()).abs().max()) <= 1e-3 * 3e-3
+    assert float(opt.state_dict()["state"][0]["step"]) == 1.0 and opt.step_count == 2
+
+
 def test_c_abi_rejects_misaligned_and_bad_sizes():
     import ctypes as C
     from tfswa_unet_b200 import _lib
@@ -70,7 +93,7 @@ def test_c_abi_rejects_misaligned_and_bad_sizes():
     assert lib.tfswa_grad_sumsq(buf.data_ptr(), 6, s.data_ptr(), None) == -1
     assert lib.tfswa_grad_sumsq(buf.data_ptr() + 4, 8, s.data_ptr(), None) == -1
     assert lib.tfswa_adamw_clip_step(buf.data_ptr(), buf.data_ptr(), buf.data_ptr(), buf.data_ptr(), 64, s.data_ptr(), None,
-                                     1.0, 1.0, 1e-3, 0.9, 0.999, 1e-8, 0.01, 0, None) == -1          # step 0
+                                     1.0, 1.0, 1e-3, 0.9, 0.999, 1e-8, 0.01, 0, None, None) == -1    # step 0
     assert b"adamw" in lib.tfswa_last_error()
 
 

@@ -569,6 +569,13 @@ int attn_axial_tma_bf16(const AttnParams& p, cudaStream_t st) {
     attr_once.done();
   }
   dim3 grid(((q_end + QTILE - 1) / QTILE) * (p.C / 16), rows, 1);
+  static int pad = -1;                  // TFSWA_TMA_SMEM_PAD=<bytes>: occupancy experiment (e.g. 70000 -> one CTA per SM)
+  if (pad < 0) { const char* e = getenv("TFSWA_TMA_SMEM_PAD"); pad = e ? atoi(e) : 0; }
+  if (pad > 0) {
+    cudaFuncSetAttribute(tc_attn_tma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<4>() + pad);
+    tc_attn_tma_kernel<4><<<grid, NTHREADS, smem_bytes<4>() + pad, st>>>(tm, p);
+    return check_launch("attn_tc(tma, padded)");
+  }
   if (D == 4) tc_attn_tma_kernel<4><<<grid, NTHREADS, smem_bytes<4>(), st>>>(tm, p);
   else if (D == 8) tc_attn_tma_kernel<8><<<grid, NTHREADS, smem_bytes<8>(), st>>>(tm, p);
   else tc_attn_tma_kernel<16><<<grid, NTHREADS, smem_bytes<16>(), st>>>(tm, p);

@@ -188,9 +188,10 @@ class FusedClipAdamW:
     def state_dict(self) -> Dict:
         a = self.arena
         state = {}
+        eff_step = self.step_count - int(self._skipped.item())      # skipped (non-finite) updates do not count (GradScaler semantics)
         for i, (p, o) in enumerate(zip(a.params, a.offsets)):
             n = p.numel()
-            state[i] = {"step": torch.tensor(float(self.step_count)),
+            state[i] = {"step": torch.tensor(float(eff_step)),
                         "exp_avg": self.exp_avg[o:o + n].view(p.shape).clone(),
                         "exp_avg_sq": self.exp_avg_sq[o:o + n].view(p.shape).clone()}
         group = {"lr": self.lr, "betas": self.betas, "eps": self.eps, "weight_decay": self.weight_decay,
@@ -209,6 +210,7 @@ class FusedClipAdamW:
             self.exp_avg[o:o + n].copy_(s["exp_avg"].reshape(-1))
             self.exp_avg_sq[o:o + n].copy_(s["exp_avg_sq"].reshape(-1))
             self.step_count = int(s["step"])
+        self._skipped.zero_()
 
 
 def cosine_lr(step: int, t_max: int, base_lr: float, eta_min: float = 1e-6) -> float:
