@@ -17,20 +17,31 @@
 //     N-group being a constant all-ones tile that the descriptor's stride field (SBO) points at.  D_h = [P_h V | l_h..]:
 //     the row sum is accumulated by the tensor core from the same bf16-rounded P as the numerator; the last key block
 //     uses a second tile with zeros at the absent keys.
-// Softmax warps (0-7): S (TMEM) -> registers -> P (TMEM, bf16) with
+// Softmax warps (0-7; a query row is shared by two threads, 32 of a tile's 64 columns each): S (TMEM) -> registers -> P
+// (bf16, written back IN PLACE over the thread's own S columns, where the PV MMA reads it as its A operand) with
 //   * packed fp32 arithmetic (fma/add.f32x2 -> FFMA2/FADD2: one issue slot per two elements),
 //   * MUFU.EX2 for 11 of 16 element pairs and a degree-3 Cody-Waite polynomial on the FMA pipe for the other 5:
 //     tools/mufu_bench.cu measures 16.0 ex2/clk/SM for MUFU alone (4.64e12/s) and 21.8/clk/SM (6.3e12/s) for this mix
 //     at 4 warps per sub-partition,
 //   * no running maximum (row bound from the per-channel extrema of k, see tc_attention.cu); the polynomial's exponent
 //     clamp is compiled out for warps whose rows cannot reach 2^-120 (bound minus lower bound, checked once per CTA).
-// Warp 8 issues every MMA, warp 9 (one lane) every TMA; the key loop has no CTA-wide barrier:
-//   bar_full[s]  (tx)  stage s (128 keys: K lo|hi, V lo|hi = 8 KB) landed          TMA      -> issuer
-//   bar_empty[s] (1)   every MMA reading stage s has completed                     issuer commit -> producer
-//   bar_s   (1)  S(t) complete                                                     issuer commit -> softmax
-//   bar_a   (8)  S(t) pulled into registers by all softmax warps                   softmax  -> issuer (may issue S(t+1))
-//   bar_b   (8)  P(t) written to TMEM                                              softmax  -> issuer (may issue PV(t))
-//   bar_pv  (1)  PV(t) complete: P columns free                                    issuer commit -> softmax
+// TMEM (256 columns, two CTAs per SM): three S/P buffers of 64 columns (tile = HPQ heads x 64/HPQ keys) + O (64).
+// Warp 8 issues every MMA (one elected lane: `elect.sync`, so ptxas moves descriptors to uniform registers without
+// waterfall loops), warp 9 every TMA; the key loop has no CTA-wide barrier and is unrolled three-fold so that buffer
+// and barrier addresses are immediates:
+//   bar_full[s]  (tx)  stage s (128 keys: K lo|hi, V lo|hi = 8 KB) landed            TMA           -> issuer
+//   bar_empty[s] (1)   every MMA reading stage s has completed                       issuer commit -> producer
+//   bar_s[b]     (1)   S(t) complete in buffer b = t % 3                             issuer commit -> softmax
+//   bar_p[b]     (8)   P(t) written over S(t) by all softmax warps                   softmax       -> issuer
+//   bar_done     (1)   the last PV MMA has completed                                 issuer commit -> softmax (epilogue)
+// On bar_p[b] the issuer issues PV(t) and, back to back, S(t+3) into the same buffer: the tensor core executes one thread's
+// MMAs in issue order, so S(t+3) cannot overtake the MMA that reads the columns it overwrites, and a softmax warp can run
+// up to two tiles ahead of the slowest one.  What was measured and dropped on the way (tools/debug/tma_trace.py timelines,
+// ncu source pages, profiles/r2_attn_history.md): 128-column tiles with a separate P buffer and three barrier pairs
+// (10.4 ms per stage-1 TSA launch at B=8: the MMA issuer's ~270-instruction loop under `if (lane == 0)` was the critical
+// path), separate S- and PV-issuer warps (9.7), this design (9.4; round 1: 10.6); software-pipelined tcgen05.ld of the
+// next tile (11.0: one tile less slack between warps), 16 softmax warps x 16 columns at 56 registers (11.3: twice the
+// per-tile bookkeeping per exponential), MUFU only (10.4), polynomial share 1/2 (9.9) and 1/4 (9.5).
 // Replaces attention.py:70-85 (+ permutes :143,:162,:217,:236), bf16 activations.
 #include "attn_common.cuh"
 #include "sm100.cuh"
@@ -64,9 +75,6 @@ template <int D> __host__ __device__ constexpr int smem_bytes() { return tail_of
 
 #ifndef TFSWA_TMA_POLY_K
 #define TFSWA_TMA_POLY_K 3
-#endif
-#ifndef TFSWA_TMA_PIPE
-#define TFSWA_TMA_PIPE 0
 #endif
 constexpr int POLY_K = TFSWA_TMA_POLY_K;   // every POLY_K-th element PAIR takes the polynomial (0 = MUFU only); -D for A/B builds
 
@@ -379,20 +387,11 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_attn_tma_kernel(const __grid_c
         for (int i = 0; i < HPT; ++i) mc[i] = m[i] * c;
         const float mc0 = mc[0], mc1 = mc[HPT - 1];
         uint32_t sc[32], pk[16];
-#if TFSWA_TMA_PIPE >= 1
-        // software pipeline (variants 1, 2): S(t+1) is waited for / loaded before tile t's P is stored and published
-        mbar_wait(&bar_s[0], ph0); ph0 ^= 1;
-        tc_fence_after();
-        __syncwarp();
-        tmem_ld_x32(my_taddr, sc);
-#endif
         for (int t0 = 0; t0 < T; t0 += (int)NBUF) {
 #pragma unroll
           for (int b = 0; b < (int)NBUF; ++b) {      // compile-time buffer index: TMEM / barrier addresses are immediates
             const int t = t0 + b;
             if (t >= T) break;
-            const int b1 = (b + 1) % (int)NBUF;      // compile-time after unrolling
-#if TFSWA_TMA_PIPE == 0
             {
               uint32_t& ph = b == 0 ? ph0 : (b == 1 ? ph1 : ph2);
               mbar_wait(&bar_s[b], ph);
@@ -402,7 +401,6 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_attn_tma_kernel(const __grid_c
               __syncwarp();
               tmem_ld_x32(my_taddr + b * BUF_COLS, sc);
             }
-#endif
             tmem_ld_wait();
             if (tid == 0) TRACE(4, t);
             const bool tail = t == T - 1 && T * KT > N;   // last tile: absent keys score 0, which may exceed the bound
@@ -410,37 +408,9 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_attn_tma_kernel(const __grid_c
 #pragma unroll
               for (int i = 0; i < 32; ++i) sc[i] = __float_as_uint(fminf(__uint_as_float(sc[i]), m[D == 4 ? i / 16 : 0]));
             }
-#if TFSWA_TMA_PIPE == 0
             if (tail || wide) { softmax_half<true, 0>(sc, pk, c, mc0); softmax_half<true, 1>(sc, pk, c, mc1); }
             else { softmax_half<false, 0>(sc, pk, c, mc0); softmax_half<false, 1>(sc, pk, c, mc1); }
-#else
-            if (tail || wide) softmax_half<true, 0>(sc, pk, c, mc0); else softmax_half<false, 0>(sc, pk, c, mc0);
-#endif
-#if TFSWA_TMA_PIPE == 1
-            if (t + 1 < T) {
-              uint32_t& ph = b1 == 0 ? ph0 : (b1 == 1 ? ph1 : ph2);
-              mbar_wait(&bar_s[b1], ph);
-              ph ^= 1;
-              if (tid == 0) TRACE(0, t + 1);
-            }
-#endif
-#if TFSWA_TMA_PIPE != 0
-            if (tail || wide) softmax_half<true, 1>(sc, pk, c, mc1); else softmax_half<false, 1>(sc, pk, c, mc1);
-#endif
             if (tid == 0) TRACE(5, t);
-#if TFSWA_TMA_PIPE >= 1
-            if (t + 1 < T) {
-#if TFSWA_TMA_PIPE == 2
-              uint32_t& ph = b1 == 0 ? ph0 : (b1 == 1 ? ph1 : ph2);
-              mbar_wait(&bar_s[b1], ph);
-              ph ^= 1;
-              if (tid == 0) TRACE(0, t + 1);
-#endif
-              tc_fence_after();
-              __syncwarp();
-              tmem_ld_x32(my_taddr + b1 * BUF_COLS, sc);            // S(t+1): in flight under the store / arrive below
-            }
-#endif
             tmem_st_x16(my_taddr + b * BUF_COLS, pk);  // score pair (2i, 2i+1) -> 32-bit cell i of my own columns
             tmem_st_wait();
             if (tid == 0) TRACE(6, t);
@@ -530,6 +500,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_attn_tma_kernel(const __grid_c
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);
 }
+
 
 }  // namespace tma_attn
 
