@@ -21,6 +21,22 @@ from .parallel import shard_range
 Tensor = torch.Tensor
 
 
+def balanced_batches(lo: int, hi: int, max_batch: int):
+    """[lo, hi) in the fewest batches of at most ``max_batch`` items, sizes as equal as possible: 17 segments -> 6 + 6 + 5,
+    not 8 + 8 + 1 (a batch-of-1 forward costs 17 ms against 14.6 ms per segment at batch 8: pure tail latency)."""
+    n = hi - lo
+    if n <= 0:
+        return []
+    nb = -(-n // max_batch)
+    base, extra = divmod(n, nb)
+    out, s = [], lo
+    for i in range(nb):
+        e = s + base + (1 if i < extra else 0)
+        out.append((s, e))
+        s = e
+    return out
+
+
 class ShardedSeparator:
     def __init__(self, model: Callable[[Tensor], Tensor], n_fft: int = 2048, hop_length: int = 512, sample_rate: int = 44100,
                  segment_length: float = 6.0, overlap: float = 0.25, batch: int = 8, normalize: bool = True,
@@ -74,8 +90,8 @@ class ShardedSeparator:
         win_seg = torch.hann_window(S, device=mono.device)                          # inference.py:227-237
         n_st = len(stem_names)
         acc = torch.zeros((n_st + 1, total), device=mono.device)                   # stems + window-weight row
-        for b0 in range(lo, hi, self.batch):
-            idx = starts[b0:min(b0 + self.batch, hi)]
+        for b0, b1 in balanced_batches(lo, hi, self.batch):
+            idx = starts[b0:b1]
             seg = torch.stack([torch.nn.functional.pad(mono[s:s + S], (0, max(0, S - (total - s)))) for s in idx])
             spec, masks = self._masks(seg)
             # The reference reconstructs without a target length (inference.py:148-150 -> stft_processor.py:136-184): a segment

@@ -41,6 +41,7 @@ class FlatArena:
     def __init__(self, model: nn.Module, group: Optional[dist.ProcessGroup] = None, bucket_bytes: int = 16 << 20):
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.skip_exchange = False               # measurement only: run the step without the gradient all-reduce
         self.params: List[nn.Parameter] = [p for p in model.parameters() if p.requires_grad]
         if not self.params:
             raise ValueError("FlatArena: the model has no trainable parameters")
@@ -117,6 +118,9 @@ class FlatArena:
     def _launch(self, b: int) -> None:
         if self.world == 1 or self._work[b] is not None:
             return
+        if self.skip_exchange:                   # measurement knob (tools/train_bench.py --measure-exposed): no collective
+            self._work[b] = _NoWork()
+            return
         lo, hi, members = self.buckets[b]
         for i in members:                        # a hook fired on a gradient outside the arena: bring it in first
             p = self.params[i]
@@ -145,6 +149,11 @@ class FlatArena:
     def remove(self) -> None:
         for h in self._hooks:
             h.remove()
+
+
+class _NoWork:
+    def wait(self) -> None:
+        pass
 
 
 class FusedClipAdamW:
@@ -241,11 +250,15 @@ class TrainStep:
         self.arena = FlatArena(model, group, bucket_bytes)
         self.optim = FusedClipAdamW(self.arena, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, max_grad_norm=max_grad_norm)
 
-    def __call__(self, model_input: Tensor, mixture_mag: Tensor, target_mags: Sequence[Tensor], lr: Optional[float] = None):
-        """-> (loss, grad_norm) as device tensors; no host synchronisation."""
+    def __call__(self, model_input: Tensor, mixture_mag: Tensor, target_mags: Sequence[Tensor], lr: Optional[float] = None,
+                 extra_loss=None):
+        """-> (loss, grad_norm) as device tensors; no host synchronisation.  ``extra_loss(model_output) -> scalar`` (optional)
+        is added to the trainer's L1 term, e.g. the weighted multi-resolution STFT term of ``losses.py``."""
         self.optim.zero_grad()
         out = self.model(model_input)
         loss = masked_magnitude_l1(out, mixture_mag, target_mags)
+        if extra_loss is not None:
+            loss = loss + extra_loss(out)
         loss.backward()
         norm = self.optim.step(lr)
         return loss.detach(), norm

@@ -10,7 +10,11 @@ One step = what src/training/trainer.py:129-219 does per batch: STFT of the mixt
 (torch.stft / cuFFT: either side of the path), model forward, masked-magnitude L1, backward, clip_grad_norm_(1.0),
 AdamW - through ``tfswa_unet_b200.train_step.TrainStep`` (flat arena, bucketed in-place NCCL all-reduce overlapped with
 backward, fused norm+clip+AdamW kernels, no host sync inside the step).  The MR-STFT term of the BASELINE wording is
-not part of the reference trainer's loss (scripts/train.py:247 use_mrstft=False) and is not added here.
+not part of the reference trainer's loss (scripts/train.py:247 use_mrstft=False); ``--mrstft`` adds it as
+SourceSeparationLoss words it (losses.py:235-283: L1 + 0.5 * MR-STFT averaged over stems) on the predicted audio
+ISTFT(mixture spectrogram x sigmoid(|mask|)) - the ISTFT the reference trainer never performs.
+``--measure-exposed`` times the same steps a second time with the gradient exchange switched off: the difference is the
+part of the all-reduce that backward did not hide.
 Timing: CUDA events around K steps after W warm-up steps, barrier + synchronize on both sides, max over ranks.
 Prints one JSON line on rank 0.
 """
@@ -46,6 +50,8 @@ def main():
     ap.add_argument("--precision", default="bf16")
     ap.add_argument("--bucket-mb", type=int, default=16)
     ap.add_argument("--profile", action="store_true")
+    ap.add_argument("--mrstft", action="store_true")
+    ap.add_argument("--measure-exposed", action="store_true")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -61,33 +67,60 @@ def main():
     mixtures = 0.1 * torch.randn(args.batch, 2, SAMPLES, device="cuda", generator=g)
     targets = [0.1 * torch.randn(args.batch, 2, SAMPLES, device="cuda", generator=g) for _ in range(2)]
 
+    from tfswa_unet_b200.losses import mrstft_loss
+    window = torch.hann_window(N_FFT, device="cuda")
+
     def one_step():
         with torch.no_grad():
             spec = stft(mixtures)
             x = torch.cat([spec.real, spec.imag], dim=1)                      # to_model_input, stft_processor.py:186-204
             mix_mag = spec.mean(dim=1).abs()                                  # trainer.py:141-142
             tg = [stft(t).mean(dim=1).abs() for t in targets]                 # trainer.py:145-149
-        return step(x, mix_mag, tg)
+        extra = None
+        if args.mrstft:
+            def extra(out):                                                    # losses.py:235-283, mrstft_weight 0.5
+                B = out.shape[0]
+                acc = 0.0
+                for i, t in enumerate(targets):
+                    re, im = out[:, 2 * i].float(), out[:, 2 * i + 1].float()
+                    mask = torch.sigmoid(torch.sqrt(re * re + im * im + 1e-8))            # trainer.py:182-183
+                    pred = torch.istft((spec * mask[:, None]).reshape(B * 2, *spec.shape[-2:]), N_FFT, HOP, N_FFT, window,
+                                       center=True, normalized=False, onesided=True, length=SAMPLES).reshape(B, 2, SAMPLES)
+                    acc = acc + mrstft_loss(pred, t)
+                return 0.5 * acc / len(targets)
+        return step(x, mix_mag, tg, extra_loss=extra)
+
+    def timed(n):
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            out = one_step()
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / n], device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dist.barrier()
+        return float(t), out
 
     for _ in range(args.warmup):
         loss, norm = one_step()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
     ops.reset_launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        loss, norm = one_step()
-    e1.record()
-    torch.cuda.synchronize()
+    ms, (loss, norm) = timed(args.steps)
     launches = ops.reset_launch_count()
-    ms = torch.tensor([e0.elapsed_time(e1) / args.steps], device="cuda")
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        dist.barrier()
-    ms = float(ms)
+    exposed = None
+    if args.measure_exposed and world > 1:
+        # the same steps without the collective (replicas drift apart afterwards: this is the last thing the script does)
+        step.arena.skip_exchange = True
+        one_step()
+        ms_no, _ = timed(args.steps)
+        step.arena.skip_exchange = False
+        exposed = {"ms_per_step_without_allreduce": ms_no, "exposed_allreduce_ms": ms - ms_no,
+                   "exposed_frac_of_step": (ms - ms_no) / ms, "allreduce_bytes": step.arena.numel * 4}
     if args.profile and rank == 0:
         from torch.profiler import profile, ProfilerActivity
         with profile(activities=[ProfilerActivity.CUDA]) as prof:
@@ -105,6 +138,8 @@ def main():
                                    "clip 1.0, AdamW", "batch_per_gpu": args.batch, "bucket_mb": args.bucket_mb,
                        "parallelism": f"dp{world} (batch-sharded replicas, NCCL gradient all-reduce overlapped with backward)"},
             "model_tflop_per_step_per_gpu": 3 * fwd_tflop, "achieved_model_tflops_per_gpu": 3 * fwd_tflop / (ms / 1e3),
+            "loss_terms": "L1 masked magnitude + 0.5 * MR-STFT(2048/1024/512) on ISTFT audio" if args.mrstft else "L1 masked magnitude (the reference trainer's loss)",
+            "allreduce": exposed,
             "loss": float(loss), "grad_norm": float(norm), "gpu_launches": launches,
             "peak_mem_gib": torch.cuda.max_memory_allocated() / 2 ** 30}))
     if world > 1:
