@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(CV_THREADS) tc_conv_kernel(const __grid_consta
   const uint32_t tmem = s_tmem;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       // ---------------- weight tiles by TMA ----------------
       for (int kb = 0; kb < p.KB; ++kb) {
         const int s = kb % p.stages;
@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(CV_THREADS) tc_conv_kernel(const __grid_consta
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       // ---------------- MMA issuer ----------------
       const uint32_t idesc = umma_idesc_bf16(CV_BM, p.BN);
       const uint32_t row_bytes = p.BK * 2;

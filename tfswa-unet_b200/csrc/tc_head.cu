@@ -87,7 +87,7 @@ tc_head_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
   const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
   const int cta = blockIdx.x, ncta = gridDim.x;
 
-  if (tid == 0) {
+  if (warp == 0 && elect_one()) {
     mbar_arrive_expect_tx(&bar_w, Cfg::W_BYTES);
     tma_load_3d(sm + Cfg::WI, &tm_wi, &bar_w, 0, 0, 0);
 #pragma unroll
@@ -104,7 +104,7 @@ tc_head_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
   for (int tile = cta; tile < p.tiles; tile += ncta, ++it) {
     const int buf = it & 1;
     const int64_t m = (int64_t)tile * 128 + r;
-    if (tid == 0) {
+    if (warp == 0 && elect_one()) {
       mbar_wait(&bar_ld[buf], (it >> 1) & 1);
       const int nxt = tile + ncta;
       if (nxt < p.tiles) {
@@ -178,7 +178,7 @@ tc_head_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
       for (int k = 0; k < C / 16; ++k) umma_bf16_ss(tmem + Cfg::Q_COL + (j & 1) * CH, ad + 2 * k, bd + 2 * k, idesc_q, k ? 1u : 0u);
       umma_commit(&bar_q[j & 1]);
     };
-    if (tid == 0) { tc_fence_after(); issue_chunk(0); issue_chunk(1); }
+    if (warp == 0 && elect_one()) { tc_fence_after(); issue_chunk(0); issue_chunk(1); }
     __syncwarp();
 
 #pragma unroll
@@ -186,7 +186,7 @@ tc_head_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
       if ((j & 1) == 0) { mbar_wait(&bar_q[0], n_q0 & 1); ++n_q0; } else { mbar_wait(&bar_q[1], n_q1 & 1); ++n_q1; }
       tc_fence_after();
       const int slot = Cfg::NSTG == 2 ? ((it * 3 + j) & 1) : 0;
-      if (tid == 0) {                                   // the staging slot's previous store must have been read out
+      if (warp == 0 && elect_one()) {                                   // the staging slot's previous store must have been read out
         if (Cfg::NSTG == 2) { if (nstore >= 2) tma_store_wait_read_h<1>(); }
         else { if (nstore >= 1) tma_store_wait_read_h<0>(); }
       }
@@ -213,7 +213,7 @@ tc_head_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
       fence_async_smem();
       tc_fence_before();
       __syncthreads();
-      if (tid == 0) {
+      if (warp == 0 && elect_one()) {
 #pragma unroll
         for (int b = 0; b < 3; ++b) tma_store_3d(&tm_q, stg + b * Cfg::TILE, j * CH + b * C, tile * 128, 0);
         tma_store_commit_h();
@@ -223,7 +223,7 @@ tc_head_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
       __syncwarp();
     }
   }
-  if (tid == 0) tma_store_wait_all_h();
+  if (warp == 0 && elect_one()) tma_store_wait_all_h();
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, Cfg::TMEM_COLS);

@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(TC_THREADS) tc_linear_kernel(const __grid_cons
   const uint32_t tmem = s_tmem;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       // ---------------- TMA producer ----------------
       for (int kb = 0; kb < p.KB; ++kb) {
         const int s = kb % p.stages;
@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(TC_THREADS) tc_linear_kernel(const __grid_cons
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       // ---------------- MMA issuer ----------------
       const uint32_t idesc = umma_idesc_bf16(TC_BM, p.BN);
       const uint32_t row_bytes = p.BK * 2;

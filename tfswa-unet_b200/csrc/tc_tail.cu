@@ -97,7 +97,7 @@ tc_tail_kernel(const __grid_constant__ CUtensorMap tm_att, const __grid_constant
   const uint32_t tmem = s_tmem;
   const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
 
-  if (tid == 0) {
+  if (warp == 0 && elect_one()) {
     mbar_arrive_expect_tx(&bar_w, Cfg::W_BYTES);
     tma_load_3d(sm + Cfg::WP, &tm_wp, &bar_w, 0, 0, z);
     tma_load_3d(sm + Cfg::W1, &tm_w1, &bar_w, 0, 0, z);
@@ -116,7 +116,7 @@ tc_tail_kernel(const __grid_constant__ CUtensorMap tm_att, const __grid_constant
   for (int tile = cta; tile < p.tiles; tile += ncta, ++it) {
     const int buf = it & 1;
     mbar_wait(&bar_ld[buf], (it >> 1) & 1);              // att + x1 tiles landed (every thread reads the residual tile)
-    if (tid == 0) {
+    if (warp == 0 && elect_one()) {
       const int nxt = tile + ncta;
       if (nxt < p.tiles) {                               // prefetch the next tile into the other buffer (its readers are long done)
         mbar_arrive_expect_tx(&bar_ld[buf ^ 1], 2 * Cfg::TILE);
@@ -185,7 +185,7 @@ tc_tail_kernel(const __grid_constant__ CUtensorMap tm_att, const __grid_constant
     __syncthreads();
 
     // ---------------- MMA2: hidden = LN_hat(y) W1'^T ----------------
-    if (tid == 0) {
+    if (warp == 0 && elect_one()) {
       tc_fence_after();
       const uint64_t ad = umma_smem_desc(base + Cfg::A1, ROWB), bd = umma_smem_desc(base + Cfg::W1, ROWB);
 #pragma unroll
@@ -221,7 +221,7 @@ tc_tail_kernel(const __grid_constant__ CUtensorMap tm_att, const __grid_constant
     __syncthreads();
 
     // ---------------- MMA3: z_acc = hidden W2^T (into the y accumulator columns, long since consumed) ----------------
-    if (tid == 0) {
+    if (warp == 0 && elect_one()) {
       tc_fence_after();
 #pragma unroll
       for (int kb = 0; kb < Cfg::KB2; ++kb) {
@@ -254,13 +254,13 @@ tc_tail_kernel(const __grid_constant__ CUtensorMap tm_att, const __grid_constant
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
-    if (tid == 0) {
+    if (warp == 0 && elect_one()) {
       tma_store_3d(&tm_out, sm + Cfg::A1, 0, tile * 128, z);     // rows beyond M are clipped by the tensor map
       tma_store_commit();
     }
     __syncwarp();
   }
-  if (tid == 0) tma_store_wait_all();
+  if (warp == 0 && elect_one()) tma_store_wait_all();
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, Cfg::TMEM_COLS);

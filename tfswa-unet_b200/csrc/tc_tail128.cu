@@ -84,7 +84,7 @@ tc_tail128_kernel(const __grid_constant__ CUtensorMap tm_att, const __grid_const
   const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
 
   if (driver) {
-    if (lane == 0) {
+    if (elect_one()) {
       // ---- the weight ring.  Pair G (global counter) lives in slot G % 3; q = G % 10 selects its contents. ----
       auto produce = [&](int G) {
         const int slot = G % 3, q = G % T8_PAIRS;
