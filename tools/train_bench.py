@@ -51,6 +51,7 @@ def main():
     ap.add_argument("--bucket-mb", type=int, default=16)
     ap.add_argument("--profile", action="store_true")
     ap.add_argument("--mrstft", action="store_true")
+    ap.add_argument("--recompute", default="none", choices=["none", "blocks", "stage1"])
     ap.add_argument("--measure-exposed", action="store_true")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -62,7 +63,7 @@ def main():
     T.set_precision(args.precision)
     torch.manual_seed(0)                                     # identical initial weights on every rank
     model = T.TFSWAUNet(4, 4, [2, 2, 6, 2], [32, 64, 128, 256], 8, 4, 8).train().cuda()
-    step = TrainStep(model, lr=1e-3, weight_decay=1e-2, max_grad_norm=1.0, bucket_bytes=args.bucket_mb << 20)
+    step = TrainStep(model, lr=1e-3, weight_decay=1e-2, max_grad_norm=1.0, bucket_bytes=args.bucket_mb << 20, recompute=args.recompute)
     g = torch.Generator(device="cuda").manual_seed(1234 + rank)
     mixtures = 0.1 * torch.randn(args.batch, 2, SAMPLES, device="cuda", generator=g)
     targets = [0.1 * torch.randn(args.batch, 2, SAMPLES, device="cuda", generator=g) for _ in range(2)]
@@ -139,7 +140,7 @@ def main():
                        "parallelism": f"dp{world} (batch-sharded replicas, NCCL gradient all-reduce overlapped with backward)"},
             "model_tflop_per_step_per_gpu": 3 * fwd_tflop, "achieved_model_tflops_per_gpu": 3 * fwd_tflop / (ms / 1e3),
             "loss_terms": "L1 masked magnitude + 0.5 * MR-STFT(2048/1024/512) on ISTFT audio" if args.mrstft else "L1 masked magnitude (the reference trainer's loss)",
-            "allreduce": exposed,
+            "allreduce": exposed, "recompute": args.recompute,
             "loss": float(loss), "grad_norm": float(norm), "gpu_launches": launches,
             "peak_mem_gib": torch.cuda.max_memory_allocated() / 2 ** 30}))
     if world > 1:
