@@ -37,8 +37,10 @@ struct AttnParams {
 int attn_simt_axial_bf16(const AttnParams& p, cudaStream_t st);
 // register-resident warp-MMA flash kernel on queries [0, q_end) (attention_axial_mma.cu); needs p.kext
 int attn_axial_mma_bf16(const AttnParams& p, cudaStream_t st);
-// tcgen05 + TMA flash kernel on queries [0, q_end) (tc_attn_tma.cu); needs p.kext
-int attn_axial_tma_bf16(const AttnParams& p, cudaStream_t st);
+// tcgen05 + TMA flash kernel on queries [0, q_end) (tc_attn_tma.cu); needs p.kext and a work buffer of
+// attn_axial_tma_work_bytes(p) bytes (redo list of the exact pass)
+int64_t attn_axial_tma_work_bytes(const AttnParams& p);
+int attn_axial_tma_bf16(const AttnParams& p, void* work, cudaStream_t st);
 // bf16 axial attention backward on warp-level MMAs (attention_bwd_mma.cu); returns 1 when the shape is not covered
 int attn_bwd_mma_bf16(const AttnParams& p, cudaStream_t st);
 

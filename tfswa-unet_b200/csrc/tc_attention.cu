@@ -582,10 +582,17 @@ __global__ void __launch_bounds__(TA_NTHREADS, 2) tc_attn_axial_kernel(const Att
 
 using namespace tfswa;
 
-extern "C" int64_t tfswa_attn_tc_scratch_bytes(const tfswa_attn_args* a) {
-  if (!a) return 0;
+static int64_t kext_bytes(const tfswa_attn_args* a) {
   const int64_t rows = a->geom == TFSWA_GEOM_TSA ? (int64_t)a->B * a->W : (int64_t)a->B * a->H;
-  return rows * 2 * a->C * (int64_t)sizeof(float);
+  return (rows * 2 * a->C * (int64_t)sizeof(float) + 255) / 256 * 256;
+}
+
+// [per-sequence k extrema] [work space of the TMA kernel: redo count, flags, list]
+extern "C" int64_t tfswa_attn_tc_scratch_bytes(const tfswa_attn_args* a) {
+  if (!a || a->C <= 0) return 0;
+  AttnParams p = {};
+  p.B = a->B; p.H = a->H; p.W = a->W; p.C = a->C; p.geom = a->geom;
+  return kext_bytes(a) + attn_axial_tma_work_bytes(p);
 }
 
 extern "C" int tfswa_attn_tc_fwd(const tfswa_attn_args* a, void* scratch, int64_t scratch_bytes, void* stream) {
@@ -618,17 +625,18 @@ extern "C" int tfswa_attn_tc_fwd(const tfswa_attn_args* a, void* scratch, int64_
   // TFSWA_AXIAL_KERNEL=tma|umma|mma selects the main kernel (A/B): "tma" = tcgen05 + TMEM with TMA-fed operands
   // (tc_attn_tma.cu), "umma" = round 1's thread-staged tcgen05 kernel (this file), "mma" = register-resident warp-level
   // MMAs (attention_axial_mma.cu).
-  // Measured on B200 (tools/attn_bench.py, C3 stage shapes, B=8, TSA / FSA ms): head_dim 4: tma 9.42 / 5.35, umma 10.58 / 6.26;
-  // head_dim 8: tma 1.40 / 1.13, mma 1.46 / 1.01; head_dim 16: tma 0.39 / 0.41, mma 0.36 / 0.31 -> default below.
+  // Measured on B200 (tools/attn_bench.py, C3 stage shapes, B=8, TSA / FSA ms per launch): head_dim 4: tma 9.49 / 5.20, umma
+  // (round 1) 10.58 / 6.26; head_dim 8: tma 1.34 / 0.99, mma 1.46 / 1.02; head_dim 16: tma 0.30 / 0.31, mma 0.37 / 0.33
+  // -> the TMA-fed tcgen05 kernel is the default at every head_dim.
   static int force = -1;                              // 0 = default choice, 1 = umma, 2 = mma, 3 = tma
   if (force < 0) { const char* e = getenv("TFSWA_AXIAL_KERNEL"); force = !e ? 0 : (e[0] == 'm' ? 2 : (e[0] == 't' ? 3 : 1)); }
-  const bool use_mma = force == 2 || (force == 0 && (D == 16 || (D == 8 && N < 384)));
+  const bool use_mma = force == 2;
   if (use_mma && a->heads % 8 == 0) {                // 16-row granularity: no separate remainder pass
     AttnParams pm = p; pm.q_begin = 0; pm.q_end = 0;
     return attn_axial_mma_bf16(pm, st);
   }
   if (force == 3 || force == 0) {
-    int rc = attn_axial_tma_bf16(p, st);
+    int rc = attn_axial_tma_bf16(p, (char*)scratch + kext_bytes(a), st);
     if (rc) return rc;
     if (q_tc < N) {                                  // ragged remainder (< 32 queries per sequence), see below
       AttnParams ps = p;

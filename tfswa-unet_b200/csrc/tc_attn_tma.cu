@@ -55,7 +55,7 @@ namespace tma_attn {
 
 #ifdef TFSWA_TMA_TRACE
 __device__ long long g_trace[8][128];   // debug: clock64 per (event, tile) of one CTA
-#define TRACE(ev, t) do { if (blockIdx.x == 0 && blockIdx.y == 1000 && (t) < 128) g_trace[ev][t] = clock64(); } while (0)
+#define TRACE(ev, t) do { if (blockIdx.x == 0 && (t) < 128) g_trace[ev][t] = clock64(); } while (0)
 #else
 #define TRACE(ev, t) do { } while (0)
 #endif
@@ -136,23 +136,42 @@ __device__ __forceinline__ void softmax_half(const uint32_t (&sc)[32], uint32_t 
 constexpr uint32_t NBUF = 3, BUF_COLS = 64;
 constexpr uint32_t O_COL2 = NBUF * BUF_COLS;          // 192: O accumulators, HPQ x 16 columns (d = 16: 32)
 
+// PERSISTENT CTAs.  A work item is (sequence, 128-query tile, 16-channel quad).  A launch-per-item version of this kernel
+// measured 10.9 k cycles of fixed cost per CTA next to 1.1 k cycles per key tile (TSA 65 tiles, FSA 33: 13 % / 23 % of the
+// time; stage 3 has 4-5 tiles per item): TMEM allocation, barrier init, the constant operand tiles, the first TMA and MMA
+// latencies.  Here 2 x #SM CTAs loop over the items (item = blockIdx.x + k * gridDim.x, so CTAs that run together share a
+// sequence's K|V in L2), the set-up is done once, the TMA warp runs up to four stages ahead ACROSS item boundaries, and
+// the roles only meet on mbarriers:
+//   bar_q (8)  the item's masked Q copies are in shared memory                      softmax -> issuer
+// Rows whose bound was too loose (denominator underflow) are not repeated in place - that would need a CTA-wide decision
+// per item - but appended to a device list that a second, normally empty launch of the same kernel processes with exact
+// row maxima (`exact`: pass 0 streams S and reduces the maxima, pass 1 is the normal one).
+struct Items {
+  int n;                 // implicit item range [0, n) ...
+  const int* list;       // ... or (list != nullptr) the *count entries of a device list
+  const int* count;
+  int nqt, nquads;       // item -> (row, query tile, quad): item = (row * nqt + qt) * nquads + quad
+  int* redo_count;       // non-exact launches: items with an underflowed row are appended here (flag = first writer wins)
+  int* redo_flag;
+  int* redo_list;
+  int exact;
+};
+
 template <int D>
-__global__ void __launch_bounds__(NTHREADS, 2) tc_attn_tma_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
+__global__ void __launch_bounds__(NTHREADS, 2) tc_attn_tma_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p, const Items items) {
   constexpr int HPQ = 16 / D;            // heads per CTA (one 16-channel "quad")
   constexpr int KT = 64 / HPQ;           // keys per S tile and head: HPQ heads x KT keys = 64 TMEM columns (16 / 32 / 64)
   constexpr int TPS = SKEYS / KT;        // S tiles per shared-memory stage (8 / 4 / 2)
   constexpr int HPT = D == 4 ? 2 : 1;    // head slots per softmax thread (32 columns = 2 heads x 16 keys at d = 4)
+  constexpr int NCH = HPT * D;           // channels of my head slots (8 / 8 / 16), starting at channel c0 of the quad
   constexpr int Q_OFF = 0, ST_OFF = stage_off<D>(), ONES_OFF = ones_off<D>(), TAIL_OFF = tail_off<D>();
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ __align__(8) uint64_t bar_full[NSTAGE], bar_empty[NSTAGE], bar_s[NBUF], bar_p[NBUF], bar_done;
+  __shared__ __align__(8) uint64_t bar_full[NSTAGE], bar_empty[NSTAGE], bar_s[NBUF], bar_p[NBUF], bar_done, bar_q;
   __shared__ uint32_t s_tmem;
-  __shared__ float s_kext[2][16];        // per channel of the quad: min / max of k over the whole sequence
   __shared__ float s_xch[HPQ == 1 ? 256 : 1];   // d = 16, exact pass: the two threads of a row exchange their maxima
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const bool softmax = warp < 8, issuer = warp == 8, producer = warp == 9;
-  const int nquads = p.C / 16;
-  const int row = blockIdx.y, q0 = (blockIdx.x / nquads) * QTILE, quad = blockIdx.x % nquads;
+  const bool issuer = warp == 8, producer = warp == 9;       // warps 0-7: softmax
   const bool tsa = p.geom == TFSWA_GEOM_TSA;
   const int N = tsa ? p.H : p.W;
   const int quarter = warp & 3, half = (warp >> 2) & 1;
@@ -161,21 +180,17 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_attn_tma_kernel(const __grid_c
   const int T = (N + KT - 1) / KT;                   // S tiles
   const int NST = (N + SKEYS - 1) / SKEYS;           // stages (TMA loads) per pass
   const int tail_keys = N - (NST - 1) * SKEYS;       // valid keys in the last stage (1..128)
-  // sequence `row` -> tensor coordinates: TSA row = b * W + w (keys along h), FSA row = b * H + h (keys along w)
-  const int cb = tsa ? row / p.W : row / p.H;
-  const int cf = tsa ? row - cb * p.W : row - cb * p.H;
-  int64_t tok_base, tok_stride;
-  if (tsa) { tok_base = (int64_t)cb * p.H * p.W + cf; tok_stride = p.W; }
-  else { tok_base = (int64_t)row * p.W; tok_stride = 1; }
+  const bool exact = items.exact != 0;
+  const int n_items = items.list ? *items.count : items.n;
 
-  // ---- setup ----
+  // ---- set-up, once per CTA ----
   if (warp == 0) {
     if (lane == 0) {
 #pragma unroll
       for (int i = 0; i < NSTAGE; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 1); }
 #pragma unroll
       for (int i = 0; i < (int)NBUF; ++i) { mbar_init(&bar_s[i], 1); mbar_init(&bar_p[i], 8); }
-      mbar_init(&bar_done, 1);
+      mbar_init(&bar_done, 1); mbar_init(&bar_q, 8);
       fence_barrier_init();
     }
     __syncwarp();
@@ -188,128 +203,93 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_attn_tma_kernel(const __grid_c
     const uint32_t v = ((i & (SKEYS - 1)) < tail_keys) ? 0x3F803F80u : 0u;
     reinterpret_cast<uint4*>(smem + TAIL_OFF)[i] = make_uint4(v, v, v, v);
   }
-  bool q_valid = false;
-  int64_t q_tok = 0;
-  uint4 qa = make_uint4(0, 0, 0, 0), qb = qa;        // my row's 16 q channels
-  if (softmax) {
-    if (q0 + r < (p.q_end ? p.q_end : N)) { q_tok = tok_base + (int64_t)(q0 + r) * tok_stride; q_valid = true; }
-    if (q_valid) {
-      const uint4* src = reinterpret_cast<const uint4*>((const bf16*)p.qkv + q_tok * p.ldq + quad * 16);
-      qa = src[0]; qb = src[1];
-    }
-    // masked copies of Q (K-major, 8-row x 16-byte core matrices): copy h keeps head h's channels.  The two threads of a
-    // row split the copies.
-    const uint32_t w[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};   // 2 channels per word
-#pragma unroll
-    for (int h = 0; h < HPQ; ++h) {                  // compile-time h: the masks are immediates, no local array
-      if ((HPQ >= 2 ? h / (HPQ / 2) : 0) != half) continue;
-      uint32_t m8[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) m8[i] = (2 * i >= D * h && 2 * i < D * h + D) ? w[i] : 0u;
-      uint8_t* dst = smem + Q_OFF + h * 4096 + (r >> 3) * 256 + (r & 7) * 16;
-      *reinterpret_cast<uint4*>(dst) = make_uint4(m8[0], m8[1], m8[2], m8[3]);
-      *reinterpret_cast<uint4*>(dst + 128) = make_uint4(m8[4], m8[5], m8[6], m8[7]);
-    }
-  }
-  if (tid < 32) {   // per-channel extrema of k over the sequence (attn_kext_kernel)
-    const float* ke = p.kext + ((int64_t)row * 2 + (tid >> 4)) * p.C + quad * 16 + (tid & 15);
-    s_kext[tid >> 4][tid & 15] = *ke;
-  }
   fence_async_smem();                    // generic-proxy writes above are read by tcgen05.mma through the async proxy
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t sbase = smem_u32(smem);
   const uint32_t tmem = s_tmem;
-  const uint32_t my_taddr = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * 32);   // my 32 columns of a buffer
 
-  // my head slots: d = 4: heads 2*half, 2*half + 1 (16 keys each per tile); d = 8: head `half`; d = 16: head 0, keys half*32..
-  // row bounds per head: sum_d min/max(q_d kmax_d, q_d kmin_d) <= s_ij <= ... (raw score units)
-  float m[HPT];
-  bool wide = false;                     // some row of this warp spans more than 120 binades: polynomial needs its clamp
-#pragma unroll
-  for (int hh = 0; hh < HPT; ++hh) m[hh] = 0.f;
-  if (softmax) {
-    const uint32_t w[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
-#pragma unroll
-    for (int h = 0; h < HPQ; ++h) {                  // compile-time h (no runtime-indexed register arrays)
-      float hi = 0.f, lo = 0.f;
-#pragma unroll
-      for (int d = 0; d < D; ++d) {
-        const int ch = h * D + d;
-        const float qv = __uint_as_float((ch & 1) ? (w[ch >> 1] & 0xFFFF0000u) : (w[ch >> 1] << 16));   // bf16 -> fp32
-        const float a = qv * s_kext[1][ch], b = qv * s_kext[0][ch];
-        hi += fmaxf(a, b); lo += fminf(a, b);
-      }
-#pragma unroll
-      for (int hh = 0; hh < HPT; ++hh) {
-        if ((D == 4 ? half * 2 + hh : (D == 8 ? half : 0)) == h) {
-          m[hh] = hi;
-          wide = wide || !((hi - lo) * c < 120.0f);
-        }
-      }
-    }
-    wide = __any_sync(0xffffffffu, wide);
-  }
+  // item -> sequence `row`, first query q0, quad; TSA row = b * W + w (keys along h), FSA row = b * H + h (keys along w)
+  struct Where { int row, q0, quad, cb, cf; };
+  auto locate = [&](int it) {
+    const int item = items.list ? items.list[it] : it;
+    const int per_row = items.nqt * items.nquads;
+    Where w;
+    w.row = item / per_row;
+    const int rem = item - w.row * per_row;
+    const int qt = rem / items.nquads;
+    w.quad = rem - qt * items.nquads;
+    w.q0 = qt * QTILE;
+    w.cb = tsa ? w.row / p.W : w.row / p.H;
+    w.cf = tsa ? w.row - w.cb * p.W : w.row - w.cb * p.H;
+    return w;
+  };
 
-  // pipeline positions, monotonic across passes: stage counter, tile counter (buffer = gt % 3, parity = (gt / 3) & 1)
-  uint32_t n_stage = 0, n_done = 0;
+  uint32_t n_stage = 0;                  // stages issued / consumed so far (monotonic over passes and items)
   // tile t of a pass uses TMEM buffer t % 3; every role keeps the parity of the next phase it will wait for per buffer
   // (softmax: bar_s, issuer: bar_p) in three scalars, so the 3-way unrolled loops address buffers with immediates
   uint32_t ph0 = 0, ph1 = 0, ph2 = 0;
-  auto wait_buf = [&](uint64_t* bars, int b) {      // runtime b (prologue / rare paths)
+  auto wait_buf = [&](uint64_t* bars, int b) {      // runtime b (rare paths)
     const uint32_t ph = b == 0 ? ph0 : (b == 1 ? ph1 : ph2);
     mbar_wait(&bars[b], ph);
     if (b == 0) ph0 ^= 1; else if (b == 1) ph1 ^= 1; else ph2 ^= 1;
   };
 
-  for (int attempt = 0; attempt < 2; ++attempt) {
-    const bool exact = attempt == 1 || p.force_exact;
-    // pass 0 (only if exact): stream S, reduce the exact row maxima.  pass 1: P = ex2(S c - m c), O += P [V | 1].
-    for (int pass = exact ? 0 : 1; pass < 2; ++pass) {
-      const bool maxpass = pass == 0;
-      if (producer) {
-        // ---- warp 9, one lane: TMA loads, NSTAGE-1 stages ahead; a stage is reused once every MMA that read it has completed ----
-        if (elect_one()) {
-          for (int i = 0; i < NST; ++i) {
-            const uint32_t g = n_stage + i, st = g % NSTAGE;
-            if (g >= NSTAGE) mbar_wait(&bar_empty[st], ((g / NSTAGE) - 1) & 1);   // stage g - NSTAGE released (waited in order, every one)
+  if (producer) {
+    // ---- warp 9, one lane: TMA loads, up to NSTAGE stages ahead (also across items); a stage is reused once every MMA that
+    // read it has completed ----
+    if (elect_one()) {
+      for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+        const Where w = locate(it);
+        const int ck = p.C + w.quad * 16, cv = 2 * p.C + w.quad * 16;
+        for (int pass = exact ? 0 : 1; pass < 2; ++pass) {
+          for (int i = 0; i < NST; ++i, ++n_stage) {
+            const uint32_t g = n_stage, st = g % NSTAGE;
+            if (g >= NSTAGE) mbar_wait(&bar_empty[st], ((g / NSTAGE) - 1) & 1);   // stage g - NSTAGE released
             uint8_t* dst = smem + ST_OFF + st * STAGE_BYTES;
             mbar_arrive_expect_tx(&bar_full[st], STAGE_BYTES);
-            const int ck = p.C + quad * 16, cv = 2 * p.C + quad * 16, k0 = i * SKEYS;
+            const int k0 = i * SKEYS;
             if (tsa) {
-              tma_load_4d(dst, &tm, &bar_full[st], ck, cf, k0, cb);
-              tma_load_4d(dst + BOX_BYTES, &tm, &bar_full[st], ck + 8, cf, k0, cb);
-              tma_load_4d(dst + 2 * BOX_BYTES, &tm, &bar_full[st], cv, cf, k0, cb);
-              tma_load_4d(dst + 3 * BOX_BYTES, &tm, &bar_full[st], cv + 8, cf, k0, cb);
+              tma_load_4d(dst, &tm, &bar_full[st], ck, w.cf, k0, w.cb);
+              tma_load_4d(dst + BOX_BYTES, &tm, &bar_full[st], ck + 8, w.cf, k0, w.cb);
+              tma_load_4d(dst + 2 * BOX_BYTES, &tm, &bar_full[st], cv, w.cf, k0, w.cb);
+              tma_load_4d(dst + 3 * BOX_BYTES, &tm, &bar_full[st], cv + 8, w.cf, k0, w.cb);
             } else {
-              tma_load_4d(dst, &tm, &bar_full[st], ck, k0, cf, cb);
-              tma_load_4d(dst + BOX_BYTES, &tm, &bar_full[st], ck + 8, k0, cf, cb);
-              tma_load_4d(dst + 2 * BOX_BYTES, &tm, &bar_full[st], cv, k0, cf, cb);
-              tma_load_4d(dst + 3 * BOX_BYTES, &tm, &bar_full[st], cv + 8, k0, cf, cb);
+              tma_load_4d(dst, &tm, &bar_full[st], ck, k0, w.cf, w.cb);
+              tma_load_4d(dst + BOX_BYTES, &tm, &bar_full[st], ck + 8, k0, w.cf, w.cb);
+              tma_load_4d(dst + 2 * BOX_BYTES, &tm, &bar_full[st], cv, k0, w.cf, w.cb);
+              tma_load_4d(dst + 3 * BOX_BYTES, &tm, &bar_full[st], cv + 8, k0, w.cf, w.cb);
             }
           }
         }
-      } else if (issuer) {
-        // ---- warp 8: every MMA.  P(t) written (bar_p) -> O += P(t) [V | 1], then S(t+3) into the same TMEM buffer: the
-        // two are issued back to back by one thread and the tensor core executes a thread's MMAs in issue order, so S(t+3)
-        // cannot overtake the PV MMA that reads the columns it overwrites ----
-        const uint32_t idesc_s = umma_idesc_bf16(128, KT);
-        const uint32_t idesc_pv = idesc_bf16_bmn(128, 16);
-        auto issue_S = [&](int u, uint32_t b) {      // lane 0; S(u) -> buffer b
-          const uint32_t st = (n_stage + u / TPS) % NSTAGE;
-          const uint32_t kaddr = sbase + ST_OFF + st * STAGE_BYTES + (u % TPS) * KT * 16;
-          const uint64_t kdesc = umma_smem_desc_ns(kaddr, BOX_BYTES, 128);
+      }
+    }
+  } else if (issuer) {
+    // ---- warp 8: every MMA.  P(t) written (bar_p) -> O += P(t) [V | 1], then S(t+3) into the same TMEM buffer: the two are
+    // issued back to back by one thread and the tensor core executes a thread's MMAs in issue order, so S(t+3) cannot
+    // overtake the PV MMA that reads the columns it overwrites ----
+    const uint32_t idesc_s = umma_idesc_bf16(128, KT);
+    const uint32_t idesc_pv = idesc_bf16_bmn(128, 16);
+    uint32_t n_q = 0;
+    auto issue_S = [&](int u, uint32_t b) {        // one elected lane; S(u) -> buffer b
+      const uint32_t st = (n_stage + u / TPS) % NSTAGE;
+      const uint32_t kaddr = sbase + ST_OFF + st * STAGE_BYTES + (u % TPS) * KT * 16;
+      const uint64_t kdesc = umma_smem_desc_ns(kaddr, BOX_BYTES, 128);
 #pragma unroll
-          for (int h = 0; h < HPQ; ++h)
-            umma_bf16_ss(tmem + b * BUF_COLS + h * KT, umma_smem_desc_ns(sbase + Q_OFF + h * 4096, 128, 256), kdesc, idesc_s, 0u);
-          umma_commit(&bar_s[b]);
-          TRACE(2, u);
-        };
-        auto wait_stage = [&](int u) {               // all lanes: the stage holding tile u has landed
-          const uint32_t g = n_stage + u / TPS, st = g % NSTAGE;
-          mbar_wait(&bar_full[st], (g / NSTAGE) & 1);
-        };
+      for (int h = 0; h < HPQ; ++h)
+        umma_bf16_ss(tmem + b * BUF_COLS + h * KT, umma_smem_desc_ns(sbase + Q_OFF + h * 4096, 128, 256), kdesc, idesc_s, 0u);
+      umma_commit(&bar_s[b]);
+      TRACE(2, u);
+    };
+    auto wait_stage = [&](int u) {                 // all lanes: the stage holding tile u has landed
+      const uint32_t g = n_stage + u / TPS, st = g % NSTAGE;
+      mbar_wait(&bar_full[st], (g / NSTAGE) & 1);
+    };
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+      mbar_wait(&bar_q, n_q & 1); ++n_q;           // this item's masked Q copies are in shared memory
+      for (int pass = exact ? 0 : 1; pass < 2; ++pass) {
+        const bool maxpass = pass == 0;
         for (int u = 0; u < (int)NBUF && u < T; ++u) {
           if (u % TPS == 0) wait_stage(u);
           if (elect_one()) { tc_fence_after(); issue_S(u, u); }
@@ -317,14 +297,14 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_attn_tma_kernel(const __grid_c
         }
         for (int t0 = 0; t0 < T; t0 += (int)NBUF) {
 #pragma unroll
-          for (int b = 0; b < (int)NBUF; ++b) {      // compile-time buffer index
+          for (int b = 0; b < (int)NBUF; ++b) {    // compile-time buffer index
             const int t = t0 + b;
             if (t >= T) break;
             const uint32_t st = (n_stage + t / TPS) % NSTAGE;
             const int u = t + NBUF;
             if (u < T && u % TPS == 0) wait_stage(u);
             uint32_t& ph = b == 0 ? ph0 : (b == 1 ? ph1 : ph2);
-            mbar_wait(&bar_p[b], ph);                                   // P(t) written over S(t) (max pass: S(t) consumed)
+            mbar_wait(&bar_p[b], ph);              // P(t) written over S(t) (max pass: S(t) consumed)
             ph ^= 1;
             if (elect_one()) {
               tc_fence_after();
@@ -358,88 +338,45 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_attn_tma_kernel(const __grid_c
             __syncwarp();
           }
         }
-      } else if (maxpass) {
-        // ---- exact row maxima (fallback / force_exact) ----
-#pragma unroll
-        for (int i = 0; i < HPT; ++i) m[i] = -CUDART_INF_F;
-        for (int t = 0; t < T; ++t) {
-          const int b = t % (int)NBUF;
-          wait_buf(bar_s, b);
-          tc_fence_after();
-          const int kcount = min(KT, N - t * KT);      // valid keys of this tile (per head)
-          uint32_t s[32];
-          __syncwarp();
-          tmem_ld_x32(my_taddr + b * BUF_COLS, s);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const int key = D == 4 ? (i & 15) : (D == 8 ? i : half * 32 + i);
-            if (key < kcount) m[D == 4 ? i / 16 : 0] = fmaxf(m[D == 4 ? i / 16 : 0], __uint_as_float(s[i]));
-          }
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&bar_p[b]);                       // S(t) consumed
-        }
-      } else {
-        // ---- P = ex2(S c - m c), written over S ----
-        float mc[HPT];
-#pragma unroll
-        for (int i = 0; i < HPT; ++i) mc[i] = m[i] * c;
-        const float mc0 = mc[0], mc1 = mc[HPT - 1];
-        uint32_t sc[32], pk[16];
-        for (int t0 = 0; t0 < T; t0 += (int)NBUF) {
-#pragma unroll
-          for (int b = 0; b < (int)NBUF; ++b) {      // compile-time buffer index: TMEM / barrier addresses are immediates
-            const int t = t0 + b;
-            if (t >= T) break;
-            {
-              uint32_t& ph = b == 0 ? ph0 : (b == 1 ? ph1 : ph2);
-              mbar_wait(&bar_s[b], ph);
-              ph ^= 1;
-              tc_fence_after();
-              if (tid == 0) TRACE(0, t);
-              __syncwarp();
-              tmem_ld_x32(my_taddr + b * BUF_COLS, sc);
-            }
-            tmem_ld_wait();
-            if (tid == 0) TRACE(4, t);
-            const bool tail = t == T - 1 && T * KT > N;   // last tile: absent keys score 0, which may exceed the bound
-            if (tail) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) sc[i] = __float_as_uint(fminf(__uint_as_float(sc[i]), m[D == 4 ? i / 16 : 0]));
-            }
-            if (tail || wide) { softmax_half<true, 0>(sc, pk, c, mc0); softmax_half<true, 1>(sc, pk, c, mc1); }
-            else { softmax_half<false, 0>(sc, pk, c, mc0); softmax_half<false, 1>(sc, pk, c, mc1); }
-            if (tid == 0) TRACE(5, t);
-            tmem_st_x16(my_taddr + b * BUF_COLS, pk);  // score pair (2i, 2i+1) -> 32-bit cell i of my own columns
-            tmem_st_wait();
-            if (tid == 0) TRACE(6, t);
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bar_p[b]);                     // P(t) in TMEM
-            if (tid == 0) TRACE(1, t);
-          }
-        }
-        mbar_wait(&bar_done, n_done & 1); ++n_done;                    // every PV MMA has completed
-        tc_fence_after();
-      }
-      n_stage += NST;
-      if (maxpass) {
-        if (HPQ == 1 && softmax) s_xch[half * 128 + r] = m[0];
-        tc_fence_before();
-        __syncthreads();
-        tc_fence_after();
-        if (HPQ == 1) {                                // the two threads of a row each saw half of the keys
-          if (softmax) m[0] = fmaxf(s_xch[r], s_xch[128 + r]);
-          __syncthreads();
-        }
+        n_stage += NST;
       }
     }
-    // ---- epilogue: O / l.  D_h = [P_h V over the 8-channel group holding head h | l_h x 8] ----
+  } else {
+    // ---- warps 0-7: softmax.  Item boundaries are software-pipelined: the next item's q row is fetched before the key loop
+    // of the current one, and the epilogue of item i (wait for its last PV MMA, O / l, stores) runs AFTER the masked Q copies
+    // of item i+1 have been handed to the issuer, i.e. underneath the first S MMAs of item i+1. ----
+    const uint32_t my_taddr = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * 32);   // my 32 columns of a buffer
     const uint32_t o_taddr = tmem + ((uint32_t)(quarter * 32) << 16) + O_COL2;
-    uint32_t o[32];
-    bool bad = false;
-    if (softmax) {
+    const int c0 = D == 16 ? 0 : half * 8;         // first channel (within the quad) of my head slots
+    uint32_t n_done = 0;
+    auto q_token = [&](const Where& w, bool& valid) {
+      int64_t tok_base, tok_stride;
+      if (tsa) { tok_base = (int64_t)w.cb * p.H * p.W + w.cf; tok_stride = p.W; }
+      else { tok_base = (int64_t)w.row * p.W; tok_stride = 1; }
+      valid = w.q0 + r < (p.q_end ? p.q_end : N);
+      return tok_base + (int64_t)(valid ? w.q0 + r : 0) * tok_stride;
+    };
+    auto load_q = [&](const Where& w, uint4& qa, uint4& qb) {
+      bool valid;
+      const int64_t tok = q_token(w, valid);
+      qa = make_uint4(0, 0, 0, 0); qb = qa;
+      if (valid) {
+        const uint4* src = reinterpret_cast<const uint4*>((const bf16*)p.qkv + tok * p.ldq + w.quad * 16);
+        qa = src[0]; qb = src[1];
+      }
+    };
+    // deferred epilogue of the previous item
+    bool e_pending = false, e_valid = false;
+    int64_t e_tok = 0;
+    int e_quad = 0, e_item = 0;
+    float e_m[HPT];
+#pragma unroll
+    for (int i = 0; i < HPT; ++i) e_m[i] = 0.f;
+    auto epilogue = [&]() {
+      mbar_wait(&bar_done, n_done & 1); ++n_done;    // every PV MMA of that item has completed
+      tc_fence_after();
+      // O / l.  D_h = [P_h V over the 8-channel group holding head h | l_h x 8]
+      uint32_t o[32];
       __syncwarp();
       if (D == 8) {
         uint32_t t16[16];
@@ -451,56 +388,182 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_attn_tma_kernel(const __grid_c
         tmem_ld_x32(o_taddr + (D == 4 ? 32 * half : 0), o);
         tmem_ld_wait();
       }
-      // the bound keeps every exponent <= 0; if it was so loose that a whole row underflowed (denominator ~ 0) the CTA
-      // repeats the computation with the exact maximum
-      if (D == 16) bad = q_valid && !(__uint_as_float(o[16]) > 1e-30f);
+      tc_fence_before();                             // (the next item's first PV MMA overwrites O only after all 8 warps arrived on bar_p)
+      // the bound keeps every exponent <= 0; if it was so loose that a whole row underflowed (denominator ~ 0) the item is
+      // queued for the exact launch, which overwrites all of its rows
+      bool bad = false;
+      if (D == 16) bad = e_valid && !(__uint_as_float(o[16]) > 1e-30f);
       else {
 #pragma unroll
-        for (int hh = 0; hh < HPT; ++hh) bad = bad || (q_valid && !(__uint_as_float(o[hh * 16 + 8]) > 1e-30f));
+        for (int hh = 0; hh < HPT; ++hh) bad = bad || (e_valid && !(__uint_as_float(o[hh * 16 + 8]) > 1e-30f));
       }
-    }
-    tc_fence_before();
-    const bool redo = attempt == 0 && !p.force_exact && __syncthreads_or(bad);
-    if (redo) continue;
-    if (softmax && q_valid) {
-      if (D == 16) {                                 // both threads of the row hold the same 32 columns: split the 16 dims
-        const float l = __uint_as_float(o[16]);
-        const float inv = 1.0f / l;
-        float v[8];
-#pragma unroll
-        for (int d = 0; d < 8; ++d) v[d] = __uint_as_float(half ? o[8 + d] : o[d]) * inv;
-        store8((bf16*)p.out + q_tok * p.ldo + quad * 16 + half * 8, v);
-        if (p.lse && half == 0) p.lse[q_tok * p.heads + quad] = m[0] * c + log2f(l);
-      } else {
-#pragma unroll
-        for (int hh = 0; hh < HPT; ++hh) {
-          const int head = half * HPT + hh;          // head within the quad
-          const int off = hh * 16 + ((D == 4) ? (hh & 1) * 4 : 0);   // head h's dims start at (h*D) % 8 inside its group
-          const float l = __uint_as_float(o[hh * 16 + 8]);
+      if (!exact && items.redo_list != nullptr && __any_sync(0xffffffffu, bad) && lane == 0) {
+        if (atomicExch(&items.redo_flag[e_item], 1) == 0) items.redo_list[atomicAdd(items.redo_count, 1)] = e_item;
+      }
+      if (e_valid) {
+        if (D == 16) {                               // both threads of the row hold the same 32 columns: split the 16 dims
+          const float l = __uint_as_float(o[16]);
           const float inv = 1.0f / l;
-          bf16* op = (bf16*)p.out + q_tok * p.ldo + quad * 16 + head * D;
-          if (D == 4) {
-            float v[4];
+          float v[8];
 #pragma unroll
-            for (int d = 0; d < 4; ++d) v[d] = __uint_as_float(o[off + d]) * inv;
-            store4(op, v);
-          } else {
-            float v[8];
+          for (int d = 0; d < 8; ++d) v[d] = __uint_as_float(half ? o[8 + d] : o[d]) * inv;
+          store8((bf16*)p.out + e_tok * p.ldo + e_quad * 16 + half * 8, v);
+          if (p.lse && half == 0) p.lse[e_tok * p.heads + e_quad] = e_m[0] * c + log2f(l);
+        } else {
 #pragma unroll
-            for (int d = 0; d < 8; ++d) v[d] = __uint_as_float(o[off + d]) * inv;
-            store8(op, v);
+          for (int hh = 0; hh < HPT; ++hh) {
+            const int head = half * HPT + hh;        // head within the quad
+            const int off = hh * 16 + ((D == 4) ? (hh & 1) * 4 : 0);   // head h's dims start at (h*D) % 8 inside its group
+            const float l = __uint_as_float(o[hh * 16 + 8]);
+            const float inv = 1.0f / l;
+            bf16* op = (bf16*)p.out + e_tok * p.ldo + e_quad * 16 + head * D;
+            if (D == 4) {
+              float v[4];
+#pragma unroll
+              for (int d = 0; d < 4; ++d) v[d] = __uint_as_float(o[off + d]) * inv;
+              store4(op, v);
+            } else {
+              float v[8];
+#pragma unroll
+              for (int d = 0; d < 8; ++d) v[d] = __uint_as_float(o[off + d]) * inv;
+              store8(op, v);
+            }
+            if (p.lse) p.lse[e_tok * p.heads + e_quad * HPQ + head] = e_m[hh] * c + log2f(l);
           }
-          if (p.lse) p.lse[q_tok * p.heads + quad * HPQ + head] = m[hh] * c + log2f(l);
         }
       }
+    };
+
+    uint4 qa = make_uint4(0, 0, 0, 0), qb = qa;      // my row's 16 q channels of the current item
+    if ((int)blockIdx.x < n_items) { const Where w0 = locate(blockIdx.x); load_q(w0, qa, qb); }
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+      const Where w = locate(it);
+      bool q_valid;
+      const int64_t q_tok = q_token(w, q_valid);
+      // per-channel extrema of k over the sequence (attn_kext_kernel), channels of my head slots only
+      float kmin[NCH], kmax[NCH];
+      {
+        const float* ke = p.kext + (int64_t)w.row * 2 * p.C + w.quad * 16 + c0;
+#pragma unroll
+        for (int i = 0; i < NCH; i += 4) {
+          const float4 a = *reinterpret_cast<const float4*>(ke + i), b = *reinterpret_cast<const float4*>(ke + p.C + i);
+          kmin[i] = a.x; kmin[i + 1] = a.y; kmin[i + 2] = a.z; kmin[i + 3] = a.w;
+          kmax[i] = b.x; kmax[i + 1] = b.y; kmax[i + 2] = b.z; kmax[i + 3] = b.w;
+        }
+      }
+      const uint32_t qw[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};   // 2 channels per word
+      // masked copies of Q (K-major, 8-row x 16-byte core matrices): copy h keeps head h's channels.  The two threads of a
+      // row split the copies.  (Every S MMA of the previous item has completed: this warp saw its last bar_s.)
+#pragma unroll
+      for (int h = 0; h < HPQ; ++h) {              // compile-time h: the masks are immediates, no local array
+        if ((HPQ >= 2 ? h / (HPQ / 2) : 0) != half) continue;
+        uint32_t m8[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) m8[i] = (2 * i >= D * h && 2 * i < D * h + D) ? qw[i] : 0u;
+        uint8_t* dst = smem + Q_OFF + h * 4096 + (r >> 3) * 256 + (r & 7) * 16;
+        *reinterpret_cast<uint4*>(dst) = make_uint4(m8[0], m8[1], m8[2], m8[3]);
+        *reinterpret_cast<uint4*>(dst + 128) = make_uint4(m8[4], m8[5], m8[6], m8[7]);
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_q);
+      // row bounds per head slot: sum_d min/max(q_d kmax_d, q_d kmin_d) <= s_ij <= ... (raw score units)
+      float m[HPT];
+      bool wide = false;                 // some row of this warp spans more than 120 binades: polynomial needs its clamp
+#pragma unroll
+      for (int hh = 0; hh < HPT; ++hh) {
+        float hi = 0.f, lo = 0.f;
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+          const int i = hh * D + d;                // index into my channel range; quad channel = c0 + i
+          // q channel c0 + i lives in word (c0 + i) / 2; c0 is 0 or 8, so both candidates have compile-time indices
+          const uint32_t word = (D != 16 && half) ? qw[(4 + (i >> 1)) & 7] : qw[(i >> 1) & 7];
+          const float qv = __uint_as_float((i & 1) ? (word & 0xFFFF0000u) : (word << 16));   // bf16 -> fp32
+          const float a = qv * kmax[i], b = qv * kmin[i];
+          hi += fmaxf(a, b); lo += fminf(a, b);
+        }
+        m[hh] = hi;
+        wide = wide || !((hi - lo) * c < 120.0f);
+      }
+      wide = __any_sync(0xffffffffu, wide);
+
+      if (e_pending) epilogue();                     // previous item: underneath this item's first S MMAs
+      if (it + (int)gridDim.x < n_items) { const Where wn = locate(it + gridDim.x); load_q(wn, qa, qb); }   // next item's q row
+
+      if (exact) {
+        // ---- pass 0: exact row maxima ----
+#pragma unroll
+        for (int i = 0; i < HPT; ++i) m[i] = -CUDART_INF_F;
+        for (int t = 0; t < T; ++t) {
+          const int b = t % (int)NBUF;
+          wait_buf(bar_s, b);
+          tc_fence_after();
+          const int kcount = min(KT, N - t * KT);  // valid keys of this tile (per head)
+          uint32_t s32[32];
+          __syncwarp();
+          tmem_ld_x32(my_taddr + b * BUF_COLS, s32);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int key = D == 4 ? (i & 15) : (D == 8 ? i : half * 32 + i);
+            if (key < kcount) m[D == 4 ? i / 16 : 0] = fmaxf(m[D == 4 ? i / 16 : 0], __uint_as_float(s32[i]));
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bar_p[b]);   // S(t) consumed
+        }
+        if (HPQ == 1) {                            // the two threads of a row each saw half of the keys
+          s_xch[half * 128 + r] = m[0];
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          m[0] = fmaxf(s_xch[r], s_xch[128 + r]);
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+        }
+      }
+
+      // ---- P = ex2(S c - m c), written over S ----
+      float mc[HPT];
+#pragma unroll
+      for (int i = 0; i < HPT; ++i) mc[i] = m[i] * c;
+      const float mc0 = mc[0], mc1 = mc[HPT - 1];
+      uint32_t sc[32], pk[16];
+      for (int t0 = 0; t0 < T; t0 += (int)NBUF) {
+#pragma unroll
+        for (int b = 0; b < (int)NBUF; ++b) {      // compile-time buffer index: TMEM / barrier addresses are immediates
+          const int t = t0 + b;
+          if (t >= T) break;
+          {
+            uint32_t& ph = b == 0 ? ph0 : (b == 1 ? ph1 : ph2);
+            mbar_wait(&bar_s[b], ph);
+            ph ^= 1;
+            tc_fence_after();
+            __syncwarp();
+            tmem_ld_x32(my_taddr + b * BUF_COLS, sc);
+          }
+          tmem_ld_wait();
+          const bool tail = t == T - 1 && T * KT > N;   // last tile: absent keys score 0, which may exceed the bound
+          if (tail) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) sc[i] = __float_as_uint(fminf(__uint_as_float(sc[i]), m[D == 4 ? i / 16 : 0]));
+          }
+          if (tail || wide) { softmax_half<true, 0>(sc, pk, c, mc0); softmax_half<true, 1>(sc, pk, c, mc1); }
+          else { softmax_half<false, 0>(sc, pk, c, mc0); softmax_half<false, 1>(sc, pk, c, mc1); }
+          tmem_st_x16(my_taddr + b * BUF_COLS, pk);  // score pair (2i, 2i+1) -> 32-bit cell i of my own columns
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bar_p[b]);     // P(t) in TMEM
+        }
+      }
+      e_pending = true; e_valid = q_valid; e_tok = q_tok; e_quad = w.quad; e_item = items.list ? items.list[it] : it;
+#pragma unroll
+      for (int i = 0; i < HPT; ++i) e_m[i] = m[i];
     }
-    break;
+    if (e_pending) epilogue();
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);
 }
-
 
 }  // namespace tma_attn
 
@@ -521,8 +584,17 @@ static int make_tmap_qkv(CUtensorMap* out, const AttnParams& p) {
   return TFSWA_OK;
 }
 
-// queries [0, p.q_end) of every sequence (q_end = 0: all); needs p.kext filled by attn_kext_kernel
-int attn_axial_tma_bf16(const AttnParams& p, cudaStream_t st) {
+// bytes of work space after the k extrema: [redo count (16 B)] [redo flag per item] [redo list]
+int64_t attn_axial_tma_work_bytes(const AttnParams& p) {
+  const int N = p.geom == TFSWA_GEOM_TSA ? p.H : p.W;
+  const int64_t rows = p.geom == TFSWA_GEOM_TSA ? (int64_t)p.B * p.W : (int64_t)p.B * p.H;
+  const int64_t n_items = rows * ((N + tma_attn::QTILE - 1) / tma_attn::QTILE) * (p.C / 16);
+  return 16 + 2 * n_items * (int64_t)sizeof(int);
+}
+
+// queries [0, p.q_end) of every sequence (q_end = 0: all); needs p.kext filled by attn_kext_kernel; `work` = device buffer
+// of attn_axial_tma_work_bytes(p) bytes
+int attn_axial_tma_bf16(const AttnParams& p, void* work, cudaStream_t st) {
   using namespace tma_attn;
   const int D = p.C / p.heads;
   const int N = p.geom == TFSWA_GEOM_TSA ? p.H : p.W;
@@ -531,33 +603,45 @@ int attn_axial_tma_bf16(const AttnParams& p, cudaStream_t st) {
   CUtensorMap tm;
   int rc = make_tmap_qkv(&tm, p);
   if (rc) return rc;
+  static int sms = 0;
   static DeviceOnce attr_once;
   if (attr_once.needed()) {
     cudaError_t e1 = cudaFuncSetAttribute(tc_attn_tma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<4>());
     cudaError_t e2 = cudaFuncSetAttribute(tc_attn_tma_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<8>());
     cudaError_t e3 = cudaFuncSetAttribute(tc_attn_tma_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<16>());
-    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) { set_error("attn_tc: cudaFuncSetAttribute failed"); return TFSWA_ECUDA; }
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, attr_once.dev);
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || sms <= 0) { set_error("attn_tc: cudaFuncSetAttribute failed"); return TFSWA_ECUDA; }
     attr_once.done();
   }
-  dim3 grid(((q_end + QTILE - 1) / QTILE) * (p.C / 16), rows, 1);
+  Items items = {};
+  items.nqt = (q_end + QTILE - 1) / QTILE;
+  items.nquads = p.C / 16;
+  items.n = rows * items.nqt * items.nquads;
+  items.exact = p.force_exact ? 1 : 0;
+  int* wk = (int*)work;
+  if (!items.exact) {
+    if (cudaMemsetAsync(wk, 0, 16 + (size_t)items.n * sizeof(int), st) != cudaSuccess) return check_launch("attn_tc(tma) memset");
+    items.redo_count = wk; items.redo_flag = wk + 4; items.redo_list = wk + 4 + items.n;
+  }
   static int pad = -1;                  // TFSWA_TMA_SMEM_PAD=<bytes>: occupancy experiment (e.g. 70000 -> one CTA per SM)
   if (pad < 0) { const char* e = getenv("TFSWA_TMA_SMEM_PAD"); pad = e ? atoi(e) : 0; }
-  if (pad > 0) {
-    cudaFuncSetAttribute(tc_attn_tma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<4>() + pad);
-    tc_attn_tma_kernel<4><<<grid, NTHREADS, smem_bytes<4>() + pad, st>>>(tm, p);
-    return check_launch("attn_tc(tma, padded)");
-  }
-  if (D == 4) tc_attn_tma_kernel<4><<<grid, NTHREADS, smem_bytes<4>(), st>>>(tm, p);
-  else if (D == 8) tc_attn_tma_kernel<8><<<grid, NTHREADS, smem_bytes<8>(), st>>>(tm, p);
-  else tc_attn_tma_kernel<16><<<grid, NTHREADS, smem_bytes<16>(), st>>>(tm, p);
-  return check_launch("attn_tc(tma)");
+  auto launch = [&](const Items& its, int grid) {
+    if (D == 4) {
+      if (pad > 0) cudaFuncSetAttribute(tc_attn_tma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<4>() + pad);
+      tc_attn_tma_kernel<4><<<grid, NTHREADS, smem_bytes<4>() + (pad > 0 ? pad : 0), st>>>(tm, p, its);
+    } else if (D == 8) tc_attn_tma_kernel<8><<<grid, NTHREADS, smem_bytes<8>(), st>>>(tm, p, its);
+    else tc_attn_tma_kernel<16><<<grid, NTHREADS, smem_bytes<16>(), st>>>(tm, p, its);
+  };
+  const int full = 2 * sms;             // two resident CTAs per SM
+  launch(items, items.n < full ? items.n : full);
+  rc = check_launch("attn_tc(tma)");
+  if (rc || items.exact) return rc;
+  // the (normally empty) exact launch over the items whose bound underflowed
+  Items redo = items;
+  redo.list = items.redo_list; redo.count = items.redo_count; redo.exact = 1;
+  redo.redo_count = nullptr; redo.redo_flag = nullptr; redo.redo_list = nullptr;
+  launch(redo, items.n < sms ? items.n : sms);
+  return check_launch("attn_tc(tma, exact pass)");
 }
 
 }  // namespace tfswa
-
-#ifdef TFSWA_TMA_TRACE
-// debug builds only (tools/build_variant.sh trace tc_attn_tma.cu -DTFSWA_TMA_TRACE): copy the per-tile clock samples out
-extern "C" int tfswa_dbg_tma_trace(long long* host) {
-  return (int)cudaMemcpyFromSymbol(host, tfswa::tma_attn::g_trace, sizeof(long long) * 8 * 128);
-}
-#endif
