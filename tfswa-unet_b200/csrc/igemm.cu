@@ -7,6 +7,7 @@
 // (blocks.py:172).  Tiles: TM x TN outputs per CTA (256 threads, 8x4 per thread), K in chunks of 16
 // through double-buffered shared memory; 128-bit global accesses throughout.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace tfswa {
 
@@ -14,6 +15,7 @@ enum { KIND_LINEAR = 0, KIND_CONV3 = 1, KIND_DOWN = 2, KIND_UP = 3 };
 
 // bf16 linear weight gradient on the tensor cores (wgrad_mma.cu); returns 1 when the shape is not covered
 int wgrad_mma_bf16(const tfswa_linear_args* a, const void* g, int64_t ldg, int64_t g_bs, float* dw, float* dbias, cudaStream_t st);
+int wgrad_tc_bf16(const tfswa_linear_args* a, const void* g, int64_t ldg, int64_t g_bs, float* dw, float* dbias, cudaStream_t st);
 int conv_wgrad_mma_bf16(const tfswa_conv_args* a, const void* g, float* dw, float* dbias, cudaStream_t st);
 
 struct IgemmParams {
@@ -442,8 +444,12 @@ int tfswa_linear_wgrad(const tfswa_linear_args* a, const void* g, int64_t ldg, i
   TFSWA_REQUIRE(a->K % 4 == 0 && a->N % 4 == 0 && a->ldx % 4 == 0 && ldg % 4 == 0 && a->x_bs % 4 == 0 && g_bs % 4 == 0,
                 "linear_wgrad: alignment (multiples of 4 elements)");
   TFSWA_REQUIRE(!(a->prologue & TFSWA_PRO_LNHAT) || a->row_stats, "linear_wgrad: PRO_LNHAT needs row_stats");
-  if (a->dtype == TFSWA_BF16) {                      // tensor-core path (wgrad_mma.cu); 1 = shape not covered, fall through
-    const int rc = wgrad_mma_bf16(a, g, ldg, g_bs, dw, dbias, (cudaStream_t)stream);
+  if (a->dtype == TFSWA_BF16) {                      // tensor-core paths; 1 = shape not covered, fall through
+    static int force_mma = -1;                       // TFSWA_WGRAD=mma: skip the tcgen05 kernel (A/B)
+    if (force_mma < 0) { const char* e = getenv("TFSWA_WGRAD"); force_mma = (e && e[0] == 'm') ? 1 : 0; }
+    int rc = force_mma ? 1 : wgrad_tc_bf16(a, g, ldg, g_bs, dw, dbias, (cudaStream_t)stream);   // tcgen05 + TMA (wgrad_tc.cu)
+    if (rc != 1) return rc;
+    rc = wgrad_mma_bf16(a, g, ldg, g_bs, dw, dbias, (cudaStream_t)stream);                        // warp-level MMA (wgrad_mma.cu)
     if (rc != 1) return rc;
   }
   IgemmParams p = {};
