@@ -19,20 +19,26 @@ pytestmark = pytest.mark.gpu
     (900, 512, 128, 3, False),      # stage-3 fc2: two k tiles of 256
     (700, 1024, 256, 3, False),     # stage-4 fc2: four k tiles
     (640, 384, 128, 1, False),      # stage-3 fusion conv: two k tiles of 192
-    (130, 256, 768, 1, True),
+    (300, 256, 768, 1, True),
+    (1554, 32, 96, 1, True),        # a single branch's q|k|v (tests/test_gpu_backward.py tsa_c32)
+    (1554, 32, 32, 1, False),
 ])
-def test_wgrad_tc_matches_torch(M, K, N, nb, ln):
+@pytest.mark.parametrize("slab", [True, False])
+def test_wgrad_tc_matches_torch(M, K, N, nb, ln, slab):
     from tfswa_unet_b200 import ops, _lib as L
-    # slab views: x lives inside a wider (M, nb, K + 32) buffer, g inside (M, nb, N + 64)
-    xbig = seeded((M, nb, K + 32), 51, 1.0).cuda().to(torch.bfloat16)
-    gbig = seeded((M, nb, N + 64), 52, 0.5).cuda().to(torch.bfloat16)
-    x, g = xbig[:, :, :K], gbig[:, :, :N]
+    if slab:      # slab views: x lives inside a wider (M, nb, K + 32) buffer, g inside (M, nb, N + 64)
+        xbig = seeded((M, nb, K + 32), 51, 1.0).cuda().to(torch.bfloat16)
+        gbig = seeded((M, nb, N + 64), 52, 0.5).cuda().to(torch.bfloat16)
+        x, g = xbig[:, :, :K], gbig[:, :, :N]
+    else:
+        x = seeded((M, nb, K), 51, 1.0).cuda().to(torch.bfloat16)
+        g = seeded((M, nb, N), 52, 0.5).cuda().to(torch.bfloat16)
     stats = None
     xf = x.float()
     if ln:
         mean = xf.mean(-1)                                             # (M, nb)
         rstd = torch.rsqrt(xf.var(-1, unbiased=False) + 1e-5)
-        stats = torch.stack([mean.t(), rstd.t()], 1).contiguous()      # (nb, 2, M): mean | rstd per batch
+        stats = torch.stack([mean.t(), rstd.t()], -1).contiguous()     # (nb, M, 2): (mean, rstd) per token, as tfswa_row_stats writes them
         xf = ((xf - mean[..., None]) * rstd[..., None]).to(torch.bfloat16).float()     # the kernel feeds bf16 to the MMA
     dw, db = ops.linear_wgrad(x, g, prologue=L.PRO_LNHAT if ln else L.PRO_NONE, row_stats=stats, want_bias=True)
     torch.cuda.synchronize()

@@ -5,7 +5,7 @@
 // The reduction runs over millions of tokens while the result is at most 1152 x 1024: the kernel is a stream over the
 // tokens, HBM-bound (~50 FLOP/B).  Both operands are TOKEN-major in memory (G: tokens x N, X: tokens x K) while the MMA
 // reduces over tokens, i.e. both are MN-MAJOR UMMA operands (the layout the attention kernel's V operand uses): a TMA box
-// (32 or 64 columns x 64 tokens, 64B / 128B swizzle) lands in shared memory exactly as `tcgen05.mma` wants it, with the
+// (32 or 64 columns x 64 / 128 tokens, 64B / 128B swizzle) lands in shared memory exactly as `tcgen05.mma` wants it, with the
 // token axis as the MMA's K.  No thread touches the operands unless the forward had a LayerNorm prologue: then four warps
 // rewrite the X boxes in place ((x - mean) * rstd per token, swizzle-agnostic because the op is per row) and hand the
 // stage over with a proxy fence.
@@ -23,14 +23,13 @@ using namespace sm100;
 
 namespace wgtc {
 
-constexpr int TOK = 64;                 // tokens per stage
+constexpr int MAX_TOK = 256;            // tokens per stage: 64 / 128 / 256, chosen per shape so that a stage is 32-48 KB
 constexpr int NT = 128;                 // output rows (n) per CTA = UMMA M
 constexpr int STAGES = 4;
 constexpr int THREADS = 192;            // warp 0: TMA, warp 1: MMA issue + TMEM alloc, warps 2-5: prologue transform + epilogue
-constexpr int A_BYTES = NT * TOK * 2;   // 16 KB: G tile (boxes of cbA columns, [token][cbA * 2 B] each)
 
 struct Params {
-  const float* row_stats;               // (2, M) per batch: mean | rstd (PRO_LNHAT) or nullptr
+  const float* row_stats;               // (M, 2) per batch: (mean, rstd) per token (PRO_LNHAT) or nullptr
   int64_t rs_bs;
   float* dw; int64_t w_bs;              // (N, K) fp32 per batch
   float* dbias; int64_t bias_bs;
@@ -38,6 +37,7 @@ struct Params {
   int N, K, msplit;
   int cbA, cbX;                         // columns per TMA box of G / X (32 -> 64B swizzle, 64 -> 128B swizzle)
   int BKW;                              // k columns per CTA (UMMA N): multiple of 16, <= 256
+  int TOK;                              // tokens per stage (TMA box rows)
   uint32_t tmem_cols;
 };
 
@@ -60,6 +60,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant_
   __shared__ __align__(8) uint64_t bar_full[STAGES], bar_ready[STAGES], bar_empty[STAGES], bar_acc;
   __shared__ uint32_t s_tmem;
   __shared__ __align__(16) uint16_t s_ones[256];           // 16 x 16 bf16 ones (K-major core matrices: any layout of ones is ones)
+  __shared__ __align__(8) float2 s_rs[STAGES][MAX_TOK];     // LayerNorm prologue: (mean, rstd) of a stage's tokens, cp.async ring
 
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
@@ -68,6 +69,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant_
   const int zb = blockIdx.z / p.msplit, split = blockIdx.z % p.msplit;
   const int64_t m_begin = (int64_t)split * p.rows_per_cta;
   const int64_t m_end = m_begin + p.rows_per_cta < p.M ? m_begin + p.rows_per_cta : p.M;
+  const int TOK = p.TOK;
+  const uint32_t A_BYTES = (uint32_t)NT * TOK * 2;           // G tile (boxes of cbA columns, [token][cbA * 2 B] each)
   const int nchunks = m_end > m_begin ? (int)((m_end - m_begin + TOK - 1) / TOK) : 0;
   const int bkw = min(p.BKW, p.K - k0);                     // valid k columns of this tile (multiple of 16)
   const uint32_t x_bytes = (uint32_t)TOK * p.BKW * 2;
@@ -118,7 +121,6 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant_
         mbar_wait(lnhat ? &bar_ready[s] : &bar_full[s], (c / STAGES) & 1);
         tc_fence_after();
         const uint32_t sa = base + s * stage_bytes;
-#pragma unroll
         for (int k = 0; k < TOK / 16; ++k) {
           const uint64_t ad = desc_mn(sa + k * stepA, p.cbA, boxA);
           umma_bf16_ss(tmem, ad, desc_mn(sa + A_BYTES + k * stepX, p.cbX, boxX), idesc, (c | k) ? 1u : 0u);
@@ -132,21 +134,37 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant_
     const int et = tid - 64;                 // 0..127: transform / epilogue threads; warp % 4 selects the TMEM lane quarter
     if (lnhat) {
       // ---------------- LayerNorm prologue on the X boxes, in place: x <- (x - mean_m) * rstd_m (0 beyond M) ----------------
+      // (mean, rstd) of the tokens of chunk c + 2 are fetched with 4-byte cp.async while chunk c is transformed: a plain
+      // load after the TMA barrier put a global-memory latency on every stage's critical path (1.5 TB/s instead of 3+)
       const float* rs = p.row_stats + (int64_t)zb * p.rs_bs;
       const uint32_t rowb = (uint32_t)p.cbX * 2;                     // bytes per token row inside a box
       const uint32_t chunks_per_row = rowb / 16, chunks = x_bytes / 16;
+      auto prefetch = [&](int c) {
+        if (c < nchunks) {
+          for (int row = et; row < TOK; row += 128) {
+            int64_t mm = m_begin + (int64_t)c * TOK + row;
+            if (mm >= p.M) mm = p.M - 1;                             // (value unused: the row is zeroed)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(&s_rs[c % STAGES][row])), "l"(rs + 2 * mm) : "memory");
+          }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      };
+      prefetch(0); prefetch(1);
       for (int c = 0; c < nchunks; ++c) {
         const int s = c % STAGES;
+        prefetch(c + 2);
+        asm volatile("cp.async.wait_group 2;" ::: "memory");         // chunk c's statistics have landed (this thread's copies) ...
+        asm volatile("bar.sync 1, 128;" ::: "memory");               // ... and everybody else's
         mbar_wait(&bar_full[s], (c / STAGES) & 1);
         uint8_t* xs = sm + (size_t)s * stage_bytes + A_BYTES;
         const int64_t m = m_begin + (int64_t)c * TOK;
         for (uint32_t i = et; i < chunks; i += 128) {
           const uint32_t row = (i / chunks_per_row) % TOK;           // token inside the box (swizzle permutes chunks within a row only)
-          const int64_t mm = m + row;
           uint4* ptr = reinterpret_cast<uint4*>(xs + (size_t)i * 16);
           uint4 v = *ptr;
-          if (mm < p.M) {
-            const float mean = rs[mm], rstd = rs[p.M + mm];
+          if (m + row < p.M) {
+            const float2 st = s_rs[s][row];
+            const float mean = st.x, rstd = st.y;
             __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -198,12 +216,12 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant_
 }  // namespace wgtc
 
 // token-major bf16 matrix (cols, M rows, batch) with boxes of `cb` columns x 64 tokens; swizzle span = cb * 2 bytes
-static int make_tmap_tokens(CUtensorMap* out, const void* base, int cols, int64_t M, int batch, int64_t ld, int64_t bs, int cb) {
+static int make_tmap_tokens(CUtensorMap* out, const void* base, int cols, int64_t M, int batch, int64_t ld, int64_t bs, int cb, int tok) {
   PFN_encodeTiled enc = get_encode_tiled();
   if (!enc) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return TFSWA_ECUDA; }
   cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)M, (cuuint64_t)batch};
   cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)(batch > 1 ? bs : ld * M) * 2};
-  cuuint32_t box[3] = {(cuuint32_t)cb, (cuuint32_t)wgtc::TOK, 1};
+  cuuint32_t box[3] = {(cuuint32_t)cb, (cuuint32_t)tok, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, cb == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
@@ -217,7 +235,7 @@ int wgrad_tc_bf16(const tfswa_linear_args* a, const void* g, int64_t ldg, int64_
   using namespace wgtc;
   if (a->prologue != TFSWA_PRO_NONE && a->prologue != TFSWA_PRO_LNHAT) return 1;
   if (a->K % 32 || a->N % 32 || a->ldx % 8 || ldg % 8 || a->x_bs % 8 || g_bs % 8 || (((uintptr_t)a->x | (uintptr_t)g) & 15)) return 1;
-  if (a->M >= (1ll << 31) || a->M < TOK) return 1;
+  if (a->M >= (1ll << 31) || a->M < MAX_TOK) return 1;
   Params p = {};
   p.row_stats = a->prologue == TFSWA_PRO_LNHAT ? a->row_stats : nullptr; p.rs_bs = a->rs_bs;
   p.dw = dw; p.w_bs = (int64_t)a->N * a->K; p.dbias = dbias; p.bias_bs = a->N;
@@ -227,11 +245,12 @@ int wgrad_tc_bf16(const tfswa_linear_args* a, const void* g, int64_t ldg, int64_
   // k tile: the largest divisor-friendly width <= 256 (multiple of the box width)
   p.BKW = a->K <= 256 ? a->K : (a->K % 256 == 0 ? 256 : (a->K % 192 == 0 ? 192 : 128));
   if (p.BKW % p.cbX || a->K % p.BKW) return 1;
+  p.TOK = p.BKW <= 64 ? 128 : 64;                     // stage = (128 + BKW) * TOK * 2 bytes: 40 / 48 / 32..48 KB
   p.tmem_cols = 512;                                  // accumulator at [0, BKW), bias accumulator at [256, 272)
   const int kt = a->K / p.BKW, nt = (a->N + NT - 1) / NT;
   static int sms = 0;
   static DeviceOnce attr_once;
-  const size_t smem = (size_t)STAGES * (A_BYTES + (size_t)TOK * 256 * 2) + 1024;
+  const size_t smem = (size_t)STAGES * ((size_t)NT * 64 * 2 + (size_t)64 * 256 * 2) + 1024;      // the largest stage: 48 KB
   if (attr_once.needed()) {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, attr_once.dev);
     if (cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess || sms <= 0) {
@@ -244,15 +263,15 @@ int wgrad_tc_bf16(const tfswa_linear_args* a, const void* g, int64_t ldg, int64_
   if (want < 1) want = 1;
   const int64_t max_split = (p.M + 2047) / 2048;
   if (want > max_split) want = max_split;
-  p.rows_per_cta = ((p.M + want - 1) / want + TOK - 1) / TOK * TOK;
+  p.rows_per_cta = ((p.M + want - 1) / want + p.TOK - 1) / p.TOK * p.TOK;
   p.msplit = (int)((p.M + p.rows_per_cta - 1) / p.rows_per_cta);
   CUtensorMap tm_g, tm_x;
-  int rc = make_tmap_tokens(&tm_g, g, a->N, a->M, a->batch, ldg, g_bs, p.cbA);
+  int rc = make_tmap_tokens(&tm_g, g, a->N, a->M, a->batch, ldg, g_bs, p.cbA, p.TOK);
   if (rc) return rc;
-  rc = make_tmap_tokens(&tm_x, a->x, a->K, a->M, a->batch, a->ldx, a->x_bs, p.cbX);
+  rc = make_tmap_tokens(&tm_x, a->x, a->K, a->M, a->batch, a->ldx, a->x_bs, p.cbX, p.TOK);
   if (rc) return rc;
   dim3 grid(kt, nt, a->batch * p.msplit);
-  const size_t smem_launch = (size_t)STAGES * (A_BYTES + (size_t)TOK * p.BKW * 2) + 1024;
+  const size_t smem_launch = (size_t)STAGES * ((size_t)NT * p.TOK * 2 + (size_t)p.TOK * p.BKW * 2) + 1024;
   wgrad_tc_kernel<<<grid, THREADS, smem_launch, st>>>(tm_g, tm_x, p);
   return check_launch("linear_wgrad(tc)");
 }
