@@ -437,6 +437,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_attn_tma_kernel(const __grid_c
     uint4 qa = make_uint4(0, 0, 0, 0), qb = qa;      // my row's 16 q channels of the current item
     if ((int)blockIdx.x < n_items) { const Where w0 = locate(blockIdx.x); load_q(w0, qa, qb); }
     for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+      if (tid == 0) TRACE(0, (it - (int)blockIdx.x) / (int)gridDim.x);      // item top
       const Where w = locate(it);
       bool q_valid;
       const int64_t q_tok = q_token(w, q_valid);
@@ -467,6 +468,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_attn_tma_kernel(const __grid_c
       fence_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_q);
+      if (tid == 0) TRACE(1, (it - (int)blockIdx.x) / (int)gridDim.x);      // Q handed over
       // row bounds per head slot: sum_d min/max(q_d kmax_d, q_d kmin_d) <= s_ij <= ... (raw score units)
       float m[HPT];
       bool wide = false;                 // some row of this warp spans more than 120 binades: polynomial needs its clamp
@@ -488,6 +490,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_attn_tma_kernel(const __grid_c
       wide = __any_sync(0xffffffffu, wide);
 
       if (e_pending) epilogue();                     // previous item: underneath this item's first S MMAs
+      if (tid == 0) TRACE(4, (it - (int)blockIdx.x) / (int)gridDim.x);      // previous epilogue done
       if (it + (int)gridDim.x < n_items) { const Where wn = locate(it + gridDim.x); load_q(wn, qa, qb); }   // next item's q row
 
       if (exact) {
@@ -540,6 +543,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_attn_tma_kernel(const __grid_c
             tmem_ld_x32(my_taddr + b * BUF_COLS, sc);
           }
           tmem_ld_wait();
+          if (tid == 0 && t == 0) TRACE(5, (it - (int)blockIdx.x) / (int)gridDim.x);   // first S tile in registers
           const bool tail = t == T - 1 && T * KT > N;   // last tile: absent keys score 0, which may exceed the bound
           if (tail) {
 #pragma unroll
@@ -554,6 +558,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_attn_tma_kernel(const __grid_c
           if (lane == 0) mbar_arrive(&bar_p[b]);     // P(t) in TMEM
         }
       }
+      if (tid == 0) TRACE(6, (it - (int)blockIdx.x) / (int)gridDim.x);      // last P published
       e_pending = true; e_valid = q_valid; e_tok = q_tok; e_quad = w.quad; e_item = items.list ? items.list[it] : it;
 #pragma unroll
       for (int i = 0; i < HPT; ++i) e_m[i] = m[i];
@@ -645,3 +650,10 @@ int attn_axial_tma_bf16(const AttnParams& p, void* work, cudaStream_t st) {
 }
 
 }  // namespace tfswa
+
+#ifdef TFSWA_TMA_TRACE
+// debug builds only (tools/build_variant.sh trace tc_attn_tma.cu -DTFSWA_TMA_TRACE): copy the clock samples of CTA 0 out
+extern "C" int tfswa_dbg_tma_trace(long long* host) {
+  return (int)cudaMemcpyFromSymbol(host, tfswa::tma_attn::g_trace, sizeof(long long) * 8 * 128);
+}
+#endif

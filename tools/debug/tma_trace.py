@@ -19,9 +19,13 @@ buf = (C.c_longlong * (8 * 128))()
 rc = _lib.lib().tfswa_dbg_tma_trace(buf)
 assert rc == 0, rc
 ev = [[buf[e * 128 + t] for t in range(128)] for e in range(8)]
-names = ["w0:S ready", "w0:ld done", "w0:math done", "w0:st done", "w0:arrived", "S issued", "PV wake"]
-order = [0, 4, 5, 6, 1, 2, 3]
-t0 = min(x for x in ev[2][:3] if x)
-print("tile  " + "  ".join(f"{n:>12s}" for n in names))
-for t in range(66):
-    print(f"{t:4d}  " + "  ".join(f"{(ev[e][t] - t0) if ev[e][t] else -1:12d}" for e in order))
+# item-level timeline of CTA 0, softmax warp 0 (persistent kernel): cycles relative to the first item's top
+names = ["item top", "Q handed", "prev epi done", "S(0) in regs", "last P publ."]
+order = [0, 1, 4, 5, 6]
+t0 = ev[0][0]
+print("item  " + "  ".join(f"{n:>13s}" for n in names) + "   item time")
+for i in range(24):
+    if not ev[0][i]:
+        break
+    nxt = ev[0][i + 1] if ev[0][i + 1] else 0
+    print(f"{i:4d}  " + "  ".join(f"{(ev[e][i] - t0) if ev[e][i] else -1:13d}" for e in order) + f"   {nxt - ev[0][i] if nxt else -1:9d}")
