@@ -32,6 +32,7 @@ def _ref(qkv, B, H, W, C, heads, geom):
     (1, 64, 4, 64, 0), (2, 4, 258, 64, 1),           # head_dim 8
     (1, 512, 2, 64, 0), (1, 128, 3, 32, 0), (1, 2, 33, 64, 1),
     (1, 256, 3, 128, 0), (2, 3, 200, 128, 1), (1, 140, 2, 128, 0), (1, 2, 300, 128, 1),   # head_dim 16 (one head per CTA)
+    (1, 257, 2, 128, 0), (1, 2, 130, 128, 1), (2, 3, 129, 128, 1), (1, 259, 2, 64, 0), (1, 2, 513, 64, 1),   # 1-3 keys past the last full tile (C3 stage 3: 129)
 ])
 def test_tc_attention_matches_simt_and_reference(B, H, W, C, geom):
     from tfswa_unet_b200 import ops
