@@ -55,7 +55,10 @@ namespace tma_attn {
 
 #ifdef TFSWA_TMA_TRACE
 __device__ long long g_trace[8][128];   // debug: clock64 per (event, tile) of one CTA
-#define TRACE(ev, t) do { if (blockIdx.x == 0 && (t) < 128) g_trace[ev][t] = clock64(); } while (0)
+#ifndef TFSWA_TMA_TRACE_BLOCK
+#define TFSWA_TMA_TRACE_BLOCK 0
+#endif
+#define TRACE(ev, t) do { if (blockIdx.x == TFSWA_TMA_TRACE_BLOCK && (t) < 128) g_trace[ev][t] = clock64(); } while (0)
 #else
 #define TRACE(ev, t) do { } while (0)
 #endif
@@ -134,6 +137,7 @@ __device__ __forceinline__ void softmax_half(const uint32_t (&sc)[32], uint32_t 
 // TMEM: three S/P buffers of 64 columns (S tile = HPQ heads x KT keys fp32; P overwrites the thread's own S columns as
 // bf16 pairs) + O.  A softmax warp may run up to two tiles ahead of the slowest one.
 constexpr uint32_t NBUF = 3, BUF_COLS = 64;
+constexpr int NRING = 8;                              // claimed-item ring (the TMA warp is at most NSTAGE items ahead of the slowest role)
 constexpr uint32_t O_COL2 = NBUF * BUF_COLS;          // 192: O accumulators, HPQ x 16 columns (d = 16: 32)
 
 // PERSISTENT CTAs.  A work item is (sequence, 128-query tile, 16-channel quad).  A launch-per-item version of this kernel
@@ -155,6 +159,7 @@ struct Items {
   int* redo_flag;
   int* redo_list;
   int exact;
+  int* next;              // dynamic item claims: a CTA's first item is blockIdx.x, the following ones gridDim.x + atomicAdd(next, 1)
 };
 
 template <int D>
@@ -168,6 +173,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_attn_tma_kernel(const __grid_c
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t bar_full[NSTAGE], bar_empty[NSTAGE], bar_s[NBUF], bar_p[NBUF], bar_done, bar_q;
   __shared__ uint32_t s_tmem;
+  __shared__ __align__(8) uint64_t bar_item[NRING];
+  __shared__ int s_ring[NRING];
   __shared__ float s_xch[HPQ == 1 ? 256 : 1];   // d = 16, exact pass: the two threads of a row exchange their maxima
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -191,6 +198,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_attn_tma_kernel(const __grid_c
 #pragma unroll
       for (int i = 0; i < (int)NBUF; ++i) { mbar_init(&bar_s[i], 1); mbar_init(&bar_p[i], 8); }
       mbar_init(&bar_done, 1); mbar_init(&bar_q, 8);
+#pragma unroll
+      for (int i = 0; i < NRING; ++i) mbar_init(&bar_item[i], 1);
       fence_barrier_init();
     }
     __syncwarp();
@@ -236,11 +245,24 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_attn_tma_kernel(const __grid_c
     if (b == 0) ph0 ^= 1; else if (b == 1) ph1 ^= 1; else ph2 ^= 1;
   };
 
+  // k-th item of this CTA, published by the TMA warp (-1: no more)
+  auto item_at = [&](int k) {
+    mbar_wait(&bar_item[k % NRING], (uint32_t)(k / NRING) & 1u);
+    return s_ring[k % NRING];
+  };
+
   if (producer) {
     // ---- warp 9, one lane: TMA loads, up to NSTAGE stages ahead (also across items); a stage is reused once every MMA that
     // read it has completed ----
     if (elect_one()) {
-      for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+      auto publish = [&](int k, int v) { s_ring[k % NRING] = v; mbar_arrive(&bar_item[k % NRING]); };
+      int it = (int)blockIdx.x < n_items ? (int)blockIdx.x : -1;
+      publish(0, it);
+      for (int k = 0; it >= 0; ++k) {
+        // claim the next item before loading this one: the softmax warps prefetch its q row during this item's key loop
+        int nxt = (int)gridDim.x + atomicAdd(items.next, 1);
+        if (nxt >= n_items) nxt = -1;
+        publish(k + 1, nxt);
         const Where w = locate(it);
         const int ck = p.C + w.quad * 16, cv = 2 * p.C + w.quad * 16;
         for (int pass = exact ? 0 : 1; pass < 2; ++pass) {
@@ -263,6 +285,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_attn_tma_kernel(const __grid_c
             }
           }
         }
+        it = nxt;
       }
     }
   } else if (issuer) {
@@ -286,7 +309,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_attn_tma_kernel(const __grid_c
       const uint32_t g = n_stage + u / TPS, st = g % NSTAGE;
       mbar_wait(&bar_full[st], (g / NSTAGE) & 1);
     };
-    for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+    for (int k = 0; item_at(k) >= 0; ++k) {
       mbar_wait(&bar_q, n_q & 1); ++n_q;           // this item's masked Q copies are in shared memory
       for (int pass = exact ? 0 : 1; pass < 2; ++pass) {
         const bool maxpass = pass == 0;
@@ -435,9 +458,10 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_attn_tma_kernel(const __grid_c
     };
 
     uint4 qa = make_uint4(0, 0, 0, 0), qb = qa;      // my row's 16 q channels of the current item
-    if ((int)blockIdx.x < n_items) { const Where w0 = locate(blockIdx.x); load_q(w0, qa, qb); }
-    for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
-      if (tid == 0) TRACE(0, (it - (int)blockIdx.x) / (int)gridDim.x);      // item top
+    int it = (int)blockIdx.x < n_items ? (int)blockIdx.x : -1;              // (== item_at(0))
+    if (it >= 0) { const Where w0 = locate(it); load_q(w0, qa, qb); }
+    for (int k = 0; it >= 0; ++k) {
+      if (tid == 0) TRACE(0, k);                   // item top
       const Where w = locate(it);
       bool q_valid;
       const int64_t q_tok = q_token(w, q_valid);
@@ -468,7 +492,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_attn_tma_kernel(const __grid_c
       fence_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_q);
-      if (tid == 0) TRACE(1, (it - (int)blockIdx.x) / (int)gridDim.x);      // Q handed over
+      if (tid == 0) TRACE(1, k);      // Q handed over
       // row bounds per head slot: sum_d min/max(q_d kmax_d, q_d kmin_d) <= s_ij <= ... (raw score units)
       float m[HPT];
       bool wide = false;                 // some row of this warp spans more than 120 binades: polynomial needs its clamp
@@ -490,8 +514,9 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_attn_tma_kernel(const __grid_c
       wide = __any_sync(0xffffffffu, wide);
 
       if (e_pending) epilogue();                     // previous item: underneath this item's first S MMAs
-      if (tid == 0) TRACE(4, (it - (int)blockIdx.x) / (int)gridDim.x);      // previous epilogue done
-      if (it + (int)gridDim.x < n_items) { const Where wn = locate(it + gridDim.x); load_q(wn, qa, qb); }   // next item's q row
+      if (tid == 0) TRACE(4, k);      // previous epilogue done
+      const int it_next = item_at(k + 1);            // claimed by the TMA warp before it loaded this item's first stage
+      if (it_next >= 0) { const Where wn = locate(it_next); load_q(wn, qa, qb); }   // next item's q row
 
       if (exact) {
         // ---- pass 0: exact row maxima ----
@@ -543,7 +568,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_attn_tma_kernel(const __grid_c
             tmem_ld_x32(my_taddr + b * BUF_COLS, sc);
           }
           tmem_ld_wait();
-          if (tid == 0 && t == 0) TRACE(5, (it - (int)blockIdx.x) / (int)gridDim.x);   // first S tile in registers
+          if (tid == 0 && t == 0) TRACE(5, k);   // first S tile in registers
           const bool tail = t == T - 1 && T * KT > N;   // last tile: absent keys score 0, which may exceed the bound
           if (tail) {
 #pragma unroll
@@ -558,10 +583,11 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_attn_tma_kernel(const __grid_c
           if (lane == 0) mbar_arrive(&bar_p[b]);     // P(t) in TMEM
         }
       }
-      if (tid == 0) TRACE(6, (it - (int)blockIdx.x) / (int)gridDim.x);      // last P published
+      if (tid == 0) TRACE(6, k);      // last P published
       e_pending = true; e_valid = q_valid; e_tok = q_tok; e_quad = w.quad; e_item = items.list ? items.list[it] : it;
 #pragma unroll
       for (int i = 0; i < HPT; ++i) e_m[i] = m[i];
+      it = it_next;
     }
     if (e_pending) epilogue();
   }
@@ -623,11 +649,10 @@ int attn_axial_tma_bf16(const AttnParams& p, void* work, cudaStream_t st) {
   items.nquads = p.C / 16;
   items.n = rows * items.nqt * items.nquads;
   items.exact = p.force_exact ? 1 : 0;
-  int* wk = (int*)work;
-  if (!items.exact) {
-    if (cudaMemsetAsync(wk, 0, 16 + (size_t)items.n * sizeof(int), st) != cudaSuccess) return check_launch("attn_tc(tma) memset");
-    items.redo_count = wk; items.redo_flag = wk + 4; items.redo_list = wk + 4 + items.n;
-  }
+  int* wk = (int*)work;                 // header: [redo count, claim counter of the main launch, claim counter of the exact launch, -]
+  if (cudaMemsetAsync(wk, 0, 16 + (items.exact ? 0 : (size_t)items.n * sizeof(int)), st) != cudaSuccess) return check_launch("attn_tc(tma) memset");
+  items.next = wk + 1;
+  if (!items.exact) { items.redo_count = wk; items.redo_flag = wk + 4; items.redo_list = wk + 4 + items.n; }
   static int pad = -1;                  // TFSWA_TMA_SMEM_PAD=<bytes>: occupancy experiment (e.g. 70000 -> one CTA per SM)
   if (pad < 0) { const char* e = getenv("TFSWA_TMA_SMEM_PAD"); pad = e ? atoi(e) : 0; }
   auto launch = [&](const Items& its, int grid) {
@@ -645,6 +670,7 @@ int attn_axial_tma_bf16(const AttnParams& p, void* work, cudaStream_t st) {
   Items redo = items;
   redo.list = items.redo_list; redo.count = items.redo_count; redo.exact = 1;
   redo.redo_count = nullptr; redo.redo_flag = nullptr; redo.redo_list = nullptr;
+  redo.next = wk + 2;
   launch(redo, items.n < sms ? items.n : sms);
   return check_launch("attn_tc(tma, exact pass)");
 }

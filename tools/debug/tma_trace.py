@@ -24,8 +24,14 @@ names = ["item top", "Q handed", "prev epi done", "S(0) in regs", "last P publ."
 order = [0, 1, 4, 5, 6]
 t0 = ev[0][0]
 print("item  " + "  ".join(f"{n:>13s}" for n in names) + "   item time")
-for i in range(24):
+for i in range(int(os.environ.get('TRACE_ITEMS', '24'))):
     if not ev[0][i]:
         break
     nxt = ev[0][i + 1] if ev[0][i + 1] else 0
     print(f"{i:4d}  " + "  ".join(f"{(ev[e][i] - t0) if ev[e][i] else -1:13d}" for e in order) + f"   {nxt - ev[0][i] if nxt else -1:9d}")
+# drift over the kernel: item durations of the first 127 items of the traced CTA
+tops = [ev[0][i] for i in range(128) if ev[0][i]]
+d = [b - a for a, b in zip(tops, tops[1:])]
+if d:
+    print("item durations (cycles), every 8th:", d[::8])
+    print(f"mean of first 16: {sum(d[:16]) / 16:.0f}   mean of last 16: {sum(d[-16:]) / 16:.0f}   mean of all {len(d)}: {sum(d) / len(d):.0f}")
