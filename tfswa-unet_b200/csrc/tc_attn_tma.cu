@@ -174,7 +174,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_attn_tma_kernel(const __grid_c
   __shared__ __align__(8) uint64_t bar_full[NSTAGE], bar_empty[NSTAGE], bar_s[NBUF], bar_p[NBUF], bar_done, bar_q;
   __shared__ uint32_t s_tmem;
   __shared__ __align__(8) uint64_t bar_item[NRING];
-  __shared__ int s_ring[NRING];
+  __shared__ int s_ring[NRING];                       // claimed items: id (-1: none left) ...
+  __shared__ int4 s_slot[NRING];                      // ... and where it is (row, b, column / row inside b, q0 | quad)
   __shared__ float s_xch[HPQ == 1 ? 256 : 1];   // d = 16, exact pass: the two threads of a row exchange their maxima
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -189,6 +190,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_attn_tma_kernel(const __grid_c
   const int tail_keys = N - (NST - 1) * SKEYS;       // valid keys in the last stage (1..128)
   const bool exact = items.exact != 0;
   const int n_items = items.list ? *items.count : items.n;
+  if ((int)blockIdx.x >= n_items) return;             // (the exact launch over the redo list is normally empty: no set-up at all)
 
   // ---- set-up, once per CTA ----
   if (warp == 0) {
@@ -220,11 +222,12 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_attn_tma_kernel(const __grid_c
   const uint32_t tmem = s_tmem;
 
   // item -> sequence `row`, first query q0, quad; TSA row = b * W + w (keys along h), FSA row = b * H + h (keys along w)
-  struct Where { int row, q0, quad, cb, cf; };
-  auto locate = [&](int it) {
+  struct Where { int row, q0, quad, cb, cf, item; };
+  auto locate = [&](int it) {             // three integer divisions: done once per item by the TMA warp, published in s_slot
     const int item = items.list ? items.list[it] : it;
     const int per_row = items.nqt * items.nquads;
     Where w;
+    w.item = item;
     w.row = item / per_row;
     const int rem = item - w.row * per_row;
     const int qt = rem / items.nquads;
@@ -250,20 +253,33 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_attn_tma_kernel(const __grid_c
     mbar_wait(&bar_item[k % NRING], (uint32_t)(k / NRING) & 1u);
     return s_ring[k % NRING];
   };
+  auto where_at = [&](int k, int item) {  // after item_at(k) returned `item` >= 0
+    const int4 v = s_slot[k % NRING];
+    Where w;
+    w.item = item; w.row = v.x; w.cb = v.y; w.cf = v.z; w.q0 = v.w & ~(QTILE - 1); w.quad = v.w & (QTILE - 1);
+    return w;
+  };
 
   if (producer) {
     // ---- warp 9, one lane: TMA loads, up to NSTAGE stages ahead (also across items); a stage is reused once every MMA that
     // read it has completed ----
     if (elect_one()) {
-      auto publish = [&](int k, int v) { s_ring[k % NRING] = v; mbar_arrive(&bar_item[k % NRING]); };
+      Where w, wn;
+      auto publish = [&](int k, int it, Where& ww) {
+        if (it >= 0) {
+          ww = locate(it);
+          s_slot[k % NRING] = make_int4(ww.row, ww.cb, ww.cf, ww.q0 | ww.quad);
+        }
+        s_ring[k % NRING] = it >= 0 ? ww.item : -1;
+        mbar_arrive(&bar_item[k % NRING]);
+      };
       int it = (int)blockIdx.x < n_items ? (int)blockIdx.x : -1;
-      publish(0, it);
+      publish(0, it, w);
       for (int k = 0; it >= 0; ++k) {
         // claim the next item before loading this one: the softmax warps prefetch its q row during this item's key loop
         int nxt = (int)gridDim.x + atomicAdd(items.next, 1);
         if (nxt >= n_items) nxt = -1;
-        publish(k + 1, nxt);
-        const Where w = locate(it);
+        publish(k + 1, nxt, wn);
         const int ck = p.C + w.quad * 16, cv = 2 * p.C + w.quad * 16;
         for (int pass = exact ? 0 : 1; pass < 2; ++pass) {
           for (int i = 0; i < NST; ++i, ++n_stage) {
@@ -285,7 +301,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_attn_tma_kernel(const __grid_c
             }
           }
         }
-        it = nxt;
+        it = nxt; w = wn;
       }
     }
   } else if (issuer) {
@@ -458,11 +474,11 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_attn_tma_kernel(const __grid_c
     };
 
     uint4 qa = make_uint4(0, 0, 0, 0), qb = qa;      // my row's 16 q channels of the current item
-    int it = (int)blockIdx.x < n_items ? (int)blockIdx.x : -1;              // (== item_at(0))
-    if (it >= 0) { const Where w0 = locate(it); load_q(w0, qa, qb); }
+    int it = item_at(0);
+    if (it >= 0) { const Where w0 = where_at(0, it); load_q(w0, qa, qb); }
     for (int k = 0; it >= 0; ++k) {
       if (tid == 0) TRACE(0, k);                   // item top
-      const Where w = locate(it);
+      const Where w = where_at(k, it);
       bool q_valid;
       const int64_t q_tok = q_token(w, q_valid);
       // per-channel extrema of k over the sequence (attn_kext_kernel), channels of my head slots only
@@ -516,7 +532,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_attn_tma_kernel(const __grid_c
       if (e_pending) epilogue();                     // previous item: underneath this item's first S MMAs
       if (tid == 0) TRACE(4, k);      // previous epilogue done
       const int it_next = item_at(k + 1);            // claimed by the TMA warp before it loaded this item's first stage
-      if (it_next >= 0) { const Where wn = locate(it_next); load_q(wn, qa, qb); }   // next item's q row
+      if (it_next >= 0) { const Where wn = where_at(k + 1, it_next); load_q(wn, qa, qb); }   // next item's q row
 
       if (exact) {
         // ---- pass 0: exact row maxima ----
@@ -584,7 +600,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_attn_tma_kernel(const __grid_c
         }
       }
       if (tid == 0) TRACE(6, k);      // last P published
-      e_pending = true; e_valid = q_valid; e_tok = q_tok; e_quad = w.quad; e_item = items.list ? items.list[it] : it;
+      e_pending = true; e_valid = q_valid; e_tok = q_tok; e_quad = w.quad; e_item = it;
 #pragma unroll
       for (int i = 0; i < HPT; ++i) e_m[i] = m[i];
       it = it_next;
