@@ -207,12 +207,15 @@ tc_tail_kernel(const __grid_constant__ CUtensorMap tm_att, const __grid_constant
         tmem_ld_wait();
 #pragma unroll
         for (int q4 = 0; q4 < 4; ++q4) {
-          float v[8];
+          uint32_t v[4];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = gelu_hidden(__uint_as_float(raw[q4 * 8 + j]) + s_b1[t * 64 + ch * 32 + q4 * 8 + j]);
+          for (int j = 0; j < 4; ++j) {
+            const float2 bb = *reinterpret_cast<const float2*>(&s_b1[t * 64 + ch * 32 + q4 * 8 + 2 * j]);
+            v[j] = gelu_hidden_bf16x2(__uint_as_float(raw[q4 * 8 + 2 * j]), __uint_as_float(raw[q4 * 8 + 2 * j + 1]), bb.x, bb.y);
+          }
           uint32_t off = r * 128 + (ch * 4 + q4) * 16;
           off ^= ((off >> 7) & 7u) << 4;
-          store8(reinterpret_cast<bf16*>(a2 + off), v);
+          *reinterpret_cast<uint4*>(a2 + off) = make_uint4(v[0], v[1], v[2], v[3]);
         }
       }
     }

@@ -262,9 +262,8 @@ tc_tail128_kernel(const __grid_constant__ CUtensorMap tm_att, const __grid_const
         uint32_t pk[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float g0 = gelu_hidden(__uint_as_float(raw[2 * j]) + s_b1[c * T8_HC + t * 16 + 2 * j]);
-          const float g1 = gelu_hidden(__uint_as_float(raw[2 * j + 1]) + s_b1[c * T8_HC + t * 16 + 2 * j + 1]);
-          asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(pk[j]) : "f"(g1), "f"(g0));
+          const float2 bb = *reinterpret_cast<const float2*>(&s_b1[c * T8_HC + t * 16 + 2 * j]);
+          pk[j] = gelu_hidden_bf16x2(__uint_as_float(raw[2 * j]), __uint_as_float(raw[2 * j + 1]), bb.x, bb.y);
         }
         __syncwarp();
         tmem_st_x8(lane_addr + T8_G_COL + b * 32 + t * 8, pk);      // hidden columns (2j, 2j+1) -> 32-bit cell j: A operand of MMA3_c
