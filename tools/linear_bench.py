@@ -7,7 +7,13 @@ from tfswa_unet_b200 import ops, _lib as L
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 cases = [("fc1 s1", 4239400, 3, 32, 128, True, True, False), ("qkv s1", 4239400, 1, 32, 288, True, False, False),
          ("fc2 s1", 4239400, 3, 128, 32, False, False, True), ("proj s1", 4239400, 3, 32, 32, False, False, True),
-         ("fc1 s3", 264192, 3, 128, 512, True, True, False), ("fc2 s3", 264192, 3, 512, 128, False, False, True)]
+         ("fc1 s3", 264192, 3, 128, 512, True, True, False), ("fc2 s3", 264192, 3, 512, 128, False, False, True),
+         ("qkv s3", 264192, 1, 128, 1152, True, False, False), ("in_proj s3", 264192, 1, 128, 128, False, False, False),
+         ("fusion s1", 4239400, 1, 96, 32, False, True, False), ("fusion s2", 1056768, 1, 192, 64, False, True, False),
+         ("fusion s3", 264192, 1, 384, 128, False, True, False), ("qkv s4", 65536, 1, 256, 2304, True, False, False)]
+only = os.environ.get("LINEAR_BENCH_ONLY")
+if only:
+    cases = [c for c in cases if only in c[0]]
 for name, M, nb, K, N, ln, gelu, res in cases:
     M = M * B // 8
     x = torch.randn(M, nb, K, device="cuda").to(torch.bfloat16)
