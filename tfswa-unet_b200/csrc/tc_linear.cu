@@ -288,6 +288,7 @@ constexpr int PL_MAX_STAGES = 8;
 struct PlParams {
   TcLinearParams g;
   int tiles_n, nstages, has_r1;
+  int nsb;                             // staging buffers per epilogue group (1 or 2): stores of that many tiles may be in flight per group
   int tiles_m, total, rows, row_major;   // rows = tiles_m * batch; row_major: a CTA walks all n-tiles of a row block before the next one
   uint32_t ring_bytes, stg_bytes;      // bytes of the load ring / of ONE staging buffer (128 x BN bf16)
 };
@@ -356,9 +357,11 @@ __global__ void __launch_bounds__(PL_THREADS, 1) tc_linear_persist_kernel(const 
       for (int i = 0; tile_of(i, m0, n0, z); ++i) {
         const int b = i & 1;
         if (pp.has_r1) {
-          if (i >= 2) mbar_wait(&stg_free[b], (uint32_t)((i >> 1) - 1) & 1u);   // the store of tile i-2 has read staging[b]
+          const int k = i >> 1;                      // k-th tile of group b: staging buffer k % nsb of that group
+          if (k >= 1) mbar_wait(&stg_free[b], (uint32_t)(k - 1) & 1u);   // the group's store of tile k - nsb has read that buffer
+          uint8_t* dst = staging + (size_t)(b * pp.nsb + k % pp.nsb) * pp.stg_bytes;
           mbar_arrive_expect_tx(&r1_full[b], 128u * p.BN * 2u);
-          for (int bx = 0; bx < nbox; ++bx) tma_load_3d(staging + b * pp.stg_bytes + bx * box_bytes, &tmr, &r1_full[b], n0 + bx * p.OB, (int)m0, z);
+          for (int bx = 0; bx < nbox; ++bx) tma_load_3d(dst + bx * box_bytes, &tmr, &r1_full[b], n0 + bx * p.OB, (int)m0, z);
         }
         for (int kb = 0; kb < p.KB; ++kb, ++g) {
           const uint32_t s = g % S;
@@ -406,15 +409,15 @@ __global__ void __launch_bounds__(PL_THREADS, 1) tc_linear_persist_kernel(const 
     const int row_in_tile = quad * 32 + lane;
     const uint32_t swz_mask = (ob_bytes >> 4) - 1u;
     const uint32_t ob_shift = p.OB == 64 ? 6u : (p.OB == 32 ? 5u : 4u);
-    uint8_t* stg = staging + gi * pp.stg_bytes;
     // per-group copies of the bias and rowsum(W) rows of the current batch entry (all N columns): reloaded only when z changes
-    float* sb_all = reinterpret_cast<float*>(staging + 2 * pp.stg_bytes) + (size_t)gi * 2 * p.N;
+    float* sb_all = reinterpret_cast<float*>(staging + 2 * (size_t)pp.nsb * pp.stg_bytes) + (size_t)gi * 2 * p.N;
     float* sw_all = sb_all + p.N;
     int cur_z = -1;
     const uint32_t bar_id = 1 + gi;
     uint32_t n_use = 0;                               // tiles this group has processed (phase of acc_full / r1_full / stg_ok)
     int64_t m0; int n0, zt;
     for (int i = gi; tile_of(i, m0, n0, zt); i += 2, ++n_use) {
+      uint8_t* stg = staging + (size_t)(gi * pp.nsb + n_use % pp.nsb) * pp.stg_bytes;
       if (zt != cur_z) {                              // (group-uniform) new batch entry: its bias / rowsum(W) rows
         asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");   // nobody still reads the old rows
         for (int ii = et; ii < p.N; ii += 256) {
@@ -438,7 +441,8 @@ __global__ void __launch_bounds__(PL_THREADS, 1) tc_linear_persist_kernel(const 
       // on stg_ok (no group-wide rendezvous); with one, the landed residual tile (r1_full) implies it
       if (!pp.has_r1) {
         if (et == 0) {
-          if (n_use) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          if (pp.nsb == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the store of tile n_use - 2 (same buffer)
+          else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
           mbar_arrive(&stg_ok[gi]);
         }
       }
@@ -550,7 +554,8 @@ __global__ void __launch_bounds__(PL_THREADS, 1) tc_linear_persist_kernel(const 
       if (et == 0 && pp.has_r1) {
         // with a residual the TMA warp wants staging[gi] back as early as possible (it loads the group's next residual tile
         // into it, two tiles ahead): wait for the store's reads here rather than at the top of the next tile
-        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        if (pp.nsb == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the buffer of the group's NEXT tile is free
+        else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         mbar_arrive(&stg_free[gi]);
       }
     }
@@ -644,10 +649,12 @@ extern "C" int tfswa_linear_tc_fwd(const tfswa_linear_args* a, const void* w_bf1
   pp.row_major = (pp.tiles_n > 1 && pp.rows >= 8 * sms) ? 1 : 0;
   pp.stg_bytes = (uint32_t)TC_BM * p.BN * 2;
   const int64_t rows_bytes = 4 * (int64_t)a->N * (int64_t)sizeof(float);   // bias + rowsum(W) rows, one copy per epilogue group
-  const int64_t ring_room = 220 * 1024 - 1024 - 2 * (int64_t)pp.stg_bytes - rows_bytes;
+  pp.nsb = 1;        // (2 = two stores in flight per group: measured no gain on the write-dominated shapes and it costs ring depth)
+  const int64_t ring_room = 220 * 1024 - 1024 - 2 * (int64_t)pp.nsb * pp.stg_bytes - rows_bytes;
   pp.nstages = (int)(ring_room / stage_bytes);
   if (pp.nstages > PL_MAX_STAGES) pp.nstages = PL_MAX_STAGES;
-  if (!force_v1 && total64 < (1ll << 30) && total64 >= 2 * (int64_t)sms && pp.nstages >= 2 && p.tmem_cols <= 256 && p.BN >= 32) {
+  if (!force_v1 && total64 < (1ll << 30) && total64 >= 2 * (int64_t)sms && pp.nstages >= 2 && p.tmem_cols <= 256 && p.BN >= 32 &&
+      a->epilogue != TFSWA_EPI_GELU) {     // (erf-GELU epilogues are issue-bound: measured equal or faster on the one-tile-per-CTA kernel, 3 CTAs / SM)
     pp.g = p;
     pp.has_r1 = a->r1 ? 1 : 0;
     pp.ring_bytes = (uint32_t)pp.nstages * stage_bytes;
@@ -656,7 +663,7 @@ extern "C" int tfswa_linear_tc_fwd(const tfswa_linear_args* a, const void* w_bf1
       rc = make_tmap_bf16_3d(&tmr, a->r1, a->N, a->M, a->batch, a->ldr1, a->r1_bs, p.OB, TC_BM);
       if (rc) return rc;
     }
-    const size_t psmem = 1024 + pp.ring_bytes + 2 * (size_t)pp.stg_bytes + (size_t)rows_bytes;
+    const size_t psmem = 1024 + pp.ring_bytes + 2 * (size_t)pp.nsb * pp.stg_bytes + (size_t)rows_bytes;
     tc_linear_persist_kernel<<<sms, PL_THREADS, psmem, (cudaStream_t)stream>>>(tmx, tmw, tmy, tmr, pp);
     return check_launch("linear_tc(persistent)");
   }
