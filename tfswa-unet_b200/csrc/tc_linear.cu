@@ -282,25 +282,29 @@ __global__ void __launch_bounds__(TC_THREADS) tc_linear_kernel(const __grid_cons
 // so the loads and MMAs of the next tiles and the other group's epilogue run under a group's epilogue.  The one-tile-per-CTA
 // kernel above reaches 2.1-4.3 TB/s on the block's GEMMs (every CTA pays TMEM allocation, barrier set-up, descriptor fetch
 // and a cold pipeline for 40-64 KB of traffic); it remains the path for problems with fewer than two tiles per SM.
-constexpr int PL_THREADS = 64 + 512;
+constexpr int PL_MAXG = 3;                 // epilogue groups (8 warps each); tile i -> group i % NG.  Two instantiations: NG = 2 (96 registers:
+                                           // tiles of 96-128 columns) and NG = 3 (72 registers: narrow tiles, where a third group hides more latency)
 constexpr int PL_MAX_STAGES = 8;
 
 struct PlParams {
   TcLinearParams g;
   int tiles_n, nstages, has_r1;
+  int ng;                              // epilogue groups in use (2 or 3) = TMEM accumulators = tiles in flight behind the MMA warp
+  uint32_t tmem_total;                 // power of two >= ng * tmem_cols
   int nsb;                             // staging buffers per epilogue group (1 or 2): stores of that many tiles may be in flight per group
   int tiles_m, total, rows, row_major;   // rows = tiles_m * batch; row_major: a CTA walks all n-tiles of a row block before the next one
   uint32_t ring_bytes, stg_bytes;      // bytes of the load ring / of ONE staging buffer (128 x BN bf16)
 };
 
-__global__ void __launch_bounds__(PL_THREADS, 1) tc_linear_persist_kernel(const __grid_constant__ CUtensorMap tmx,
+template <int NG>
+__global__ void __launch_bounds__(64 + NG * 256, 1) tc_linear_persist_kernel(const __grid_constant__ CUtensorMap tmx,
                                                                           const __grid_constant__ CUtensorMap tmw,
                                                                           const __grid_constant__ CUtensorMap tmy,
                                                                           const __grid_constant__ CUtensorMap tmr,
                                                                           const PlParams pp) {
   const TcLinearParams& p = pp.g;
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bar_full[PL_MAX_STAGES], bar_empty[PL_MAX_STAGES], acc_full[2], acc_empty[2], stg_free[2], r1_full[2], stg_ok[2];
+  __shared__ __align__(8) uint64_t bar_full[PL_MAX_STAGES], bar_empty[PL_MAX_STAGES], acc_full[PL_MAXG], acc_empty[PL_MAXG], stg_free[PL_MAXG], r1_full[PL_MAXG], stg_ok[PL_MAXG];
   __shared__ uint32_t s_tmem;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -317,11 +321,11 @@ __global__ void __launch_bounds__(PL_THREADS, 1) tc_linear_persist_kernel(const 
       prefetch_tmap(&tmx); prefetch_tmap(&tmw); prefetch_tmap(&tmy);
       if (pp.has_r1) prefetch_tmap(&tmr);
       for (int s = 0; s < S; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
-      for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 8); mbar_init(&stg_free[b], 1); mbar_init(&r1_full[b], 1); mbar_init(&stg_ok[b], 1); }
+      for (int b = 0; b < NG; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 8); mbar_init(&stg_free[b], 1); mbar_init(&r1_full[b], 1); mbar_init(&stg_ok[b], 1); }
       fence_barrier_init();
     }
     __syncwarp();
-    tmem_alloc(&s_tmem, 2 * p.tmem_cols);
+    tmem_alloc(&s_tmem, pp.tmem_total);
   }
   tc_fence_before();
   __syncthreads();
@@ -355,9 +359,9 @@ __global__ void __launch_bounds__(PL_THREADS, 1) tc_linear_persist_kernel(const 
       uint32_t g = 0;
       int64_t m0; int n0, z;
       for (int i = 0; tile_of(i, m0, n0, z); ++i) {
-        const int b = i & 1;
+        const int b = i % NG;
         if (pp.has_r1) {
-          const int k = i >> 1;                      // k-th tile of group b: staging buffer k % nsb of that group
+          const int k = i / NG;                      // k-th tile of group b: staging buffer k % nsb of that group
           if (k >= 1) mbar_wait(&stg_free[b], (uint32_t)(k - 1) & 1u);   // the group's store of tile k - nsb has read that buffer
           uint8_t* dst = staging + (size_t)(b * pp.nsb + k % pp.nsb) * pp.stg_bytes;
           mbar_arrive_expect_tx(&r1_full[b], 128u * p.BN * 2u);
@@ -381,8 +385,8 @@ __global__ void __launch_bounds__(PL_THREADS, 1) tc_linear_persist_kernel(const 
       uint32_t g = 0;
       int64_t m0; int n0, z;
       for (int i = 0; tile_of(i, m0, n0, z); ++i) {
-        const int b = i & 1;
-        if (i >= 2) { mbar_wait(&acc_empty[b], (uint32_t)((i >> 1) - 1) & 1u); tc_fence_after(); }   // epilogue of tile i-2 has drained buffer b
+        const int b = i % NG;
+        if (i >= NG) { mbar_wait(&acc_empty[b], (uint32_t)(i / NG - 1) & 1u); tc_fence_after(); }   // epilogue of tile i - NG has drained buffer b
         for (int kb = 0; kb < p.KB; ++kb, ++g) {
           const uint32_t s = g % S;
           mbar_wait(&bar_full[s], (g / S) & 1u);
@@ -410,13 +414,13 @@ __global__ void __launch_bounds__(PL_THREADS, 1) tc_linear_persist_kernel(const 
     const uint32_t swz_mask = (ob_bytes >> 4) - 1u;
     const uint32_t ob_shift = p.OB == 64 ? 6u : (p.OB == 32 ? 5u : 4u);
     // per-group copies of the bias and rowsum(W) rows of the current batch entry (all N columns): reloaded only when z changes
-    float* sb_all = reinterpret_cast<float*>(staging + 2 * (size_t)pp.nsb * pp.stg_bytes) + (size_t)gi * 2 * p.N;
+    float* sb_all = reinterpret_cast<float*>(staging + (size_t)NG * pp.nsb * pp.stg_bytes) + (size_t)gi * 2 * p.N;
     float* sw_all = sb_all + p.N;
     int cur_z = -1;
     const uint32_t bar_id = 1 + gi;
     uint32_t n_use = 0;                               // tiles this group has processed (phase of acc_full / r1_full / stg_ok)
     int64_t m0; int n0, zt;
-    for (int i = gi; tile_of(i, m0, n0, zt); i += 2, ++n_use) {
+    for (int i = gi; tile_of(i, m0, n0, zt); i += NG, ++n_use) {
       uint8_t* stg = staging + (size_t)(gi * pp.nsb + n_use % pp.nsb) * pp.stg_bytes;
       if (zt != cur_z) {                              // (group-uniform) new batch entry: its bias / rowsum(W) rows
         asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");   // nobody still reads the old rows
@@ -563,7 +567,7 @@ __global__ void __launch_bounds__(PL_THREADS, 1) tc_linear_persist_kernel(const 
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, 2 * p.tmem_cols);
+  if (warp == 0) tmem_dealloc(tmem, pp.tmem_total);
 }
 
 static int pick_bn(int N) {
@@ -634,7 +638,8 @@ extern "C" int tfswa_linear_tc_fwd(const tfswa_linear_args* a, const void* w_bf1
   static DeviceOnce pl_once;
   if (force_v1 < 0) { const char* e = getenv("TFSWA_LINEAR_KERNEL"); force_v1 = (e && !strcmp(e, "v1")) ? 1 : 0; }
   if (pl_once.needed()) {
-    cudaError_t e = cudaFuncSetAttribute(tc_linear_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(tc_linear_persist_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_linear_persist_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, pl_once.dev);
     if (e != cudaSuccess || sms <= 0) { set_error("linear_tc: cudaFuncSetAttribute(persistent): %s", cudaGetErrorString(e)); return TFSWA_ECUDA; }
     pl_once.done();
@@ -648,13 +653,21 @@ extern "C" int tfswa_linear_tc_fwd(const tfswa_linear_args* a, const void* w_bf1
   pp.total = (int)total64;
   pp.row_major = (pp.tiles_n > 1 && pp.rows >= 8 * sms) ? 1 : 0;
   pp.stg_bytes = (uint32_t)TC_BM * p.BN * 2;
-  const int64_t rows_bytes = 4 * (int64_t)a->N * (int64_t)sizeof(float);   // bias + rowsum(W) rows, one copy per epilogue group
+  pp.ng = p.BN <= 64 ? 3 : 2;
+  {
+    static int force_ng = -1;           // TFSWA_LINEAR_GROUPS=2|3 (development A/B)
+    if (force_ng < 0) { const char* e = getenv("TFSWA_LINEAR_GROUPS"); force_ng = e ? atoi(e) : 0; }
+    if (force_ng == 2 || (force_ng == 3 && 3 * p.tmem_cols <= 512)) pp.ng = force_ng;
+  }
+  pp.tmem_total = pp.ng * p.tmem_cols <= 256 ? (pp.ng * p.tmem_cols <= 128 ? (pp.ng * p.tmem_cols <= 64 ? 64 : 128) : 256) : 512;
+  const int64_t rows_bytes = 2 * (int64_t)pp.ng * a->N * (int64_t)sizeof(float);   // bias + rowsum(W) rows, one copy per epilogue group
   pp.nsb = 1;        // (2 = two stores in flight per group: measured no gain on the write-dominated shapes and it costs ring depth)
-  const int64_t ring_room = 220 * 1024 - 1024 - 2 * (int64_t)pp.nsb * pp.stg_bytes - rows_bytes;
+  const int64_t ring_room = 220 * 1024 - 1024 - (int64_t)pp.ng * pp.nsb * pp.stg_bytes - rows_bytes;
   pp.nstages = (int)(ring_room / stage_bytes);
   if (pp.nstages > PL_MAX_STAGES) pp.nstages = PL_MAX_STAGES;
   if (!force_v1 && total64 < (1ll << 30) && total64 >= 2 * (int64_t)sms && pp.nstages >= 2 && p.tmem_cols <= 256 && p.BN >= 32 &&
-      a->epilogue != TFSWA_EPI_GELU) {     // (erf-GELU epilogues are issue-bound: measured equal or faster on the one-tile-per-CTA kernel, 3 CTAs / SM)
+      !(a->epilogue == TFSWA_EPI_GELU && a->N > a->K)) {   // (wide erf-GELU epilogues - fc1: N = 4K - are issue-bound: measured equal or
+                                                                // faster on the one-tile-per-CTA kernel with its 3 CTAs / SM; the fusion convs, N = K/3, are not)
     pp.g = p;
     pp.has_r1 = a->r1 ? 1 : 0;
     pp.ring_bytes = (uint32_t)pp.nstages * stage_bytes;
@@ -663,8 +676,9 @@ extern "C" int tfswa_linear_tc_fwd(const tfswa_linear_args* a, const void* w_bf1
       rc = make_tmap_bf16_3d(&tmr, a->r1, a->N, a->M, a->batch, a->ldr1, a->r1_bs, p.OB, TC_BM);
       if (rc) return rc;
     }
-    const size_t psmem = 1024 + pp.ring_bytes + 2 * (size_t)pp.nsb * pp.stg_bytes + (size_t)rows_bytes;
-    tc_linear_persist_kernel<<<sms, PL_THREADS, psmem, (cudaStream_t)stream>>>(tmx, tmw, tmy, tmr, pp);
+    const size_t psmem = 1024 + pp.ring_bytes + (size_t)pp.ng * pp.nsb * pp.stg_bytes + (size_t)rows_bytes;
+    if (pp.ng == 3) tc_linear_persist_kernel<3><<<sms, 64 + 3 * 256, psmem, (cudaStream_t)stream>>>(tmx, tmw, tmy, tmr, pp);
+    else tc_linear_persist_kernel<2><<<sms, 64 + 2 * 256, psmem, (cudaStream_t)stream>>>(tmx, tmw, tmy, tmr, pp);
     return check_launch("linear_tc(persistent)");
   }
   dim3 grid((unsigned)ceil_div64(a->M, TC_BM), a->N / p.BN, a->batch);
