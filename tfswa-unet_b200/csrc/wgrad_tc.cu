@@ -26,7 +26,11 @@ namespace wgtc {
 constexpr int MAX_TOK = 256;            // tokens per stage: 64 / 128 / 256, chosen per shape so that a stage is 32-48 KB
 constexpr int NT = 128;                 // output rows (n) per CTA = UMMA M
 constexpr int STAGES = 4;
-constexpr int THREADS = 192;            // warp 0: TMA, warp 1: MMA issue + TMEM alloc, warps 2-5: prologue transform + epilogue
+#ifndef TFSWA_WGTC_TW
+#define TFSWA_WGTC_TW 8
+#endif
+constexpr int TW = TFSWA_WGTC_TW;       // transform / epilogue warps (a multiple of 4)
+constexpr int THREADS = 64 + TW * 32;   // warp 0: TMA, warp 1: MMA issue + TMEM alloc, warps 2-9: prologue transform + epilogue
 
 struct Params {
   const float* row_stats;               // (M, 2) per batch: (mean, rstd) per token (PRO_LNHAT) or nullptr
@@ -80,7 +84,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant_
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tm_g); prefetch_tmap(&tm_x);
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_ready[s], 4); mbar_init(&bar_empty[s], 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_ready[s], TW); mbar_init(&bar_empty[s], 1); }
     mbar_init(&bar_acc, 1);
     fence_barrier_init();
   }
@@ -131,17 +135,19 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant_
       umma_commit(&bar_acc);                 // accumulators complete
     }
   } else {
-    const int et = tid - 64;                 // 0..127: transform / epilogue threads; warp % 4 selects the TMEM lane quarter
+    constexpr int ET = TW * 32;
+    const int et = tid - 64;                 // 0..ET-1: transform / epilogue threads; warp % 4 selects the TMEM lane quarter
     if (lnhat) {
       // ---------------- LayerNorm prologue on the X boxes, in place: x <- (x - mean_m) * rstd_m (0 beyond M) ----------------
       // (mean, rstd) of the tokens of chunk c + 2 are fetched with 4-byte cp.async while chunk c is transformed: a plain
       // load after the TMA barrier put a global-memory latency on every stage's critical path (1.5 TB/s instead of 3+)
       const float* rs = p.row_stats + (int64_t)zb * p.rs_bs;
       const uint32_t rowb = (uint32_t)p.cbX * 2;                     // bytes per token row inside a box
-      const uint32_t chunks_per_row = rowb / 16, chunks = x_bytes / 16;
+      const uint32_t cpr_shift = rowb == 128 ? 3u : 2u, chunks = x_bytes / 16;     // 16-byte chunks per token row: 8 or 4; TOK is 64 or 128
+      const uint32_t tok_mask = (uint32_t)TOK - 1u;
       auto prefetch = [&](int c) {
         if (c < nchunks) {
-          for (int row = et; row < TOK; row += 128) {
+          for (int row = et; row < TOK; row += ET) {
             int64_t mm = m_begin + (int64_t)c * TOK + row;
             if (mm >= p.M) mm = p.M - 1;                             // (value unused: the row is zeroed)
             asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(&s_rs[c % STAGES][row])), "l"(rs + 2 * mm) : "memory");
@@ -154,12 +160,13 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant_
         const int s = c % STAGES;
         prefetch(c + 2);
         asm volatile("cp.async.wait_group 2;" ::: "memory");         // chunk c's statistics have landed (this thread's copies) ...
-        asm volatile("bar.sync 1, 128;" ::: "memory");               // ... and everybody else's
+        asm volatile("bar.sync 1, %0;" ::"n"(ET) : "memory");         // ... and everybody else's
         mbar_wait(&bar_full[s], (c / STAGES) & 1);
         uint8_t* xs = sm + (size_t)s * stage_bytes + A_BYTES;
         const int64_t m = m_begin + (int64_t)c * TOK;
-        for (uint32_t i = et; i < chunks; i += 128) {
-          const uint32_t row = (i / chunks_per_row) % TOK;           // token inside the box (swizzle permutes chunks within a row only)
+        for (uint32_t i = et; i < chunks; i += ET) {
+          const uint32_t row = (i >> cpr_shift) & tok_mask;          // token inside the box (swizzle permutes chunks within a row only; no divisions here:
+                                                                     // with `/ chunks_per_row % TOK` this loop was the kernel's bottleneck, 3100 cycles per stage)
           uint4* ptr = reinterpret_cast<uint4*>(xs + (size_t)i * 16);
           uint4 v = *ptr;
           if (m + row < p.M) {
@@ -189,7 +196,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant_
     const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
     if (nchunks > 0) {
       float* dwrow = p.dw + (int64_t)zb * p.w_bs + (int64_t)n * p.K + k0;
-      for (int c0 = 0; c0 < bkw; c0 += 16) {
+      const int whalf = (warp - 2) >> 2;       // the TW / 4 warps of a lane quarter take alternate 16-column chunks
+      for (int c0 = whalf * 16; c0 < bkw; c0 += (TW / 4) * 16) {
         uint32_t raw[16];
         __syncwarp();
         tmem_ld_x16(lane_addr + c0, raw);
@@ -199,7 +207,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant_
           for (int j = 0; j < 16; ++j) atomicAdd(dwrow + c0 + j, __uint_as_float(raw[j]));
         }
       }
-      if (want_bias) {
+      if (want_bias && whalf == 0) {
         uint32_t raw[16];
         __syncwarp();
         tmem_ld_x16(lane_addr + 256, raw);
