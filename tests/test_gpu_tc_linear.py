@@ -73,6 +73,93 @@ def test_tc_linear_matches_reference(M, nb, K, N, ln, gelu, use_r1, use_r2):
     assert err2 <= 1e-2 * scale + 1e-3, f"tc vs simt {err2:.3e}"
 
 
+# the PERSISTENT kernel is dispatched when every SM gets at least two tiles (148 SMs: >= 296 tiles of 128 rows x BN columns); wide
+# erf-GELU epilogues (N > K) stay on the one-tile-per-CTA kernel.  (M, nb, K, N, ln, gelu, r1, r2)
+PERSISTENT_CASES = [
+    (40000, 1, 32, 32, False, False, False, False),     # BN = 32: three epilogue groups, one n-tile, interleaved walk
+    (40001, 3, 32, 32, False, False, True, False),      # residual tile through TMA into the staging buffer, ragged last row block, batch 3
+    (20000, 3, 128, 32, False, False, True, False),     # fc2 + residual: 2 k-blocks, bias rows reloaded per batch entry
+    (30000, 1, 96, 32, False, True, True, True),        # fusion conv: GELU with N < K, both residual paths (r1 by TMA, r2 by loads)
+    (160000, 1, 32, 288, True, False, False, False),    # BN = 96, three n-tiles, LayerNorm algebra, ROW-MAJOR walk (>= 8 row blocks per SM)
+    (20000, 1, 64, 576, True, False, False, False),     # BN = 64 / 192-column split, interleaved walk with several n-tiles
+    (8000, 1, 128, 1152, True, False, False, False),    # BN = 128: two groups at 96 registers, 9 n-tiles
+    (9000, 3, 512, 128, False, False, True, False),     # 8 k-blocks per tile through a 4-stage ring
+    (5000, 1, 256, 2304, True, False, False, False),    # 18 n-tiles, bias rows of 2304 columns in shared memory
+]
+
+
+@pytest.mark.parametrize("M,nb,K,N,ln,gelu,use_r1,use_r2", PERSISTENT_CASES)
+def test_tc_linear_persistent_kernel_matches_reference(M, nb, K, N, ln, gelu, use_r1, use_r2):
+    from tfswa_unet_b200 import ops, _lib as L
+    dev = "cuda"
+    g = torch.Generator(device=dev).manual_seed(7)
+    x = (torch.randn((M, nb, K), device=dev, generator=g) + 0.3).to(torch.bfloat16)
+    w = torch.randn((nb, N, K), device=dev, generator=g) / K ** 0.5
+    wb = w.to(torch.bfloat16).contiguous()
+    wsum = wb.float().sum(-1).contiguous()
+    b = 0.1 * torch.randn((nb, N), device=dev, generator=g)
+    r1 = torch.randn((M, 1, N), device=dev, generator=g).to(torch.bfloat16) if use_r1 else None     # broadcast over nb
+    r2 = torch.randn((M, nb, N), device=dev, generator=g).to(torch.bfloat16) if use_r2 else None
+    st = ops.row_stats(x) if ln else None
+    ops.reset_launch_count()
+    y = ops.linear_tc(x, wb, wsum, b, prologue=L.PRO_LNHAT if ln else 0, epilogue=L.EPI_GELU if gelu else 0, row_stats=st,
+                      r1=r1, r2=r2)
+    ref = _ref(x, wb.float(), b, st, gelu, r1, r2, ln)
+    torch.cuda.synchronize()
+    # every row block and every column block: relative L2 per 4096-row band (a dropped or duplicated tile shows up as O(1))
+    for m0 in range(0, M, 4096):
+        a, r = y[m0:m0 + 4096].float(), ref[m0:m0 + 4096]
+        assert float((a - r).norm() / r.norm()) <= 6e-3, m0
+    err = float((y.float() - ref).abs().max())
+    scale = float(ref.abs().max())
+    assert err <= 1e-2 * scale + 1e-3, f"tc_linear(persistent) err {err:.3e} vs scale {scale:.3e}"
+
+
+def test_tc_linear_persistent_is_the_kernel_that_runs():
+    """large problems really go through tc_linear_persist_kernel (<3> for narrow tiles, <2> for 96-128-column tiles), and
+    TFSWA_LINEAR_KERNEL=v1 really selects the one-tile-per-CTA kernel; both give the same bits (same arithmetic per element)"""
+    import subprocess, sys, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import torch, sys; sys.path.insert(0, %r)\n"
+            "from tfswa_unet_b200 import ops\n"
+            "torch.manual_seed(0)\n"
+            "x = torch.randn(40000, 1, 32, device='cuda').bfloat16()\n"
+            "wa = (torch.randn(1, 32, 32, device='cuda') / 6).bfloat16(); wb = (torch.randn(1, 288, 32, device='cuda') / 6).bfloat16()\n"
+            "r1 = torch.randn(40000, 1, 32, device='cuda').bfloat16()\n"
+            "from torch.profiler import profile, ProfilerActivity\n"
+            "with profile(activities=[ProfilerActivity.CUDA]) as prof:\n"
+            "    ya = ops.linear_tc(x, wa, None, None, r1=r1); yb = ops.linear_tc(x, wb, None, None); torch.cuda.synchronize()\n"
+            "print('KERNELS', [e.key for e in prof.key_averages()])\n"
+            "print('SUMS', float(ya.float().sum()), float(yb.float().sum()), float(ya.float().abs().sum()), float(yb.float().abs().sum()))\n" % root)
+    outs = {}
+    for mode in ("", "v1"):
+        env = dict(os.environ, TFSWA_LINEAR_KERNEL=mode)
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs[mode] = r.stdout
+    assert "tc_linear_persist_kernel<3>" in outs[""] and "tc_linear_persist_kernel<2>" in outs[""], outs[""][-1500:]
+    assert "tc_linear_persist_kernel" not in outs["v1"] and "tc_linear_kernel" in outs["v1"], outs["v1"][-1500:]
+    sums = {m: [l for l in o.splitlines() if l.startswith("SUMS")][0] for m, o in outs.items()}
+    assert sums[""] == sums["v1"], sums
+
+
+def test_tc_linear_persistent_column_sums():
+    """train-mode BatchNorm sums from the persistent kernel's staged tiles (M large enough for the persistent path)"""
+    from tfswa_unet_b200 import ops
+    dev = "cuda"
+    M, K, N = 50000, 96, 32
+    g = torch.Generator(device=dev).manual_seed(9)
+    x = torch.randn((M, 1, K), device=dev, generator=g).to(torch.bfloat16)
+    wb = (torch.randn((1, N, K), device=dev, generator=g) / K ** 0.5).to(torch.bfloat16)
+    b = 0.1 * torch.randn((1, N), device=dev, generator=g)
+    stats = torch.zeros((2, N), dtype=torch.float32, device=dev)
+    y = ops.linear_tc(x, wb, None, b, col_stats=stats)
+    torch.cuda.synchronize()
+    yf = y.float().reshape(M, N)
+    assert torch.allclose(stats[0], yf.sum(0), rtol=2e-4, atol=2e-2)
+    assert torch.allclose(stats[1], (yf * yf).sum(0), rtol=2e-4, atol=2e-2)
+
+
 def test_tc_linear_strided_slab_views():
     """x / y / r address column slabs of wider buffers (the (M,3,C) concat buffer and the (M,9C) qkv buffer)."""
     from tfswa_unet_b200 import ops
