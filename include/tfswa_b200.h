@@ -39,6 +39,8 @@ extern "C" {
 /* epilogue */
 #define TFSWA_EPI_NONE 0
 #define TFSWA_EPI_GELU 1
+#define TFSWA_EPI_MUL_DGELU 2   /* tfswa_linear_tc_fwd only: y = (acc + bias) * gelu'(r1) - the backward of GELU fused into the data-gradient GEMM
+                                 * of the layer above (r1 = the saved pre-activation, same shape as y; r2 must be NULL) */
 
 /* attention geometries */
 #define TFSWA_GEOM_TSA 0     /* sequences along H (reference dim 2), one per (b, w)   attention.py:143 */

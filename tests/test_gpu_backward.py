@@ -151,3 +151,51 @@ def test_unet_backward_golden(golden, name, precision):
         for k, v in case["buffers"].items():
             assert_close(f"{name}.{k}", bufs[k].float(), v.float(), 2e-4 if precision == "fp32" else 3e-2,
                          atol=0.0 if precision == "fp32" else 2e-3)
+
+
+@pytest.mark.parametrize("M,nb,C,r1_nb", [(3000, 3, 32, 1), (50000, 3, 32, 1), (40000, 1, 64, 1), (9000, 3, 128, 3)])
+def test_fused_gelu_backward_matches_two_node_form_and_torch(M, nb, C, r1_nb):
+    """fc2 over GELU(u): the one-node form whose data-gradient GEMM multiplies by gelu'(u) in its epilogue (TFSWA_EPI_MUL_DGELU;
+    large M: persistent kernel with u arriving as the residual tile, small M: one-tile kernel) against the GeluFn + LinearFn pair
+    and against torch autograd in fp32 on the same bf16-rounded inputs (attention.py:121-128)."""
+    import torch.nn.functional as TF
+    from tfswa_unet_b200 import functional as Fn
+    dev = "cuda"
+    g = torch.Generator(device=dev).manual_seed(5)
+    u0 = torch.randn((M, nb, 4 * C), device=dev, generator=g).to(torch.bfloat16)
+    w0 = torch.randn((nb, C, 4 * C), device=dev, generator=g) / (4 * C) ** 0.5
+    b0 = 0.1 * torch.randn((nb, C), device=dev, generator=g)
+    r0 = torch.randn((M, r1_nb, C), device=dev, generator=g).to(torch.bfloat16)
+    dy = torch.randn((M, nb, C), device=dev, generator=g).to(torch.bfloat16)
+    res = {}
+    for fused in (True, False):
+        Fn.USE_FUSED_GELU_BWD = fused
+        try:
+            u = u0.clone().requires_grad_(True)
+            w = w0.clone().requires_grad_(True)
+            b = b0.clone().requires_grad_(True)
+            r = r0.clone().requires_grad_(True)
+            y = Fn.gelu_linear(u, Fn.LinW(w, b), r1=r)
+            y.backward(dy)
+            res[fused] = (y.detach().float(), u.grad.float(), w.grad.float(), b.grad.float(), r.grad.float())
+        finally:
+            Fn.USE_FUSED_GELU_BWD = True
+    # torch reference (fp32 math on the bf16 inputs; h rounded to bf16 as both product forms store it)
+    u = u0.float().requires_grad_(True)
+    w = w0.to(torch.bfloat16).float().requires_grad_(True)
+    b = b0.clone().requires_grad_(True)
+    r = r0.float().requires_grad_(True)
+    h = TF.gelu(u)
+    y = torch.einsum("mbk,bnk->mbn", h, w) + b[None] + r
+    y.backward(dy.float())
+    ref = (y.detach(), u.grad, w.grad, b.grad, r.grad)
+    names = ("y", "du", "dw", "db", "dr1")
+    for i, n in enumerate(names):
+        a, t, rr = res[True][i], res[False][i], ref[i]
+        rel_pair = float((a - t).norm() / t.norm())
+        rel_ref = float((a - rr).norm() / rr.norm())
+        # du: one bf16 rounding in the fused form, two in the pair (dh is rounded before the GELU gradient multiplies it)
+        assert rel_pair <= (6e-3 if n == "du" else 1e-5), (n, rel_pair)
+        assert rel_ref <= 8e-3, (n, rel_ref)
+    # the fused form is the more accurate one for du
+    assert float((res[True][1] - ref[1]).norm()) <= 1.05 * float((res[False][1] - ref[1]).norm())

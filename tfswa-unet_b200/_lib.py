@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libtfswa_b200.so")
 
 F32, BF16 = 0, 1
 PRO_NONE, PRO_LNHAT, PRO_GELU, PRO_AFFINE = 0, 1, 2, 4
-EPI_NONE, EPI_GELU = 0, 1
+EPI_NONE, EPI_GELU, EPI_MUL_DGELU = 0, 1, 2
 GEOM_TSA, GEOM_FSA, GEOM_SWA = 0, 1, 2
 
 _i64, _i32, _p, _f = C.c_int64, C.c_int32, C.c_void_p, C.c_float

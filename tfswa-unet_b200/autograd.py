@@ -103,6 +103,41 @@ class GeluFn(torch.autograd.Function):
         return ops.act_bwd(_contig(dh), u, 0)
 
 
+class GeluLinearFn(torch.autograd.Function):
+    """y = GELU(u) W^T + b (+ r1) as ONE node (bf16 training path of the MLP: attention.py:121-128 - fc2 over the activated hidden
+    tensor).  Forward = the same two kernels as GeluFn + LinearFn; the point is the backward: dL/du = (g W) * gelu'(u) comes out of
+    the data-gradient GEMM's epilogue (TFSWA_EPI_MUL_DGELU, the saved pre-activation u arrives as the GEMM's residual tile), so the
+    4C-wide dL/dh never goes to HBM and back and the separate GELU-backward launch disappears."""
+    @staticmethod
+    def forward(ctx, u, w, bias, r1):
+        w = _contig(w.detach())
+        b = None if bias is None else _contig(bias.detach())
+        h = ops.affine_act(u, None, None, epilogue=L.EPI_GELU)
+        y = _matmul(h, w, b, r1=r1)
+        ctx.cfg = (bias is not None, None if r1 is None else r1.shape[1], u.shape[1])
+        ctx.save_for_backward(u, h, w)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        u, h, w = ctx.saved_tensors
+        has_bias, r1_nb, nb = ctx.cfg
+        g = _contig(dy)
+        dr1 = None
+        if r1_nb is not None and ctx.needs_input_grad[3]:
+            dr1 = ops.sum_batch(g) if (r1_nb == 1 and nb > 1) else g
+        dw = db = du = None
+        if ctx.needs_input_grad[1] or (has_bias and ctx.needs_input_grad[2]):
+            dw, db = ops.linear_wgrad(h, g, want_bias=has_bias)
+        if ctx.needs_input_grad[0]:
+            wt = w.transpose(1, 2).contiguous()                      # (nb, K, N): dh = g @ W
+            if _tc_ok(g, wt.shape[1], wt.shape[2]) and u.is_contiguous():
+                du = ops.linear_tc(g, wt.to(torch.bfloat16).contiguous(), None, None, epilogue=L.EPI_MUL_DGELU, r1=u)
+            else:
+                du = ops.act_bwd(_matmul(g, wt, None), u, 0)
+        return du, dw, db, dr1
+
+
 class AttentionFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, qkv, pad_kv, rel_bias, B, H, W, C, heads, geom, ws, shift, use_shift_mask):

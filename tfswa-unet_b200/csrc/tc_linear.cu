@@ -205,12 +205,21 @@ __global__ void __launch_bounds__(TC_THREADS) tc_linear_kernel(const __grid_cons
       if (row_ok) {
       if (r1row) {
         float t[8];
-        load8(r1row + c, t);
+        if (p.epilogue == TFSWA_EPI_MUL_DGELU) {       // r1 = saved pre-activation: dL/dpre = dL/dh * gelu'(pre)
+          load8(r1row + c, t);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] += t[j];
-        load8(r1row + c + 8, t);
+          for (int j = 0; j < 8; ++j) v[j] *= gelu_erf_grad_fast(t[j]);
+          load8(r1row + c + 8, t);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[8 + j] += t[j];
+          for (int j = 0; j < 8; ++j) v[8 + j] *= gelu_erf_grad_fast(t[j]);
+        } else {
+          load8(r1row + c, t);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] += t[j];
+          load8(r1row + c + 8, t);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[8 + j] += t[j];
+        }
       }
       if (r2row) {
         float t[8];
@@ -502,8 +511,13 @@ __global__ void __launch_bounds__(64 + NG * 256, 1) tc_linear_persist_kernel(con
           if (pp.has_r1) {                             // the residual tile was loaded into this very position by TMA
             float tt[8];
             load8(dst, tt);
+            if (p.epilogue == TFSWA_EPI_MUL_DGELU) {   // ... or the saved pre-activation: dL/dpre = dL/dh * gelu'(pre)
 #pragma unroll
-            for (int j = 0; j < 8; ++j) o8[j] += tt[j];
+              for (int j = 0; j < 8; ++j) o8[j] *= gelu_erf_grad_fast(tt[j]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) o8[j] += tt[j];
+            }
           }
           store8(dst, o8);
         }
@@ -596,6 +610,8 @@ extern "C" int tfswa_linear_tc_fwd(const tfswa_linear_args* a, const void* w_bf1
   TFSWA_REQUIRE(a->prologue == TFSWA_PRO_NONE || a->prologue == TFSWA_PRO_LNHAT, "linear_tc: prologue %d unsupported", a->prologue);
   TFSWA_REQUIRE(a->prologue != TFSWA_PRO_LNHAT || (a->row_stats && wsum), "linear_tc: LN needs row_stats and wsum");
   TFSWA_REQUIRE(!a->pre, "linear_tc: the pre-activation output is not produced by this kernel");
+  TFSWA_REQUIRE(a->epilogue == TFSWA_EPI_NONE || a->epilogue == TFSWA_EPI_GELU || a->epilogue == TFSWA_EPI_MUL_DGELU, "linear_tc: epilogue %d unsupported", a->epilogue);
+  TFSWA_REQUIRE(a->epilogue != TFSWA_EPI_MUL_DGELU || (a->r1 && !a->r2 && !a->col_stats), "linear_tc: TFSWA_EPI_MUL_DGELU needs r1 (the pre-activation) and no r2 / col_stats");
   TFSWA_REQUIRE(!a->col_stats || (a->batch == 1 && a->epilogue == TFSWA_EPI_NONE && !a->r1 && !a->r2),
                 "linear_tc: col_stats needs batch 1 and a plain epilogue (the statistics are those of the stored tensor)");
   TFSWA_REQUIRE(a->ldy % 8 == 0 && a->y_bs % 8 == 0 && a->ldx % 8 == 0 && a->x_bs % 8 == 0, "linear_tc: 16-byte alignment of ld/strides");

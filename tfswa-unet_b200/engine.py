@@ -132,7 +132,7 @@ def _mlp(y: Tensor, fc1, fc2) -> Tensor:
         u = Fn.linear(y, fc1, prologue=L.PRO_LNHAT, row_stats=st2)
         if Fn.USE_TC and y.dtype == torch.bfloat16:
             # bf16: GELU as its own node so that fc2 (forward, dgrad, wgrad) stays on the tensor-core kernels
-            return Fn.linear(Fn.gelu(u), fc2, r1=y)
+            return Fn.gelu_linear(u, fc2, r1=y)
         return Fn.linear(u, fc2, prologue=L.PRO_GELU, r1=y)
     h = Fn.linear(y, fc1, prologue=L.PRO_LNHAT, epilogue=L.EPI_GELU, row_stats=st2)
     return Fn.linear(h, fc2, r1=y)

@@ -97,6 +97,18 @@ def gelu(u: Tensor) -> Tensor:
     return ops.affine_act(u, None, None, epilogue=L.EPI_GELU)
 
 
+USE_FUSED_GELU_BWD = True   # training, bf16: GELU backward inside fc2's data-gradient GEMM (False: GeluFn + LinearFn, for A/B tests)
+
+
+def gelu_linear(u: Tensor, lw: LinW, *, r1: Optional[Tensor] = None) -> Tensor:
+    """GELU(u) W^T + b (+ r1): fc2 over the pre-activation u of fc1.  One autograd node whose backward fuses the GELU gradient
+    into the data-gradient GEMM; without autograd (or with the switch off) the two-step form."""
+    if USE_FUSED_GELU_BWD and USE_TC and u.dtype == torch.bfloat16 and _needs_grad(u, lw.w, lw.b, r1):
+        from .autograd import GeluLinearFn
+        return GeluLinearFn.apply(u, lw.w, lw.b, r1)
+    return linear(gelu(u), lw, r1=r1)
+
+
 USE_FUSED_TAIL = True   # one kernel for proj + residual + LN + MLP + residual at C in {32, 64, 128} (inference, bf16)
 FUSED_TAIL_WIDTHS = (32, 64, 128)
 
