@@ -146,10 +146,15 @@ int tfswa_attn_fwd(const tfswa_attn_args* a, void* stream);
 int64_t tfswa_attn_tc_scratch_bytes(const tfswa_attn_args* a);
 int tfswa_attn_tc_fwd(const tfswa_attn_args* a, void* scratch, int64_t scratch_bytes, void* stream);
 
-/* SW-MSA (8x8 windows, attention.py:347-403) with scores and probabilities held in registers: warp-level tensor-core
- * MMAs (m16n8k16, bf16 in / fp32 accumulate), exact row maxima, no shared-memory round trip for S or P.  bf16 only;
- * head_dim in {4,8,16,32}; the default-off mask / relative-bias features are served by tfswa_attn_fwd. */
+/* SW-MSA (8x8 windows, attention.py:347-403), bf16, default-off mask / relative-bias features excluded (they are served
+ * by tfswa_attn_fwd).  head_dim 4 and 8: the windows whose 64 tokens exist and do not wrap around the rolled frame run
+ * on tcgen05 - one TMA box (8 channels, 8, 8, 1) of the q|k|v token matrix is a window's K (K-major) and V (MN-major)
+ * operand, two heads of a window fill the 128-row tile through a masked copy of Q, exact row maxima (one thread per
+ * row), P in TMEM, the denominator through a ones tile; the bottom / right fringe (pad / wrap-around) and head_dim
+ * 16 / 32 run on warp-level MMAs (m16n8k16) with scores and probabilities in registers.
+ * tfswa_attn_win_tc_interior_launches: diagnostics - how many tcgen05 interior launches this process has made. */
 int tfswa_attn_win_tc_fwd(const tfswa_attn_args* a, void* stream);
+long long tfswa_attn_win_tc_interior_launches(void);
 
 /* ---- convolutions (implicit GEMM over NHWC) ---------------------------------------------------
  * kind: 0 = 3x3 s1 p1 (output_head.0, tfswa_unet.py:140), 1 = 4x4 s2 p1 (DownsampleBlock, blocks.py:157),

@@ -1,6 +1,7 @@
-"""GPU (-m gpu): register-resident SW-MSA window attention (tfswa_attn_win_tc_fwd, warp-level MMAs) against the fp32-math
-SIMT kernel on the same bf16 q|k|v AND against a torch fp32 restatement of attention.py:358-401, for every head_dim of the
-model, padded windows and cyclic shift."""
+"""GPU (-m gpu): SW-MSA window attention (tfswa_attn_win_tc_fwd: tcgen05 + TMA for the interior windows at head_dim 4 / 8,
+warp-level MMAs for the pad / wrap-around fringe and head_dim 16 / 32) against the fp32-math SIMT kernel on the same bf16
+q|k|v AND against a torch fp32 restatement of attention.py:358-401, for every head_dim of the model, padded windows and
+cyclic shift."""
 import pytest
 import torch
 
@@ -37,10 +38,16 @@ def _ref_windows(qkv, B, H, W, C, heads, ws, shift, pad_kv):
     (1, 16, 24, 128, 4), (1, 9, 17, 128, 0),          # head_dim 16, two channel slabs
     (1, 16, 8, 256, 4), (2, 13, 9, 256, 0),           # head_dim 32
     (1, 40, 16, 64, 4),                               # heads = 16 -> head_dim 4 with a 64-channel slab
+    # shapes with many interior windows (tcgen05 + TMA path): > 8 items per persistent CTA (the published-item ring wraps),
+    # odd interior widths (head_dim 8 pairs windows: the last pair has one), no fringe at all, fringe only on one side
+    (2, 200, 264, 32, 4), (1, 129, 101, 32, 0), (1, 64, 64, 32, 0), (1, 68, 33, 32, 4),
+    (2, 100, 93, 64, 4), (1, 259, 131, 64, 0), (1, 48, 24, 64, 0), (3, 28, 20, 64, 4),
+    (1, 96, 72, 64, 4),                               # heads = 16 -> head_dim 4, four quads
 ])
 def test_window_attention_matches_simt(B, H, W, C, shift):
-    from tfswa_unet_b200 import ops
-    heads = 16 if (C, H) == (64, 40) else 8
+    from tfswa_unet_b200 import ops, _lib
+    heads = 16 if (C, H) in ((64, 40), (64, 96)) else 8
+    tc_before = _lib.lib().tfswa_attn_win_tc_interior_launches()
     M = B * H * W
     big = seeded((M, 9 * C), 31, 1.5).cuda().to(torch.bfloat16)
     qkv = big[:, 6 * C:9 * C]                                     # the SW-MSA slab of a fused 9C-wide qkv buffer
@@ -59,6 +66,9 @@ def test_window_attention_matches_simt(B, H, W, C, shift):
     finally:
         ops.enable_timing(False)
     assert tags and tags[0].startswith("attn_tc[swa"), tags     # the tensor-core window kernel really ran
+    interior = ((H - shift) // 8) * ((W - shift) // 8)
+    want_tc = 1 if (C // heads in (4, 8) and interior > 0) else 0   # ... and its tcgen05 form wherever an interior window exists
+    assert _lib.lib().tfswa_attn_win_tc_interior_launches() - tc_before == want_tc
     ops.USE_TC_ATTENTION = False
     try:
         ops.attention(qkv, out_s, B, H, W, C, heads, 2, ws=8, shift=shift, pad_kv=pad_kv, lse=lse_s)

@@ -76,6 +76,7 @@ SIGNATURES = {
     "tfswa_attn_tc_scratch_bytes": (C.c_int64, [C.POINTER(AttnArgs)]),
     "tfswa_attn_tc_fwd": (C.c_int, [C.POINTER(AttnArgs), _p, _i64, _p]),
     "tfswa_attn_win_tc_fwd": (C.c_int, [C.POINTER(AttnArgs), _p]),
+    "tfswa_attn_win_tc_interior_launches": (C.c_longlong, []),
     "tfswa_conv_fwd": (C.c_int, [C.POINTER(ConvArgs), _p]),
     "tfswa_conv_tc_fwd": (C.c_int, [C.POINTER(ConvArgs), _p, _p]),
     "tfswa_stem_fwd": (C.c_int, [_p, _p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p]),

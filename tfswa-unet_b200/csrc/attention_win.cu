@@ -12,6 +12,7 @@
 // map (roll + pad are index arithmetic; zero-padded tokens are real keys whose k|v equal the folded qkv bias
 // `pad_kv`) into padded shared-memory rows (pitch = slab + 8 elements: conflict-free fragment loads and ldmatrix).
 #include "attn_common.cuh"
+#include <stdlib.h>
 
 namespace tfswa {
 
@@ -64,7 +65,19 @@ __global__ void __launch_bounds__(WIN_THREADS) attn_win_mma_kernel(const AttnPar
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
-  const int win = blockIdx.x, ch0 = blockIdx.y * CS;
+  int win = blockIdx.x;
+  const int ch0 = blockIdx.y * CS;
+  if (p.win_edge) {
+    // fringe windows only (the interior ran on tc_attn_win.cu): per image first the window rows below the interior, then
+    // the columns right of it
+    const int nb = (p.nWh - p.nWh_int) * p.nWw, nr = p.nWw - p.nWw_int;
+    const int per_img = nb + p.nWh_int * nr;
+    const int b = win / per_img, e = win - b * per_img;
+    int wh, ww;
+    if (e < nb) { wh = p.nWh_int + e / p.nWw; ww = e - (e / p.nWw) * p.nWw; }
+    else { const int e2 = e - nb; wh = e2 / nr; ww = p.nWw_int + (e2 - wh * nr); }
+    win = (b * p.nWh + wh) * p.nWw + ww;
+  }
   const bf16* qkv = (const bf16*)p.qkv;
 
   if (tid < WIN_TOK) {
@@ -216,8 +229,23 @@ extern "C" int tfswa_attn_win_tc_fwd(const tfswa_attn_args* a, void* stream) {
   attn_fill_geometry(p);
   TFSWA_REQUIRE((p.Hp == a->H && p.Wp == a->W) || a->pad_kv, "attn_win_tc: padded windows need pad_kv");
   const int CS = p.C >= 64 ? 64 : 32;
-  dim3 grid((unsigned)(p.B * p.nWh * p.nWw), p.C / CS, 1);
   cudaStream_t st = (cudaStream_t)stream;
+  int64_t n_win = (int64_t)p.B * p.nWh * p.nWw;
+  // head_dim 4 / 8: the windows whose 64 tokens exist and do not wrap around the rolled frame run on tcgen05 with TMA-fed
+  // operands (tc_attn_win.cu); this kernel keeps the bottom / right fringe.  TFSWA_WIN_KERNEL=mma: everything here (A/B, tests)
+  static int force_mma = -1;
+  if (force_mma < 0) { const char* e = getenv("TFSWA_WIN_KERNEL"); force_mma = (e && e[0] == 'm') ? 1 : 0; }
+  if (!force_mma && (D == 4 || D == 8)) {
+    const int nWh_int = (p.H - p.shift) / p.ws, nWw_int = (p.W - p.shift) / p.ws;
+    const int rc = attn_win_tc_bf16(p, nWh_int, nWw_int, st);
+    if (rc < 0 || rc > 1) return rc;
+    if (rc == 0) {
+      p.win_edge = 1; p.nWh_int = nWh_int; p.nWw_int = nWw_int;
+      n_win = (int64_t)p.B * ((int64_t)p.nWh * p.nWw - (int64_t)nWh_int * nWw_int);
+      if (n_win == 0) return TFSWA_OK;
+    }
+  }
+  dim3 grid((unsigned)n_win, p.C / CS, 1);
 #define TFSWA_WIN_CASE(d, cs) if (D == d && CS == cs) { attn_win_mma_kernel<d, cs><<<grid, WIN_THREADS, 0, st>>>(p); return check_launch("attn_win_tc"); }
   TFSWA_WIN_CASE(4, 32) TFSWA_WIN_CASE(4, 64) TFSWA_WIN_CASE(8, 32) TFSWA_WIN_CASE(8, 64)
   TFSWA_WIN_CASE(16, 32) TFSWA_WIN_CASE(16, 64) TFSWA_WIN_CASE(32, 64)

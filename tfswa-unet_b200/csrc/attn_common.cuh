@@ -24,6 +24,7 @@ struct AttnParams {
   int B, H, W, C, heads;
   int geom, ws, shift, use_shift_mask;
   int Hp, Wp, nWh, nWw;
+  int win_edge, nWh_int, nWw_int;   // SW-MSA: blockIdx.x enumerates only the windows outside the interior [0, nWh_int) x [0, nWw_int)
   int q_begin, q_end;   // axial kernels: queries [q_begin, q_end) of every sequence (q_end = 0 means the whole sequence)
   float qscale;   // head_dim^-0.5 * log2(e)
   float* kext;     // tc attention: per-sequence per-channel min/max of k (scratch, (rows, 2, C) fp32)
@@ -41,6 +42,9 @@ int attn_axial_mma_bf16(const AttnParams& p, cudaStream_t st);
 // attn_axial_tma_work_bytes(p) bytes (redo list of the exact pass)
 int64_t attn_axial_tma_work_bytes(const AttnParams& p);
 int attn_axial_tma_bf16(const AttnParams& p, void* work, cudaStream_t st);
+// SW-MSA on tcgen05 + TMA for the interior windows [0, nWh_int) x [0, nWw_int) (tc_attn_win.cu, head_dim 4 / 8); returns 1
+// when the shape is not covered (nothing launched)
+int attn_win_tc_bf16(const AttnParams& p, int nWh_int, int nWw_int, cudaStream_t st);
 // bf16 axial attention backward on warp-level MMAs (attention_bwd_mma.cu); returns 1 when the shape is not covered
 int attn_bwd_mma_bf16(const AttnParams& p, cudaStream_t st);
 

@@ -44,6 +44,7 @@
 // per-tile bookkeeping per exponential), MUFU only (10.4), polynomial share 1/2 (9.9) and 1/4 (9.5).
 // Replaces attention.py:70-85 (+ permutes :143,:162,:217,:236), bf16 activations.
 #include "attn_common.cuh"
+#include "attn_tc_math.cuh"
 #include "sm100.cuh"
 #include <stdlib.h>
 
@@ -81,57 +82,12 @@ template <int D> __host__ __device__ constexpr int smem_bytes() { return tail_of
 #endif
 constexpr int POLY_K = TFSWA_TMA_POLY_K;   // every POLY_K-th element PAIR takes the polynomial (0 = MUFU only); -D for A/B builds
 
-__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-
-// kind::f16 instruction descriptor with a K-major A and an MN-major B operand (bit 16)
-__device__ __forceinline__ uint32_t idesc_bf16_bmn(uint32_t M, uint32_t N) { return umma_idesc_bf16(M, N) | (1u << 16); }
-
-__device__ __forceinline__ float ex2_f32(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) { uint32_t y; asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(y) : "f"(hi), "f"(lo)); return y; }
-__device__ __forceinline__ uint64_t pk2(float a, float b) { uint64_t r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
-__device__ __forceinline__ uint64_t pk2u(uint32_t a, uint32_t b) { uint64_t r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "r"(a), "r"(b)); return r; }
-__device__ __forceinline__ void up2(uint64_t r, float& a, float& b) { asm("mov.b64 {%0,%1}, %2;" : "=f"(a), "=f"(b) : "l"(r)); }
-__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) { uint64_t d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
-__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) { uint64_t d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
-__device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) { uint64_t d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
-
-// 2^x for a pair of x <= 0 on the FMA / ALU pipes: x = n + r (round to nearest through the 1.5 * 2^23 trick), degree-3
-// minimax polynomial of 2^r on [-0.5, 0.5] (7.5e-5 relative - P is rounded to bf16, 3.9e-3), exponent patched in with an
-// integer shift-add.  3 FADD2 + 3 FFMA2 + 2 LEA for two results.  CLAMP bounds n at -125 (needed only when the row's
-// bound is more than 120 binades above its smallest possible score).
-template <bool CLAMP>
-__device__ __forceinline__ void ex2_poly2(uint64_t x, float& e0, float& e1) {
-  constexpr float MAGIC = 12582912.0f;
-  if (CLAMP) { float a, b; up2(x, a, b); x = pk2(fmaxf(a, -125.0f), fmaxf(b, -125.0f)); }
-  const uint64_t t = add2(x, pk2(MAGIC, MAGIC));
-  const uint64_t u = add2(t, pk2(-MAGIC, -MAGIC));
-  const uint64_t r = sub2(x, u);
-  uint64_t p = fma2(pk2(0.0551716685f, 0.0551716685f), r, pk2(0.2426111251f, 0.2426111251f));
-  p = fma2(p, r, pk2(0.6932609677f, 0.6932609677f));
-  p = fma2(p, r, pk2(0.9999280572f, 0.9999280572f));
-  float p0, p1, t0, t1;
-  up2(p, p0, p1); up2(t, t0, t1);
-  e0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
-  e1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
-}
+using namespace tcmath;                  // TMA box load, MN-major descriptor, packed fp32 helpers, FMA-pipe exponential
 
 // 16 scores sc[16*HALF ..] -> 8 packed bf16x2 probabilities pk[8*HALF ..]: p = 2^(s*c - mc)
 template <bool CLAMP, int HALF>
 __device__ __forceinline__ void softmax_half(const uint32_t (&sc)[32], uint32_t (&pk)[16], float c, float mc) {
-  const uint64_t c2 = pk2(c, c), nm = pk2(-mc, -mc);
-#pragma unroll
-  for (int i = 8 * HALF; i < 8 * HALF + 8; ++i) {
-    const uint64_t x = fma2(pk2u(sc[2 * i], sc[2 * i + 1]), c2, nm);
-    float e0, e1;
-    if (POLY_K > 0 && (i % POLY_K) == POLY_K - 1) ex2_poly2<CLAMP>(x, e0, e1);
-    else { float x0, x1; up2(x, x0, x1); e0 = ex2_f32(x0); e1 = ex2_f32(x1); }
-    pk[i] = pack_bf16x2(e0, e1);
-  }
+  tcmath::softmax_half<CLAMP, HALF, POLY_K>(sc, pk, c, mc);
 }
 
 // TMEM: three S/P buffers of 64 columns (S tile = HPQ heads x KT keys fp32; P overwrites the thread's own S columns as
