@@ -41,6 +41,7 @@
 #include "attn_tc_math.cuh"
 #include "sm100.cuh"
 #include <stdlib.h>
+#include <type_traits>
 
 namespace tfswa {
 
@@ -52,8 +53,8 @@ using namespace tcmath;
 
 constexpr int NTHREADS = 352;          // warps 0-3 / 4-7 softmax warpgroups, 8 / 9 MMA issuers, 10 TMA producer
 constexpr int BOX = 1024;              // one TMA box: 64 tokens x 8 channels bf16
-constexpr int WIN_BYTES = 4 * BOX;     // K lo, K hi, V lo, V hi of one window and quad
-constexpr int NSTAGE = 6;              // K|V stages: items k .. k+2 are in use by issued MMAs, the rest is prefetch
+constexpr int WIN_BYTES = 6 * BOX;     // K lo, K hi, V lo, V hi, Q lo, Q hi of one window and quad
+constexpr int NSTAGE = 4;              // q|k|v stages: items k .. k+2 are in use (issued MMAs, Q copies), one is prefetch
 constexpr int NRING = 16;              // published-item ring (the TMA warp is at most NSTAGE + 2 items ahead of the slowest reader)
 constexpr uint32_t TMEM_COLS = 256;
 constexpr uint32_t WG_COLS = 128, BUF_COLS = 64, O_COL = 32;   // per warpgroup: two buffers; O sits in the upper half of its buffer
@@ -61,12 +62,60 @@ constexpr int Q_BYTES = 4096;          // masked Q copy of one tile: 128 rows x 
 template <int D> __host__ __device__ constexpr int n_win() { return D == 4 ? 1 : 2; }
 template <int D> __host__ __device__ constexpr int stage_bytes() { return n_win<D>() * WIN_BYTES; }
 template <int D> __host__ __device__ constexpr int ones_off() { return 2 * Q_BYTES + NSTAGE * stage_bytes<D>(); }
-template <int D> __host__ __device__ constexpr int smem_bytes() { return ones_off<D>() + BOX; }   // 33 / 57 KB
+template <int D> __host__ __device__ constexpr int smem_bytes();   // 34 / 58 KB (below: needs the barrier table)
 
 #ifndef TFSWA_WINTC_POLY_K
 #define TFSWA_WINTC_POLY_K 3
 #endif
 constexpr int POLY_K = TFSWA_WINTC_POLY_K;   // every POLY_K-th element pair on the FMA-pipe polynomial (0 = MUFU only)
+
+// mbarrier / TMA / commit on 32-bit shared-window addresses: the barriers live in dynamic shared memory at constant
+// offsets from the CTA's base, so every use is [base register + immediate] (a `uint64_t*` to a __shared__ barrier costs a
+// generic->shared conversion - S2UR SR_CgaCtaId, UMOV, ULEA - at each use: ~30 instructions per item and warp)
+__device__ __forceinline__ bool try_wait_a(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void wait_a(uint32_t bar, uint32_t parity) {   // bounded like sm100::mbar_wait: a protocol bug traps
+  uint32_t spins = 0;
+  uint64_t t0 = 0;
+  while (!try_wait_a(bar, parity)) {
+    if ((++spins & 255u) == 0) {
+      uint64_t now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ull) __trap();
+    }
+  }
+}
+__device__ __forceinline__ void arrive_a(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void expect_tx_a(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void commit_a(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_a(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+// barrier table (8 bytes each), item ring and the TMEM base pointer sit behind the ones tile
+constexpr int B_FULL = 0, B_EMPTY = NSTAGE, B_Q = 2 * NSTAGE, B_S = B_Q + 2, B_P = B_S + 4, B_O = B_P + 4, B_FREE = B_O + 4,
+              B_ITEM = B_FREE + 4, NBAR = B_ITEM + NRING;
+template <int D> __host__ __device__ constexpr int bar_off() { return ones_off<D>() + BOX; }
+template <int D> __host__ __device__ constexpr int slot_off() { return (bar_off<D>() + NBAR * 8 + 15) / 16 * 16; }
+template <int D> __host__ __device__ constexpr int tptr_off() { return slot_off<D>() + NRING * 16; }
+
+template <int D> __host__ __device__ constexpr int smem_bytes() { return tptr_off<D>() + 16; }
 
 struct Items {
   int n;                 // items [0, n): item = ((b * nWh_int + wh) * nP + wp) * nquads + quad
@@ -81,31 +130,32 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_attn_win_kernel(const __grid_c
   constexpr int HPQ = 16 / D;            // heads per quad (4 / 2)
   constexpr int STAGE_BYTES = stage_bytes<D>();
   constexpr int Q_OFF = 0, ST_OFF = 2 * Q_BYTES, ONES_OFF = ones_off<D>();
+  constexpr int BAR_OFF = bar_off<D>(), SLOT_OFF = slot_off<D>(), TPTR_OFF = tptr_off<D>();
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ __align__(8) uint64_t bar_full[NSTAGE], bar_empty[NSTAGE], bar_q[2], bar_s[2][2], bar_p[2][2], bar_o[2][2], bar_free[2][2], bar_item[NRING];
-  __shared__ uint32_t s_tmem;
-  __shared__ int4 s_slot[NRING];         // (b or -1: no more items, first token row, first token column, quad | second window valid << 8)
+  int4* s_slot = reinterpret_cast<int4*>(smem + SLOT_OFF);   // (b or -1: no more items, first token row, first token column, quad | second window valid << 8)
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + TPTR_OFF);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const float c = p.qscale;              // head_dim^-0.5 * log2(e)
+  const uint32_t sbase = smem_u32(smem);
+  auto bar = [&](int idx) { return sbase + BAR_OFF + idx * 8; };
 
   // ---- set-up, once per CTA ----
   if (warp == 0) {
     if (lane == 0) {
+      uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BAR_OFF);
 #pragma unroll
-      for (int i = 0; i < NSTAGE; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 2); }
+      for (int i = 0; i < NSTAGE; ++i) { mbar_init(&bars[B_FULL + i], 1); mbar_init(&bars[B_EMPTY + i], 2); }
 #pragma unroll
-      for (int g = 0; g < 2; ++g) {
-        mbar_init(&bar_q[g], 4);
+      for (int i = 0; i < 2; ++i) mbar_init(&bars[B_Q + i], 4);
 #pragma unroll
-        for (int b = 0; b < 2; ++b) { mbar_init(&bar_s[g][b], 1); mbar_init(&bar_p[g][b], 4); mbar_init(&bar_o[g][b], 1); mbar_init(&bar_free[g][b], 4); }
-      }
+      for (int i = 0; i < 4; ++i) { mbar_init(&bars[B_S + i], 1); mbar_init(&bars[B_P + i], 4); mbar_init(&bars[B_O + i], 1); mbar_init(&bars[B_FREE + i], 4); }
 #pragma unroll
-      for (int i = 0; i < NRING; ++i) mbar_init(&bar_item[i], 1);
+      for (int i = 0; i < NRING; ++i) mbar_init(&bars[B_ITEM + i], 1);
       fence_barrier_init();
     }
     __syncwarp();
-    tmem_alloc(&s_tmem, TMEM_COLS);
+    tmem_alloc(s_tmem, TMEM_COLS);
   }
   if (warp == 10 && elect_one()) prefetch_tmap(&tm);
   if (tid < BOX / 16) reinterpret_cast<uint4*>(smem + ONES_OFF)[tid] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
@@ -113,8 +163,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_attn_win_kernel(const __grid_c
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t sbase = smem_u32(smem);
-  const uint32_t tmem = s_tmem;
+  const uint32_t tmem = *s_tmem;
 
   if (warp == 10) {
     // ---- TMA producer (one lane): claims items, publishes them two ahead of the one it loads, loads K|V boxes up to
@@ -133,7 +182,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_attn_win_kernel(const __grid_c
           v = make_int4(b, wh * 8 + p.shift, ww * 8 + p.shift, quad | (second << 8));
         }
         s_slot[k % NRING] = v;
-        mbar_arrive(&bar_item[k % NRING]);
+        arrive_a(bar(B_ITEM + k % NRING));
         return v;
       };
       auto claim = [&]() {
@@ -145,19 +194,21 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_attn_win_kernel(const __grid_c
       for (int k = 0; cur.x >= 0; ++k) {
         const int4 nn = publish(k + 2, nx.x >= 0 ? claim() : -1);
         const int st = k % NSTAGE;
-        if (k >= NSTAGE) mbar_wait(&bar_empty[st], ((k / NSTAGE) - 1) & 1);   // both PV MMAs of item k - NSTAGE have completed
-        uint8_t* dst = smem + ST_OFF + st * STAGE_BYTES;
-        mbar_arrive_expect_tx(&bar_full[st], STAGE_BYTES);
+        if (k >= NSTAGE) wait_a(bar(B_EMPTY + st), ((k / NSTAGE) - 1) & 1);   // both PV MMAs of item k - NSTAGE have completed
+        const uint32_t dst = sbase + ST_OFF + st * STAGE_BYTES, full = bar(B_FULL + st);
+        expect_tx_a(full, STAGE_BYTES);
         const int quad = cur.w & 0xff;
         const int ck = p.C + quad * 16, cv = 2 * p.C + quad * 16;
 #pragma unroll
         for (int t = 0; t < NWIN; ++t) {
           const int w0 = cur.z + ((t == 1 && (cur.w >> 8)) ? 8 : 0);   // an absent second window re-reads the first (rows dropped)
-          uint8_t* d = dst + t * WIN_BYTES;
-          tma_load_4d(d, &tm, &bar_full[st], ck, w0, cur.y, cur.x);
-          tma_load_4d(d + BOX, &tm, &bar_full[st], ck + 8, w0, cur.y, cur.x);
-          tma_load_4d(d + 2 * BOX, &tm, &bar_full[st], cv, w0, cur.y, cur.x);
-          tma_load_4d(d + 3 * BOX, &tm, &bar_full[st], cv + 8, w0, cur.y, cur.x);
+          const uint32_t d = dst + t * WIN_BYTES;
+          tma_load_4d_a(d, &tm, full, ck, w0, cur.y, cur.x);
+          tma_load_4d_a(d + BOX, &tm, full, ck + 8, w0, cur.y, cur.x);
+          tma_load_4d_a(d + 2 * BOX, &tm, full, cv, w0, cur.y, cur.x);
+          tma_load_4d_a(d + 3 * BOX, &tm, full, cv + 8, w0, cur.y, cur.x);
+          tma_load_4d_a(d + 4 * BOX, &tm, full, quad * 16, w0, cur.y, cur.x);        // raw q rows: masked per head by the softmax threads
+          tma_load_4d_a(d + 5 * BOX, &tm, full, quad * 16 + 8, w0, cur.y, cur.x);
         }
         cur = nx; nx = nn;
       }
@@ -172,20 +223,20 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_attn_win_kernel(const __grid_c
     const uint64_t qdesc = umma_smem_desc_ns(sbase + Q_OFF + g * Q_BYTES, 128, 256);
     const uint32_t ones = sbase + ONES_OFF;
     auto exists = [&](int k) {
-      mbar_wait(&bar_item[k % NRING], (uint32_t)(k / NRING) & 1u);
+      wait_a(bar(B_ITEM + k % NRING), (uint32_t)(k / NRING) & 1u);
       return s_slot[k % NRING].x >= 0;
     };
     auto win_of = [&](int k) {      // my tile's window of item k: K lo | K hi | V lo | V hi
       return sbase + ST_OFF + (k % NSTAGE) * STAGE_BYTES + (NWIN == 2 ? g * WIN_BYTES : 0);
     };
     auto issue_S = [&](int k) {     // all lanes
-      mbar_wait(&bar_full[k % NSTAGE], (uint32_t)(k / NSTAGE) & 1u);
-      mbar_wait(&bar_q[g], (uint32_t)k & 1u);
-      if (k >= 2) mbar_wait(&bar_free[g][k & 1], (uint32_t)((k >> 1) - 1) & 1u);   // O(k-2) has been read
+      wait_a(bar(B_FULL + k % NSTAGE), (uint32_t)(k / NSTAGE) & 1u);
+      wait_a(bar(B_Q + g), (uint32_t)k & 1u);
+      if (k >= 2) wait_a(bar(B_FREE + 2 * g + (k & 1)), (uint32_t)((k >> 1) - 1) & 1u);   // O(k-2) has been read
       if (elect_one()) {
         tc_fence_after();
         umma_bf16_ss(s_col + (k & 1) * BUF_COLS, qdesc, umma_smem_desc_ns(win_of(k), BOX, 128), idesc_s, 0u);
-        umma_commit(&bar_s[g][k & 1]);
+        commit_a(bar(B_S + 2 * g + (k & 1)));
       }
       __syncwarp();
     };
@@ -193,7 +244,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_attn_win_kernel(const __grid_c
       issue_S(0);
       if (exists(1)) issue_S(1);
       for (int k = 0; exists(k); ++k) {
-        mbar_wait(&bar_p[g][k & 1], (uint32_t)(k >> 1) & 1u);
+        wait_a(bar(B_P + 2 * g + (k & 1)), (uint32_t)(k >> 1) & 1u);
         if (elect_one()) {
           tc_fence_after();
           const uint32_t p_col = s_col + (k & 1) * BUF_COLS, o_col = p_col + O_COL;
@@ -209,8 +260,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_attn_win_kernel(const __grid_c
               umma_bf16_ts(o_col + 16, p_col + 8 * kk, umma_smem_desc_ns(va + BOX, 128, ones + kk * 256 - (va + BOX)), idesc_pv, kk ? 1u : 0u);
             }
           }
-          umma_commit(&bar_o[g][k & 1]);
-          umma_commit(&bar_empty[k % NSTAGE]);
+          commit_a(bar(B_O + 2 * g + (k & 1)));
+          commit_a(bar(B_EMPTY + k % NSTAGE));
         }
         __syncwarp();
         if (exists(k + 2)) issue_S(k + 2);
@@ -229,85 +280,73 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_attn_win_kernel(const __grid_c
     const uint32_t t_base = tmem + ((uint32_t)(quarter * 32) << 16) + g * WG_COLS;
     uint8_t* q_dst = smem + Q_OFF + g * Q_BYTES + (r >> 3) * 256 + (r & 7) * 16;
 
-    struct It { int64_t tok; int quad; bool exists, valid; };
-    auto slot_at = [&](int k) {
-      mbar_wait(&bar_item[k % NRING], (uint32_t)(k / NRING) & 1u);
-      const int4 v = s_slot[k % NRING];
-      It it;
-      it.exists = v.x >= 0;
-      it.quad = v.w & 0xff;
-      const bool second = (v.w >> 8) != 0;
-      it.valid = it.exists && (t_win == 0 || second);
-      const int hp = v.y + (n >> 3), wp = v.z + ((t_win == 1 && second) ? 8 : 0) + (n & 7);
-      it.tok = ((int64_t)v.x * p.H + hp) * p.W + wp;
-      return it;
+    const uint32_t q_src = sbase + ST_OFF + t_win * WIN_BYTES + 4 * BOX + n * 16;   // my token's raw q row inside a stage (lo; hi = + BOX)
+    const uint32_t q_dst_a = smem_u32(q_dst);
+
+    // item k: does it exist (slot published by the TMA warp)?
+    auto exists = [&](int k) {
+      wait_a(bar(B_ITEM + k % NRING), (uint32_t)(k / NRING) & 1u);
+      return s_slot[k % NRING].x >= 0;
     };
-    auto load_q = [&](const It& it, uint4& qa, uint4& qb) {
-      if (it.exists) {
-        const uint4* src = reinterpret_cast<const uint4*>((const bf16*)p.qkv + it.tok * p.ldq + it.quad * 16);
-        qa = src[0]; qb = src[1];
-      }
-    };
-    auto write_qm = [&](const uint4& qa, const uint4& qb) {   // my row of the masked copy: only my head's channels survive
-      const uint32_t w[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
-      uint32_t m8[8];
+    // masked copy of my q row of item k from its stage (TMA-loaded raw rows) into the tile's A operand
+    auto write_qm = [&](int k) {
+      wait_a(bar(B_FULL + k % NSTAGE), (uint32_t)(k / NSTAGE) & 1u);
+      const uint32_t src = q_src + (k % NSTAGE) * STAGE_BYTES;
+      uint32_t w[8];
+      asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(src));
+      asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]) : "r"(src + BOX));
 #pragma unroll
-      for (int i = 0; i < 8; ++i) m8[i] = (i >= w_first && i < w_first + D / 2) ? w[i] : 0u;
-      *reinterpret_cast<uint4*>(q_dst) = make_uint4(m8[0], m8[1], m8[2], m8[3]);
-      *reinterpret_cast<uint4*>(q_dst + 128) = make_uint4(m8[4], m8[5], m8[6], m8[7]);
+      for (int i = 0; i < 8; ++i) w[i] = (i >= w_first && i < w_first + D / 2) ? w[i] : 0u;
+      asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(q_dst_a), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+      asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(q_dst_a + 128), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
       fence_async_smem();
+      __syncwarp();
+      if (lane == 0) arrive_a(bar(B_Q + g));
     };
-    auto epilogue = [&](const It& it, int j, float m) {     // item number j of this CTA
-      mbar_wait(&bar_o[g][j & 1], (uint32_t)(j >> 1) & 1u);
+    // O / l of item j (buffer PAR = j & 1) -> out rows of my token; frees the buffer for S(j + 2)
+    auto epilogue = [&](auto PAR, int j, float m) {
+      constexpr int B = decltype(PAR)::value;
+      wait_a(bar(B_O + 2 * g + B), (uint32_t)(j >> 1) & 1u);
       tc_fence_after();
       uint32_t o[16];
-      tmem_ld_x16(t_base + (j & 1) * BUF_COLS + O_COL + ((D == 8 && slot) ? 16 : 0), o);
+      tmem_ld_x16(t_base + B * BUF_COLS + O_COL + ((D == 8 && slot) ? 16 : 0), o);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bar_free[g][j & 1]);       // the buffer may take S(j + 2)
-      if (it.valid) {
+      if (lane == 0) arrive_a(bar(B_FREE + 2 * g + B));        // the buffer may take S(j + 2)
+      const int4 v = s_slot[j % NRING];                        // (still there: the ring is NRING - NSTAGE - 2 items deeper than any reader lags)
+      const bool second = (v.w >> 8) != 0;
+      if (t_win == 0 || second) {
+        const int quad = v.w & 0xff;
+        const int hp = v.y + (n >> 3), wp = v.z + (t_win == 1 ? 8 : 0) + (n & 7);
+        const int64_t tok = (int64_t)((v.x * p.H + hp) * p.W + wp);
         const float l = __uint_as_float(o[8]);
-        const float inv = 1.0f / l;
-        bf16* op = (bf16*)p.out + it.tok * p.ldo + it.quad * 16 + head * D;
+        const float inv = rcp_approx(l);
+        bf16* op = (bf16*)p.out + tok * p.ldo + quad * 16 + head * D;
         if (D == 4) {
-          float v[4];
+          float r4[4];
 #pragma unroll
-          for (int d = 0; d < 4; ++d) v[d] = __uint_as_float(slot ? o[4 + d] : o[d]) * inv;
-          store4(op, v);
+          for (int d = 0; d < 4; ++d) r4[d] = __uint_as_float(slot ? o[4 + d] : o[d]) * inv;
+          store4(op, r4);
         } else {
-          float v[8];
+          float r8[8];
 #pragma unroll
-          for (int d = 0; d < 8; ++d) v[d] = __uint_as_float(o[d]) * inv;
-          store8(op, v);
+          for (int d = 0; d < 8; ++d) r8[d] = __uint_as_float(o[d]) * inv;
+          store8(op, r8);
         }
-        if (p.lse) p.lse[it.tok * p.heads + it.quad * HPQ + head] = m * c + log2f(l);
+        if (p.lse) p.lse[tok * p.heads + quad * HPQ + head] = m * c + log2f(l);
       }
     };
-
-    uint4 qa = make_uint4(0, 0, 0, 0), qb = qa;
-    It cur = slot_at(0);
-    load_q(cur, qa, qb);
-    if (cur.exists) {
-      write_qm(qa, qb);
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bar_q[g]);
-    }
-    It nx = slot_at(1);
-    load_q(nx, qa, qb);
-    It prev = cur;
+    // one item: buffer PAR = k & 1 (compile time: TMEM and barrier addresses are immediates)
     float prev_m = 0.f;
-    for (int k = 0; cur.exists; ++k) {
-      mbar_wait(&bar_s[g][k & 1], (uint32_t)(k >> 1) & 1u);   // S(k) complete: the Q copy it read may be replaced
+    auto item = [&](auto PAR, int k, bool more) {
+      constexpr int B = decltype(PAR)::value;
+      wait_a(bar(B_S + 2 * g + B), (uint32_t)(k >> 1) & 1u);   // S(k) complete: the Q copy it read may be replaced
       tc_fence_after();
-      if (nx.exists) write_qm(qa, qb);
-      __syncwarp();
-      if (nx.exists && lane == 0) mbar_arrive(&bar_q[g]);
-      It n2 = nx;
-      if (nx.exists) { n2 = slot_at(k + 2); load_q(n2, qa, qb); }   // q row of item k+2 (lands during this item's softmax)
+      if (more) write_qm(k + 1);
 
       // ---- exact row maximum over the 64 keys, P = ex2(S c - m c) written over S ----
-      const uint32_t buf = t_base + (k & 1) * BUF_COLS;
+      const uint32_t buf = t_base + B * BUF_COLS;
       uint32_t sc[32], pka[16], pkb[16];
       float m = -CUDART_INF_F;
       tmem_ld_x32(buf, sc);
@@ -323,7 +362,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_attn_win_kernel(const __grid_c
       softmax_half<true, 1, POLY_K>(sc, pkb, c, mc);
       // previous item's epilogue: its PV MMAs have completed meanwhile, and the buffer it frees receives S(k+1) before this
       // item's softmax ends
-      if (k > 0) epilogue(prev, k - 1, prev_m);
+      if (k > 0) epilogue(std::integral_constant<int, 1 - B>{}, k - 1, prev_m);
       tmem_ld_x32(buf, sc);                          // keys 0-31 again (cheaper than keeping 64 scores live at 80 registers)
       tmem_ld_wait();
       softmax_half<true, 0, POLY_K>(sc, pka, c, mc);
@@ -333,11 +372,20 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_attn_win_kernel(const __grid_c
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bar_p[g][k & 1]);
+      if (lane == 0) arrive_a(bar(B_P + 2 * g + B));
+      prev_m = m;
+    };
 
-      prev = cur; prev_m = m;
-      cur = nx; nx = n2;
-      if (!cur.exists) { epilogue(prev, k, prev_m); break; }
+    if (exists(0)) {
+      write_qm(0);
+      for (int k = 0;; k += 2) {
+        const bool more1 = exists(k + 1);
+        item(std::integral_constant<int, 0>{}, k, more1);
+        if (!more1) { epilogue(std::integral_constant<int, 0>{}, k, prev_m); break; }
+        const bool more2 = exists(k + 2);
+        item(std::integral_constant<int, 1>{}, k + 1, more2);
+        if (!more2) { epilogue(std::integral_constant<int, 1>{}, k + 1, prev_m); break; }
+      }
     }
   }
   tc_fence_before();
@@ -391,6 +439,7 @@ int attn_win_tc_bf16(const AttnParams& p, int nWh_int, int nWw_int, cudaStream_t
   using namespace win_tc;
   const int D = p.C / p.heads;
   if ((D != 4 && D != 8) || p.C % 16 != 0 || nWh_int <= 0 || nWw_int <= 0) return 1;
+  if ((int64_t)p.B * p.H * p.W > 0x7fffffffll) return 1;
   if (((uintptr_t)p.qkv & 15) || (p.ldq % 8) || ((uintptr_t)p.out & 15) || (p.ldo % 8)) return 1;
   CUtensorMap tm;
   int rc = make_tmap_win(&tm, p);
