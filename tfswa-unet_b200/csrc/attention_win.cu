@@ -1,9 +1,12 @@
 // SW-MSA window attention (attention.py:347-403) with the scores, probabilities and outputs of a window living in
 // registers: warp-level mma.sync.m16n8k16 (bf16 in, fp32 accumulate) in the FlashAttention-2 register layout.
 //
-// Why not tcgen05 here: a window is 64 queries x 64 keys per head - half of the 128-row UMMA tile, with keys that differ
-// per 64-row group - and at head_dim 4..32 the kernel is bound by the 64*64 exponentials per (window, head), not by the
-// MMA.  A warp owns (head, 16 query rows): S = Q K^T is 8 n-tiles of accumulators (32 scores per thread), the row
+// Since round 2 this kernel serves what the tcgen05 + TMA kernel (tc_attn_win.cu) does not take: at head_dim 4 / 8 the
+// FRINGE windows (those with zero-padded tokens or tokens that wrap around the rolled frame: the last two window rows /
+// columns at shift 4, 4.6 % of the stage-1 windows) - p.win_edge enumerates only those - and every window at head_dim
+// 16 / 32 (stages 3 / 4: 2 % of the C3 step; a 128-row tile of ONE 16-channel head would need the keys of two windows
+// side by side in TMEM, i.e. one CTA per SM).  TFSWA_WIN_KERNEL=mma routes everything here (A/B, tests).
+// A warp owns (head, 16 query rows): S = Q K^T is 8 n-tiles of accumulators (32 scores per thread), the row
 // maximum is exact (the whole key range is in registers: no online rescaling, no bound), P is re-packed in place as
 // the A operand of the PV MMA, and the row sum comes from one more MMA against a ones operand, so the bf16-rounded P
 // feeds numerator and denominator alike.  No shared-memory round trip for S or P, no barriers after staging.
