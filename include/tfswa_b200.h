@@ -244,6 +244,30 @@ int tfswa_head_tail_bwd(const void* v, const float* scale, const float* shift, c
                         float* dshift, int32_t B, int32_t H, int32_t W, int32_t C, int32_t Cout, int32_t dtype, void* stream);
 
 /* =====================================================================================================
+ * The spectrogram steps either side of the model in overlap-add separation (row f3 of SURVEY 8f).  STFT / ISTFT stay
+ * batched cuFFT (torch.stft / torch.istft); these entry points replace the eager element-wise chains between them
+ * and the model.  All buffers are dense fp32 / complex64 (interleaved re, im).
+ * ===================================================================================================== */
+
+/* spec (B, F, T) complex64 -> x (B, 2, F, T) fp32 = [real | imag] planes (stft_processor.py:186-204 to_model_input);
+ * normalize != 0: instance normalisation over time per (b, channel, f) row, (v - mean) / (std + eps) with the unbiased
+ * std (SpectrogramNormalizer.forward, stft_processor.py:283-297), and stats (B, 2, F, 2) receives {mean, std + eps}. */
+int tfswa_spec_pack_norm(const void* spec_c64, float* x, float* stats, int32_t B, int32_t F, int32_t T, float eps,
+                         int32_t normalize, void* stream);
+/* out (B, S, F, T) complex64 = spec[b, f, t] * w,  w = masks[b, s, f, t]  (normalize == 0)  or
+ * masks * std[b, s, f] + mean[b, s, f]: the reference "denormalises" the masks with the statistics of INPUT channel s
+ * (inference.py:132-133, stft_processor.py:299-312), so S <= 2 there.  Replaces inference.py:139-145. */
+int tfswa_spec_mask_apply(const float* masks, const void* spec_c64, const float* stats, void* out_c64, int32_t B, int32_t S,
+                          int32_t F, int32_t T, int32_t normalize, void* stream);
+/* Hann-weighted overlap-add of nseg reconstructed segments (inference.py:209-216): wav (nseg, S, L) fp32, starts (nseg)
+ * int64 device array of output offsets in ascending order (first_start / last_start: its first and last entry, on the
+ * host), win (>= min(seg_len, L)) fp32, acc (S + 1, total) fp32: rows 0..S-1 += wav * win, row S += win, over the first
+ * min(seg_len, total - start, L) samples of each segment.  Per output sample the segments are added in ascending
+ * order with separately rounded products - the arithmetic of the reference's sequential loop; no atomics. */
+int tfswa_ola_add(const float* wav, const int64_t* starts, int64_t first_start, int64_t last_start, const float* win, float* acc,
+                  int32_t nseg, int32_t S, int64_t L, int64_t seg_len, int64_t total, void* stream);
+
+/* =====================================================================================================
  * Optimiser step over a flat fp32 parameter arena (row f1 of SURVEY 8f).  Replaces
  * torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm) + optimizer.step() of src/training/trainer.py:214-219
  * for the AdamW of scripts/train.py:251-255 (one parameter group, decoupled weight decay on every parameter).

@@ -554,3 +554,47 @@ def head_tail_bwd(v: Tensor, scale: Optional[Tensor], shift: Optional[Tensor], w
     _call("tfswa_head_tail_bwd", v.data_ptr(), _p(scale), _p(shift), w3.data_ptr(), b3.data_ptr(), _p(dmasks), _p(dlogits),
           dv.data_ptr(), dw3.data_ptr(), db3.data_ptr(), _p(dsc), _p(dsh), B, H, W, C_, Cout, _dt(v), _stream())
     return dv, dw3, db3, dsc, dsh
+
+
+# ---- spectrogram steps around the model in overlap-add separation -------------
+def spec_pack_norm(spec: Tensor, normalize: bool = True, eps: float = 1e-8):
+    """complex64 STFT (B, F, T) -> model input (B, 2, F, T) fp32 [real | imag] (stft_processor.py:186-204), instance-normalised
+    over time when ``normalize`` (stft_processor.py:283-297); returns (x, stats (B, 2, F, 2) = {mean, std + eps} or None)."""
+    _cuda(spec)
+    if spec.dtype != torch.complex64 or spec.dim() != 3 or not spec.is_contiguous():
+        raise ValueError("spec_pack_norm: contiguous complex64 (B, F, T) expected")
+    B, F, T = spec.shape
+    x = torch.empty((B, 2, F, T), dtype=torch.float32, device=spec.device)
+    stats = torch.empty((B, 2, F, 2), dtype=torch.float32, device=spec.device) if normalize else None
+    _call("tfswa_spec_pack_norm", spec.data_ptr(), x.data_ptr(), _p(stats), B, F, T, float(eps), int(normalize), _stream(),
+          work={"bytes": 16 * B * F * T})
+    return x, stats
+
+
+def spec_mask_apply(masks: Tensor, spec: Tensor, stats: Optional[Tensor]) -> Tensor:
+    """masks (B, S, F, T) fp32, spec (B, F, T) complex64 -> stems (B, S, F, T) complex64 = spec * (masks * std + mean)
+    (inference.py:132-145); ``stats`` None = masks applied as they are."""
+    _cuda(masks, spec)
+    if masks.dtype != torch.float32 or not masks.is_contiguous() or spec.dtype != torch.complex64 or not spec.is_contiguous():
+        raise ValueError("spec_mask_apply: contiguous fp32 masks and complex64 spec expected")
+    B, S, F, T = masks.shape
+    if tuple(spec.shape) != (B, F, T):
+        raise ValueError(f"spec_mask_apply: spec {tuple(spec.shape)} does not match masks {tuple(masks.shape)}")
+    out = torch.empty((B, S, F, T), dtype=torch.complex64, device=masks.device)
+    _call("tfswa_spec_mask_apply", masks.data_ptr(), spec.data_ptr(), _p(stats), out.data_ptr(), B, S, F, T,
+          int(stats is not None), _stream(), work={"bytes": (12 * S + 8) * B * F * T})
+    return out
+
+
+def ola_add(wav: Tensor, starts, win: Tensor, acc: Tensor, seg_len: int) -> None:
+    """acc (S + 1, total) += Hann-weighted segments: wav (nseg, S, L) fp32, ``starts`` ascending python ints (inference.py:209-216)."""
+    _cuda(wav, win, acc)
+    if wav.dtype != torch.float32 or not wav.is_contiguous() or acc.dtype != torch.float32 or not acc.is_contiguous():
+        raise ValueError("ola_add: contiguous fp32 buffers expected")
+    nseg, S, Lw = wav.shape
+    if len(starts) != nseg or acc.shape[0] != S + 1 or win.numel() < min(seg_len, Lw) or list(starts) != sorted(starts):
+        raise ValueError("ola_add: inconsistent segment list / buffers")
+    st = torch.tensor(list(starts), dtype=torch.int64).to(wav.device, non_blocking=True)
+    _call("tfswa_ola_add", wav.data_ptr(), st.data_ptr(), int(starts[0]), int(starts[-1]), _f32c(win).data_ptr(), acc.data_ptr(),
+          nseg, S, Lw, int(seg_len), acc.shape[1], _stream())
+

@@ -6,8 +6,11 @@ packing (:121), optional instance normalisation over time (:124-125, stft_proces
 (:128-129), mask * spectrogram per stem (:139-145), ISTFT (:148-150), Hann-weighted overlap-add and normalisation
 (:209-223) - but segments are processed ``batch`` at a time instead of one by one, and the segment list is
 sharded contiguously over the ranks of the process group; the only exchange is one all-reduce (SUM) of the
-per-rank output and window-weight buffers.  STFT/ISTFT are torch.stft/istft (cuFFT): they sit either side of the
-path, not on it.
+per-rank output and window-weight buffers.  STFT/ISTFT are torch.stft/istft (batched cuFFT).  On a CUDA device the
+element-wise chains between them and the model are three kernels of libtfswa_b200 (csrc/spec.cu):
+real/imag packing + instance normalisation, mask denormalisation + mask * spectrogram for all stems, and the windowed
+overlap-add of a whole batch; the ISTFT of all stems of a batch is one call.  On CPU tensors (the gloo tests of the
+sharding logic) the same steps are eager torch ops.
 """
 from __future__ import annotations
 
@@ -54,10 +57,16 @@ class ShardedSeparator:
         return [i * self.hop_samples for i in range(n)]          # samples past the last full hop stay uncovered (reference quirk)
 
     def _masks(self, seg: Tensor):
-        """seg (b, S) mono -> complex spec (b, F, T), masks (b, stems, F, T)"""
+        """seg (b, S) mono -> complex spec (b, F, T), masked complex stems (b, stems, F, T)"""
         win = torch.hann_window(self.n_fft, device=seg.device)
         spec = torch.stft(seg, self.n_fft, self.hop, self.n_fft, win, center=True, pad_mode="reflect", normalized=False,
                           onesided=True, return_complex=True)
+        if seg.is_cuda:
+            from . import ops
+            spec = spec.contiguous()
+            x, stats = ops.spec_pack_norm(spec, self.normalize)                     # to_model_input + SpectrogramNormalizer in one pass
+            masks = self.model(x)
+            return spec, ops.spec_mask_apply(masks.float().contiguous(), spec, stats)   # (b, stems, F, T) complex stems
         x = torch.stack([spec.real, spec.imag], dim=1)                              # to_model_input, stft_processor.py:186-204
         if self.normalize:
             mean = x.mean(dim=-1, keepdim=True)
@@ -68,7 +77,7 @@ class ShardedSeparator:
             masks = masks * std + mean
         else:
             masks = self.model(x.contiguous())
-        return spec, masks
+        return spec, spec[:, None] * masks                                          # inference.py:139-145
 
     @torch.no_grad()
     def separate(self, audio: Tensor, stem_names: Optional[List[str]] = None) -> Dict[str, Tensor]:
@@ -78,10 +87,10 @@ class ShardedSeparator:
         mono = audio.mean(dim=0) if audio.shape[0] > 1 else audio[0]               # inference.py:84-85
         total = mono.shape[0]
         if total <= self.segment_samples:                                          # inference.py:92-95: one segment as it is -
-            spec, masks = self._masks(mono[None])                                  # no padding, no window, ISTFT's own length
+            spec, stems = self._masks(mono[None])                                  # no padding, no window, ISTFT's own length
             win = torch.hann_window(self.n_fft, device=mono.device)
-            return {name: torch.istft(spec * masks[:, i], self.n_fft, self.hop, self.n_fft, win, center=True, normalized=False,
-                                      onesided=True) for i, name in enumerate(stem_names[:masks.shape[1]])}
+            return {name: torch.istft(stems[:, i], self.n_fft, self.hop, self.n_fft, win, center=True, normalized=False,
+                                      onesided=True) for i, name in enumerate(stem_names[:stems.shape[1]])}
         starts = self.plan(total)
         world = dist.get_world_size(self.group) if dist.is_initialized() else 1
         rank = dist.get_rank(self.group) if dist.is_initialized() else 0
@@ -93,14 +102,21 @@ class ShardedSeparator:
         for b0, b1 in balanced_batches(lo, hi, self.batch):
             idx = starts[b0:b1]
             seg = torch.stack([torch.nn.functional.pad(mono[s:s + S], (0, max(0, S - (total - s)))) for s in idx])
-            spec, masks = self._masks(seg)
+            spec, stems = self._masks(seg)
             # The reference reconstructs without a target length (inference.py:148-150 -> stft_processor.py:136-184): a segment
             # comes back (frames-1)*hop samples long - 264 192 of 264 600 for 6 s at hop 512 - and only that many samples,
             # weighted by the FIRST part of the full-length Hann window, enter the overlap-add (inference.py:209-216).
             L = (spec.shape[-1] - 1) * self.hop
-            for i in range(min(n_st, masks.shape[1])):
-                wav = torch.istft(spec * masks[:, i], self.n_fft, self.hop, self.n_fft,
-                                  torch.hann_window(self.n_fft, device=seg.device), center=True, normalized=False, onesided=True)
+            k = min(n_st, stems.shape[1])
+            fft_win = torch.hann_window(self.n_fft, device=seg.device)
+            if seg.is_cuda and k == n_st:
+                from . import ops
+                wav = torch.istft(stems.reshape(-1, *stems.shape[2:]), self.n_fft, self.hop, self.n_fft, fft_win, center=True,
+                                  normalized=False, onesided=True)                 # every stem of the batch in one cuFFT call
+                ops.ola_add(wav.view(len(idx), k, -1).contiguous(), idx, win_seg, acc, S)
+                continue
+            for i in range(k):
+                wav = torch.istft(stems[:, i], self.n_fft, self.hop, self.n_fft, fft_win, center=True, normalized=False, onesided=True)
                 for j, s in enumerate(idx):
                     n = min(S, total - s, L)
                     acc[i, s:s + n] += wav[j, :n] * win_seg[:n]
