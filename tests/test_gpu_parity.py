@@ -269,3 +269,21 @@ def test_convert_shares_parameters_and_matches():
     x = seeded((1, 2, 32, 24), 4).cuda()
     with torch.no_grad():
         assert torch.equal(a(x), b(x))
+
+
+def test_host_pipeline_matches_plain_forward():
+    """HostPipeline (double-buffered H2D / D2H on copy streams around the eval forward) returns, for every step and in order,
+    exactly what the plain forward returns - different inputs per step so that a buffer race would show."""
+    import tfswa_unet_b200 as T
+    torch.manual_seed(3)
+    model = T.TFSWAUNet(2, 2, [1, 1, 1, 1], [32, 64, 128, 256], 8, 4, 8).cuda().eval()
+    xs = [torch.randn(2, 2, 72, 40).pin_memory() for _ in range(5)]
+    outs = [torch.empty(2, 2, 72, 40).pin_memory() for _ in range(5)]
+    pipe = T.HostPipeline(model)
+    for x, o in zip(xs, outs):
+        pipe.step(x, o)
+    pipe.flush()
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        for x, o in zip(xs, outs):
+            assert torch.equal(o, model(x.cuda()).cpu())

@@ -10,5 +10,6 @@ from .attention import (FrequencySequenceAttention, MultiHeadAttention, ScaledDo
 from .blocks import DownsampleBlock, TFSWABlock, UpsampleBlock  # noqa: F401
 from .tfswa_unet import TFSWAUNet  # noqa: F401
 from .compat import convert, install_as_reference  # noqa: F401
+from .pipeline import HostPipeline  # noqa: F401
 
 __version__ = "0.1.0"
