@@ -267,6 +267,14 @@ int tfswa_spec_mask_apply(const float* masks, const void* spec_c64, const float*
 int tfswa_ola_add(const float* wav, const int64_t* starts, int64_t first_start, int64_t last_start, const float* win, float* acc,
                   int32_t nseg, int32_t S, int64_t L, int64_t seg_len, int64_t total, void* stream);
 
+/* One resolution of MultiResolutionSTFTLoss (losses.py:125-141, 171-183; row f4 of SURVEY 8f) on the complex STFTs of the
+ * predicted and the target audio (n complex64 elements each, any common dense layout):
+ *   *loss += w_mag * mean| |P| - |T| | + w_log * mean| log(|P| + eps) - log(|T| + eps) |     (double, caller-zeroed)
+ * grad_c64 (optional, n complex64): d(that value)/dP in PyTorch's convention for a real loss of a complex tensor
+ * (dL/dRe + i dL/dIm) - the backward of abs / log / l1_loss of the eager chain, from the same pass. */
+int tfswa_mrstft_mag_loss(const void* pred_c64, const void* target_c64, int64_t n, float w_mag, float w_log, float eps,
+                          double* loss, void* grad_c64, void* stream);
+
 /* =====================================================================================================
  * Optimiser step over a flat fp32 parameter arena (row f1 of SURVEY 8f).  Replaces
  * torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm) + optimizer.step() of src/training/trainer.py:214-219

@@ -99,6 +99,7 @@ SIGNATURES = {
     "tfswa_spec_pack_norm": (C.c_int, [_p, _p, _p, _i32, _i32, _i32, _f, _i32, _p]),
     "tfswa_spec_mask_apply": (C.c_int, [_p, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _p]),
     "tfswa_ola_add": (C.c_int, [_p, _p, _i64, _i64, _p, _p, _i32, _i32, _i64, _i64, _i64, _p]),
+    "tfswa_mrstft_mag_loss": (C.c_int, [_p, _p, _i64, _f, _f, _f, _p, _p, _p]),
     # optimiser step over the flat arena
     "tfswa_grad_sumsq": (C.c_int, [_p, _i64, _p, _p]),
     "tfswa_adamw_clip_step": (C.c_int, [_p, _p, _p, _p, _i64, _p, _p, _f, _f, _f, _f, _f, _f, _f, _i64, _p, _p]),

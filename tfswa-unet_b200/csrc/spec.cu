@@ -8,6 +8,8 @@
 //   * tfswa_ola_add: Hann-weighted overlap-add of a batch of reconstructed segments into the output and weight rows
 //     (inference.py:209-216), as a gather over output samples so that the per-sample summation order is the reference's
 //     (ascending segment index) and no atomics are needed.
+//   * tfswa_mrstft_mag_loss (row f4): magnitude + log-magnitude L1 of one resolution of the multi-resolution STFT loss
+//     (losses.py:125-141, 171-183) with the gradient with respect to the predicted spectrogram from the same pass.
 // STFT / ISTFT themselves stay batched cuFFT (torch.stft / torch.istft).
 #include "common.cuh"
 
@@ -100,9 +102,58 @@ __global__ void __launch_bounds__(256) ola_add_kernel(const float* __restrict__ 
   if (touched) acc[row * total + t] = a;
 }
 
+// magnitude + log-magnitude L1 of one STFT resolution (losses.py:125-141, 171-183) and its gradient with respect to the
+// predicted spectrogram, in one pass over the two complex tensors: |P| and |T| never reach HBM
+template <bool GRAD>
+__global__ void __launch_bounds__(256) mrstft_mag_loss_kernel(const float2* __restrict__ pred, const float2* __restrict__ target,
+                                                              int64_t n, float a, float b, float eps, double* __restrict__ loss,
+                                                              float2* __restrict__ grad) {
+  float acc = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float2 P = pred[i], T = target[i];
+    const float pm = sqrtf(P.x * P.x + P.y * P.y), tm = sqrtf(T.x * T.x + T.y * T.y);
+    const float dm = pm - tm;
+    const float dl = logf(pm + eps) - logf(tm + eps);
+    acc += a * fabsf(dm) + b * fabsf(dl);
+    if (GRAD) {
+      // d|dm|/dpm = sign(dm), d|dl|/dpm = sign(dl) / (pm + eps); d pm / dP = P / pm (0 at P = 0, like torch.abs)
+      const float sm = dm > 0.f ? 1.f : (dm < 0.f ? -1.f : 0.f), sl = dl > 0.f ? 1.f : (dl < 0.f ? -1.f : 0.f);
+      const float g = a * sm + b * sl / (pm + eps);
+      const float r = pm > 0.f ? g / pm : 0.f;
+      grad[i] = make_float2(P.x * r, P.y * r);
+    }
+  }
+  acc = warp_sum(acc);
+  __shared__ float part[8];
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += (double)part[w];
+    atomicAdd(loss, t);
+  }
+}
+
 }  // namespace tfswa
 
 using namespace tfswa;
+
+extern "C" int tfswa_mrstft_mag_loss(const void* pred_c64, const void* target_c64, int64_t n, float w_mag, float w_log, float eps,
+                                     double* loss, void* grad_c64, void* stream) {
+  TFSWA_REQUIRE(pred_c64 && target_c64 && loss && n > 0, "mrstft_mag_loss: bad arguments");
+  TFSWA_REQUIRE(((((uintptr_t)pred_c64) | ((uintptr_t)target_c64) | ((uintptr_t)grad_c64)) & 7) == 0, "mrstft_mag_loss: complex64 buffers must be 8-byte aligned");
+  const float a = w_mag / (float)n, b = w_log / (float)n;        // F.l1_loss: mean over the elements
+  int sms = 148;
+  int dev = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int64_t blocks = ceil_div64(n, 256 * 4);
+  if (blocks > (int64_t)sms * 8) blocks = (int64_t)sms * 8;    // grid-stride: a multiple of the SM count, 8 CTAs of 256 threads per SM
+  cudaStream_t st = (cudaStream_t)stream;
+  if (grad_c64) mrstft_mag_loss_kernel<true><<<(unsigned)blocks, 256, 0, st>>>((const float2*)pred_c64, (const float2*)target_c64, n, a, b, eps, loss, (float2*)grad_c64);
+  else mrstft_mag_loss_kernel<false><<<(unsigned)blocks, 256, 0, st>>>((const float2*)pred_c64, (const float2*)target_c64, n, a, b, eps, loss, nullptr);
+  return check_launch("mrstft_mag_loss");
+}
 
 extern "C" int tfswa_spec_pack_norm(const void* spec_c64, float* x, float* stats, int32_t B, int32_t F, int32_t T, float eps,
                                     int32_t normalize, void* stream) {

@@ -598,3 +598,21 @@ def ola_add(wav: Tensor, starts, win: Tensor, acc: Tensor, seg_len: int) -> None
     _call("tfswa_ola_add", wav.data_ptr(), st.data_ptr(), int(starts[0]), int(starts[-1]), _f32c(win).data_ptr(), acc.data_ptr(),
           nseg, S, Lw, int(seg_len), acc.shape[1], _stream())
 
+
+def mrstft_mag_loss(pred_spec: Tensor, target_spec: Tensor, w_mag: float, w_log: float, eps: float, want_grad: bool):
+    """One resolution of the MR-STFT loss on two complex64 STFTs of identical dense layout (losses.py:125-141, 171-183):
+    -> (loss fp64 (1,), d loss / d pred_spec or None)."""
+    _cuda(pred_spec, target_spec)
+    if pred_spec.dtype != torch.complex64 or target_spec.dtype != torch.complex64 or pred_spec.shape != target_spec.shape \
+            or pred_spec.stride() != target_spec.stride():
+        raise ValueError("mrstft_mag_loss: two complex64 tensors of the same shape and strides expected")
+    n = pred_spec.numel()
+    dense = torch.empty_like(pred_spec)          # preserve_format: the same dense layout as the input (e.g. stft's (B, T, F) storage)
+    if dense.stride() != pred_spec.stride() or not (pred_spec.is_contiguous() or pred_spec.transpose(-1, -2).is_contiguous()):
+        raise ValueError("mrstft_mag_loss: dense (non-overlapping, gap-free) spectrograms expected")
+    grad = dense if want_grad else None
+    loss = torch.zeros((1,), dtype=torch.float64, device=pred_spec.device)
+    _call("tfswa_mrstft_mag_loss", pred_spec.data_ptr(), target_spec.data_ptr(), n, float(w_mag), float(w_log), float(eps),
+          loss.data_ptr(), _p(grad), _stream(), work={"bytes": (16 + (8 if want_grad else 0)) * n})
+    return loss, grad
+
