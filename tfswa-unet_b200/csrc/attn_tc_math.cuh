@@ -27,6 +27,47 @@ __device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) { u
 __device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) { uint64_t d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 __device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) { uint64_t d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 
+// mbarrier / TMA / commit on 32-bit shared-window addresses: the barriers live in dynamic shared memory at constant
+// offsets from the CTA's base, so every use is [base register + immediate] (a `uint64_t*` to a __shared__ barrier costs a
+// generic->shared conversion - S2UR SR_CgaCtaId, UMOV, ULEA - at each use: ~30 instructions per item and warp)
+__device__ __forceinline__ bool try_wait_a(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void wait_a(uint32_t bar, uint32_t parity) {   // bounded like sm100::mbar_wait: a protocol bug traps
+  uint32_t spins = 0;
+  uint64_t t0 = 0;
+  while (!try_wait_a(bar, parity)) {
+    if ((++spins & 255u) == 0) {
+      uint64_t now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ull) __trap();
+    }
+  }
+}
+// hot-loop form: the first probe costs YIELD + SYNCS + BRA; the retry loop with its timeout bookkeeping is off the fast path
+__device__ __forceinline__ void wait_fast(uint32_t bar, uint32_t parity) {
+  if (!try_wait_a(bar, parity)) wait_a(bar, parity);
+}
+__device__ __forceinline__ void arrive_a(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void expect_tx_a(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void commit_a(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_a(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
 // 2^x for a pair of x <= 0 on the FMA / ALU pipes: x = n + r (round to nearest through the 1.5 * 2^23 trick), degree-3
 // minimax polynomial of 2^r on [-0.5, 0.5] (7.5e-5 relative - P is rounded to bf16, 3.9e-3), exponent patched in with an
 // integer shift-add.  3 FADD2 + 3 FFMA2 + 2 LEA for two results.  CLAMP bounds n at -125 (needed only when the row's

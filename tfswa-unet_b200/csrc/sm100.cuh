@@ -62,6 +62,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 // in hardware for a bounded time, so retries are rare on the good path; every 256th retry reads the global timer and the
 // kernel traps once a single wait has lasted more than ~4 s.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;     // fast path: one probe, none of the timeout bookkeeping below
   uint32_t spins = 0;
   uint64_t t0 = 0;
   while (!mbar_try_wait(bar, parity)) {

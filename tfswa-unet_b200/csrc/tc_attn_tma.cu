@@ -127,9 +127,11 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_attn_tma_kernel(const __grid_c
   constexpr int NCH = HPT * D;           // channels of my head slots (8 / 8 / 16), starting at channel c0 of the quad
   constexpr int Q_OFF = 0, ST_OFF = stage_off<D>(), ONES_OFF = ones_off<D>(), TAIL_OFF = tail_off<D>();
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ __align__(8) uint64_t bar_full[NSTAGE], bar_empty[NSTAGE], bar_s[NBUF], bar_p[NBUF], bar_done, bar_q;
+  // one table: every barrier is [table base register + immediate] for the 32-bit-address forms of attn_tc_math.cuh
+  constexpr int B_FULL = 0, B_EMPTY = NSTAGE, B_S = 2 * NSTAGE, B_P = B_S + (int)NBUF, B_DONE = B_P + (int)NBUF, B_Q = B_DONE + 1,
+                B_ITEM = B_Q + 1, NBAR = B_ITEM + NRING;
+  __shared__ __align__(8) uint64_t bars[NBAR];
   __shared__ uint32_t s_tmem;
-  __shared__ __align__(8) uint64_t bar_item[NRING];
   __shared__ int s_ring[NRING];                       // claimed items: id (-1: none left) ...
   __shared__ int4 s_slot[NRING];                      // ... and where it is (row, b, column / row inside b, q0 | quad)
   __shared__ float s_xch[HPQ == 1 ? 256 : 1];   // d = 16, exact pass: the two threads of a row exchange their maxima
@@ -152,12 +154,12 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_attn_tma_kernel(const __grid_c
   if (warp == 0) {
     if (lane == 0) {
 #pragma unroll
-      for (int i = 0; i < NSTAGE; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 1); }
+      for (int i = 0; i < NSTAGE; ++i) { mbar_init(&bars[B_FULL + i], 1); mbar_init(&bars[B_EMPTY + i], 1); }
 #pragma unroll
-      for (int i = 0; i < (int)NBUF; ++i) { mbar_init(&bar_s[i], 1); mbar_init(&bar_p[i], 8); }
-      mbar_init(&bar_done, 1); mbar_init(&bar_q, 8);
+      for (int i = 0; i < (int)NBUF; ++i) { mbar_init(&bars[B_S + i], 1); mbar_init(&bars[B_P + i], 8); }
+      mbar_init(&bars[B_DONE], 1); mbar_init(&bars[B_Q], 8);
 #pragma unroll
-      for (int i = 0; i < NRING; ++i) mbar_init(&bar_item[i], 1);
+      for (int i = 0; i < NRING; ++i) mbar_init(&bars[B_ITEM + i], 1);
       fence_barrier_init();
     }
     __syncwarp();
@@ -176,6 +178,10 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_attn_tma_kernel(const __grid_c
   tc_fence_after();
   const uint32_t sbase = smem_u32(smem);
   const uint32_t tmem = s_tmem;
+  // the two barriers of the key loop as 32-bit shared addresses kept in registers: wait / arrive are [register + immediate]
+  // (through `uint64_t*` the lane-0 arrive recomputed the generic->shared conversion - S2R SR_CgaCtaId, MOV, LEA - per tile)
+  const uint32_t bar0 = smem_u32(bars);
+  auto bar = [&](int idx) { return bar0 + 8u * (uint32_t)idx; };
 
   // item -> sequence `row`, first query q0, quad; TSA row = b * W + w (keys along h), FSA row = b * H + h (keys along w)
   struct Where { int row, q0, quad, cb, cf, item; };
@@ -198,15 +204,15 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_attn_tma_kernel(const __grid_c
   // tile t of a pass uses TMEM buffer t % 3; every role keeps the parity of the next phase it will wait for per buffer
   // (softmax: bar_s, issuer: bar_p) in three scalars, so the 3-way unrolled loops address buffers with immediates
   uint32_t ph0 = 0, ph1 = 0, ph2 = 0;
-  auto wait_buf = [&](uint64_t* bars, int b) {      // runtime b (rare paths)
+  auto wait_buf = [&](int first, int b) {          // runtime b (rare paths)
     const uint32_t ph = b == 0 ? ph0 : (b == 1 ? ph1 : ph2);
-    mbar_wait(&bars[b], ph);
+    wait_a(bar(first + b), ph);
     if (b == 0) ph0 ^= 1; else if (b == 1) ph1 ^= 1; else ph2 ^= 1;
   };
 
   // k-th item of this CTA, published by the TMA warp (-1: no more)
   auto item_at = [&](int k) {
-    mbar_wait(&bar_item[k % NRING], (uint32_t)(k / NRING) & 1u);
+    wait_fast(bar(B_ITEM + k % NRING), (uint32_t)(k / NRING) & 1u);
     return s_ring[k % NRING];
   };
   auto where_at = [&](int k, int item) {  // after item_at(k) returned `item` >= 0
@@ -227,7 +233,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_attn_tma_kernel(const __grid_c
           s_slot[k % NRING] = make_int4(ww.row, ww.cb, ww.cf, ww.q0 | ww.quad);
         }
         s_ring[k % NRING] = it >= 0 ? ww.item : -1;
-        mbar_arrive(&bar_item[k % NRING]);
+        arrive_a(bar(B_ITEM + k % NRING));
       };
       int it = (int)blockIdx.x < n_items ? (int)blockIdx.x : -1;
       publish(0, it, w);
@@ -240,20 +246,20 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_attn_tma_kernel(const __grid_c
         for (int pass = exact ? 0 : 1; pass < 2; ++pass) {
           for (int i = 0; i < NST; ++i, ++n_stage) {
             const uint32_t g = n_stage, st = g % NSTAGE;
-            if (g >= NSTAGE) mbar_wait(&bar_empty[st], ((g / NSTAGE) - 1) & 1);   // stage g - NSTAGE released
-            uint8_t* dst = smem + ST_OFF + st * STAGE_BYTES;
-            mbar_arrive_expect_tx(&bar_full[st], STAGE_BYTES);
+            if (g >= NSTAGE) wait_a(bar(B_EMPTY + st), ((g / NSTAGE) - 1) & 1);   // stage g - NSTAGE released
+            const uint32_t dst = sbase + ST_OFF + st * STAGE_BYTES, full = bar(B_FULL + st);
+            expect_tx_a(full, STAGE_BYTES);
             const int k0 = i * SKEYS;
             if (tsa) {
-              tma_load_4d(dst, &tm, &bar_full[st], ck, w.cf, k0, w.cb);
-              tma_load_4d(dst + BOX_BYTES, &tm, &bar_full[st], ck + 8, w.cf, k0, w.cb);
-              tma_load_4d(dst + 2 * BOX_BYTES, &tm, &bar_full[st], cv, w.cf, k0, w.cb);
-              tma_load_4d(dst + 3 * BOX_BYTES, &tm, &bar_full[st], cv + 8, w.cf, k0, w.cb);
+              tma_load_4d_a(dst, &tm, full, ck, w.cf, k0, w.cb);
+              tma_load_4d_a(dst + BOX_BYTES, &tm, full, ck + 8, w.cf, k0, w.cb);
+              tma_load_4d_a(dst + 2 * BOX_BYTES, &tm, full, cv, w.cf, k0, w.cb);
+              tma_load_4d_a(dst + 3 * BOX_BYTES, &tm, full, cv + 8, w.cf, k0, w.cb);
             } else {
-              tma_load_4d(dst, &tm, &bar_full[st], ck, k0, w.cf, w.cb);
-              tma_load_4d(dst + BOX_BYTES, &tm, &bar_full[st], ck + 8, k0, w.cf, w.cb);
-              tma_load_4d(dst + 2 * BOX_BYTES, &tm, &bar_full[st], cv, k0, w.cf, w.cb);
-              tma_load_4d(dst + 3 * BOX_BYTES, &tm, &bar_full[st], cv + 8, k0, w.cf, w.cb);
+              tma_load_4d_a(dst, &tm, full, ck, k0, w.cf, w.cb);
+              tma_load_4d_a(dst + BOX_BYTES, &tm, full, ck + 8, k0, w.cf, w.cb);
+              tma_load_4d_a(dst + 2 * BOX_BYTES, &tm, full, cv, k0, w.cf, w.cb);
+              tma_load_4d_a(dst + 3 * BOX_BYTES, &tm, full, cv + 8, k0, w.cf, w.cb);
             }
           }
         }
@@ -274,15 +280,15 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_attn_tma_kernel(const __grid_c
 #pragma unroll
       for (int h = 0; h < HPQ; ++h)
         umma_bf16_ss(tmem + b * BUF_COLS + h * KT, umma_smem_desc_ns(sbase + Q_OFF + h * 4096, 128, 256), kdesc, idesc_s, 0u);
-      umma_commit(&bar_s[b]);
+      commit_a(bar(B_S + b));
       TRACE(2, u);
     };
     auto wait_stage = [&](int u) {                 // all lanes: the stage holding tile u has landed
       const uint32_t g = n_stage + u / TPS, st = g % NSTAGE;
-      mbar_wait(&bar_full[st], (g / NSTAGE) & 1);
+      wait_fast(bar(B_FULL + st), (g / NSTAGE) & 1);
     };
     for (int k = 0; item_at(k) >= 0; ++k) {
-      mbar_wait(&bar_q, n_q & 1); ++n_q;           // this item's masked Q copies are in shared memory
+      wait_fast(bar(B_Q), n_q & 1); ++n_q;           // this item's masked Q copies are in shared memory
       for (int pass = exact ? 0 : 1; pass < 2; ++pass) {
         const bool maxpass = pass == 0;
         for (int u = 0; u < (int)NBUF && u < T; ++u) {
@@ -299,7 +305,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_attn_tma_kernel(const __grid_c
             const int u = t + NBUF;
             if (u < T && u % TPS == 0) wait_stage(u);
             uint32_t& ph = b == 0 ? ph0 : (b == 1 ? ph1 : ph2);
-            mbar_wait(&bar_p[b], ph);              // P(t) written over S(t) (max pass: S(t) consumed)
+            wait_fast(bar(B_P + b), ph);            // P(t) written over S(t) (max pass: S(t) consumed)
             ph ^= 1;
             if (elect_one()) {
               tc_fence_after();
@@ -327,8 +333,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_attn_tma_kernel(const __grid_c
                 }
               }
               if (u < T) issue_S(u, b);
-              if (t % TPS == TPS - 1 || t == T - 1) umma_commit(&bar_empty[st]);   // K rows (S) and V rows (PV) of the stage are done with
-              if (!maxpass && t == T - 1) umma_commit(&bar_done);
+              if (t % TPS == TPS - 1 || t == T - 1) commit_a(bar(B_EMPTY + st));   // K rows (S) and V rows (PV) of the stage are done with
+              if (!maxpass && t == T - 1) commit_a(bar(B_DONE));
             }
             __syncwarp();
           }
@@ -368,7 +374,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_attn_tma_kernel(const __grid_c
 #pragma unroll
     for (int i = 0; i < HPT; ++i) e_m[i] = 0.f;
     auto epilogue = [&]() {
-      mbar_wait(&bar_done, n_done & 1); ++n_done;    // every PV MMA of that item has completed
+      wait_fast(bar(B_DONE), n_done & 1); ++n_done;    // every PV MMA of that item has completed
       tc_fence_after();
       // O / l.  D_h = [P_h V over the 8-channel group holding head h | l_h x 8]
       uint32_t o[32];
@@ -463,7 +469,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_attn_tma_kernel(const __grid_c
       }
       fence_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bar_q);
+      if (lane == 0) arrive_a(bar(B_Q));
       if (tid == 0) TRACE(1, k);      // Q handed over
       // row bounds per head slot: sum_d min/max(q_d kmax_d, q_d kmin_d) <= s_ij <= ... (raw score units)
       float m[HPT];
@@ -496,7 +502,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_attn_tma_kernel(const __grid_c
         for (int i = 0; i < HPT; ++i) m[i] = -CUDART_INF_F;
         for (int t = 0; t < T; ++t) {
           const int b = t % (int)NBUF;
-          wait_buf(bar_s, b);
+          wait_buf(B_S, b);
           tc_fence_after();
           const int kcount = min(KT, N - t * KT);  // valid keys of this tile (per head)
           uint32_t s32[32];
@@ -510,7 +516,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_attn_tma_kernel(const __grid_c
           }
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&bar_p[b]);   // S(t) consumed
+          if (lane == 0) arrive_a(bar(B_P + b));    // S(t) consumed
         }
         if (HPQ == 1) {                            // the two threads of a row each saw half of the keys
           s_xch[half * 128 + r] = m[0];
@@ -533,7 +539,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_attn_tma_kernel(const __grid_c
           if (t >= T) break;
           {
             uint32_t& ph = b == 0 ? ph0 : (b == 1 ? ph1 : ph2);
-            mbar_wait(&bar_s[b], ph);
+            wait_fast(bar(B_S + b), ph);
             ph ^= 1;
             tc_fence_after();
             __syncwarp();
@@ -552,7 +558,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_attn_tma_kernel(const __grid_c
           tmem_st_wait();
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&bar_p[b]);     // P(t) in TMEM
+          if (lane == 0) arrive_a(bar(B_P + b));     // P(t) in TMEM
         }
       }
       if (tid == 0) TRACE(6, k);      // last P published

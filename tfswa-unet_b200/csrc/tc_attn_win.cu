@@ -79,44 +79,7 @@ template <int D> __host__ __device__ constexpr int smem_bytes();   // 34 / 58 KB
 #endif
 constexpr int POLY_K = TFSWA_WINTC_POLY_K;   // every POLY_K-th element pair on the FMA-pipe polynomial (0 = MUFU only)
 
-// mbarrier / TMA / commit on 32-bit shared-window addresses: the barriers live in dynamic shared memory at constant
-// offsets from the CTA's base, so every use is [base register + immediate] (a `uint64_t*` to a __shared__ barrier costs a
-// generic->shared conversion - S2UR SR_CgaCtaId, UMOV, ULEA - at each use: ~30 instructions per item and warp)
-__device__ __forceinline__ bool try_wait_a(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-  return ok != 0;
-}
 // (a __nanosleep in the retry path of the issuer / producer waits measured no difference: 0.735 ms either way)
-__device__ __forceinline__ void wait_a(uint32_t bar, uint32_t parity) {   // bounded like sm100::mbar_wait: a protocol bug traps
-  uint32_t spins = 0;
-  uint64_t t0 = 0;
-  while (!try_wait_a(bar, parity)) {
-    if ((++spins & 255u) == 0) {
-      uint64_t now;
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-      if (t0 == 0) t0 = now;
-      else if (now - t0 > 4000000000ull) __trap();
-    }
-  }
-}
-__device__ __forceinline__ void arrive_a(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
-__device__ __forceinline__ void expect_tx_a(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void commit_a(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tma_load_4d_a(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
 __device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
 // barrier table (8 bytes each), item ring and the TMEM base pointer sit behind the ones tile
