@@ -4,7 +4,7 @@
  * The reference (chynggi/TFSWA-UNet) has no FFI layer: its hot path sits behind the Python
  * nn.Module surface (src/models/attention.py, blocks.py, tfswa_unet.py) and dispatches ATen ops.
  * Each entry point below replaces the ATen op sequence of one reference call site (cited per
- * function).  The Python mirror of the reference modules (tfswa-unet_b200/*.py) binds these
+ * function).  The Python mirror of the reference modules (the .py files of tfswa-unet_b200/) binds these
  * with ctypes; INTEGRATION.md shows the stub a reference maintainer would add.
  *
  * Conventions
