@@ -103,5 +103,19 @@ __device__ __forceinline__ void softmax_half(const uint32_t (&sc)[32], uint32_t 
   }
 }
 
+// the same with an explicit choice of the polynomial pairs: bit i of MASK (i = pair index 0..15 within the 32 scores)
+template <bool CLAMP, int HALF, uint32_t MASK>
+__device__ __forceinline__ void softmax_half_mask(const uint32_t (&sc)[32], uint32_t (&pk)[16], float c, float mc) {
+  const uint64_t c2 = pk2(c, c), nm = pk2(-mc, -mc);
+#pragma unroll
+  for (int i = 8 * HALF; i < 8 * HALF + 8; ++i) {
+    const uint64_t x = fma2(pk2u(sc[2 * i], sc[2 * i + 1]), c2, nm);
+    float e0, e1;
+    if ((MASK >> i) & 1u) ex2_poly2<CLAMP>(x, e0, e1);
+    else { float x0, x1; up2(x, x0, x1); e0 = ex2_f32(x0); e1 = ex2_f32(x1); }
+    pk[i] = pack_bf16x2(e0, e1);
+  }
+}
+
 }  // namespace tcmath
 }  // namespace tfswa

@@ -20,7 +20,7 @@
 // Softmax warps (0-7; a query row is shared by two threads, 32 of a tile's 64 columns each): S (TMEM) -> registers -> P
 // (bf16, written back IN PLACE over the thread's own S columns, where the PV MMA reads it as its A operand) with
 //   * packed fp32 arithmetic (fma/add.f32x2 -> FFMA2/FADD2: one issue slot per two elements),
-//   * MUFU.EX2 for 11 of 16 element pairs and a degree-3 Cody-Waite polynomial on the FMA pipe for the other 5:
+//   * MUFU.EX2 for 10 of 16 element pairs and a degree-3 Cody-Waite polynomial on the FMA pipe for the other 6:
 //     tools/mufu_bench.cu measures 16.0 ex2/clk/SM for MUFU alone (4.64e12/s) and 21.8/clk/SM (6.3e12/s) for this mix
 //     at 4 warps per sub-partition,
 //   * no running maximum (row bound from the per-channel extrema of k, see tc_attention.cu); the polynomial's exponent
@@ -77,17 +77,19 @@ template <int D> __host__ __device__ constexpr int ones_off() { return stage_off
 template <int D> __host__ __device__ constexpr int tail_off() { return ones_off<D>() + 2 * BOX_BYTES; }
 template <int D> __host__ __device__ constexpr int smem_bytes() { return tail_off<D>() + 2 * BOX_BYTES; }   // 48 / 40 / 36 KB
 
-#ifndef TFSWA_TMA_POLY_K
-#define TFSWA_TMA_POLY_K 3
+// which of the 16 element PAIRS of a thread's 32 scores take the FMA-pipe polynomial instead of MUFU.EX2 (bit i = pair i).
+// Measured per stage-1 TSA launch (B=8) after the v14 barrier forms: 4 of 16: 8.55 ms, 5 of 16 (every third pair, the share
+// tools/mufu_bench.cu found best in isolation): 8.21, 6 of 16: 8.11, 7 of 16: 8.33, 8 of 16: 8.68 - 6 of 16 it is.
+#ifndef TFSWA_TMA_POLY_MASK
+#define TFSWA_TMA_POLY_MASK 0x5252u    // pairs 1, 4, 6 | 9, 12, 14; -D...=0 for MUFU only, 0x4924u = every third pair
 #endif
-constexpr int POLY_K = TFSWA_TMA_POLY_K;   // every POLY_K-th element PAIR takes the polynomial (0 = MUFU only); -D for A/B builds
 
 using namespace tcmath;                  // TMA box load, MN-major descriptor, packed fp32 helpers, FMA-pipe exponential
 
 // 16 scores sc[16*HALF ..] -> 8 packed bf16x2 probabilities pk[8*HALF ..]: p = 2^(s*c - mc)
 template <bool CLAMP, int HALF>
 __device__ __forceinline__ void softmax_half(const uint32_t (&sc)[32], uint32_t (&pk)[16], float c, float mc) {
-  tcmath::softmax_half<CLAMP, HALF, POLY_K>(sc, pk, c, mc);
+  tcmath::softmax_half_mask<CLAMP, HALF, TFSWA_TMA_POLY_MASK>(sc, pk, c, mc);
 }
 
 // TMEM: three S/P buffers of 64 columns (S tile = HPQ heads x KT keys fp32; P overwrites the thread's own S columns as
