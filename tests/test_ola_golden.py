@@ -55,3 +55,20 @@ def test_short_clip_follows_the_single_segment_path(go):
         ref = go["short"][name]
         assert out[name].shape == ref.shape, (out[name].shape, ref.shape)
         assert float((out[name] - ref).abs().max()) <= 1e-5 * float(ref.abs().max()) + 1e-7, name
+
+
+def test_balanced_batches_and_segment_plan():
+    """host logic of the separator: a rank's segments in the fewest batches of near-equal size (17 -> 6 + 6 + 5, not 8 + 8 + 1),
+    covering the range exactly once and in order; the segment plan of inference.py:187-201"""
+    from tfswa_unet_b200.separate import ShardedSeparator, balanced_batches
+    assert balanced_batches(0, 17, 8) == [(0, 6), (6, 12), (12, 17)]
+    assert balanced_batches(5, 5, 8) == [] and balanced_batches(3, 4, 8) == [(3, 4)]
+    for lo, hi, mb in [(0, 133, 8), (7, 40, 8), (0, 8, 8), (0, 9, 8), (2, 67, 3)]:
+        bs = balanced_batches(lo, hi, mb)
+        assert bs[0][0] == lo and bs[-1][1] == hi and all(a[1] == b[0] for a, b in zip(bs, bs[1:]))
+        sizes = [e - s for s, e in bs]
+        assert max(sizes) <= mb and max(sizes) - min(sizes) <= 1 and len(bs) == -(-(hi - lo) // mb)
+    sep = ShardedSeparator(lambda x: x, n_fft=2048, hop_length=512, sample_rate=44100, segment_length=6.0, overlap=0.25)
+    starts = sep.plan(26_460_000)                       # the 10-minute mix of BASELINE configs[3]
+    assert len(starts) == 133 and starts[1] - starts[0] == 198_450 and starts[-1] + 264_600 <= 26_460_000
+    assert sep.plan(264_600) == [0] and sep.plan(1000) == [0]
