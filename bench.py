@@ -424,6 +424,9 @@ def main():
                        "to pinned host memory inside the timed region; the copies of neighbouring steps run on copy streams "
                        "underneath the forward (double-buffered input); the closing event waits for the last read-back"},
         "gpu_launches": launches, "clocks": clocks,
+        "gpu_launches_note": "C-ABI compute calls of libtfswa_b200.so inside the timed region; each is one kernel launch except the attention "
+                             "entry points (pre-pass + main + remainder kernels): the ncu launch list of this command "
+                             "(profiles/r2h_launches_summary.md) shows ~305 kernels per step, none of them ATen / cuBLAS",
     }
     if eager is not None:
         line["gpu_eager_baseline"] = eager

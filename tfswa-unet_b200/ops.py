@@ -27,7 +27,8 @@ def _stream() -> int:
 USE_TC_ATTENTION = True   # tcgen05 attention for axial geometries at head_dim 4/8 (bf16); False forces the SIMT kernel
 
 
-# ---- launch accounting: every C-ABI compute call is exactly one kernel launch -------------------
+# ---- launch accounting: C-ABI compute calls (one kernel launch each, except the attention entry points, which launch their
+# pre-pass / main / remainder kernels: 175 calls = ~305 kernels per C3 forward, profiles/r2h_launches_summary.md) ----
 LAUNCHES = 0
 _TIMING = None          # None, or {kernel tag: [(start_event, end_event, work_dict), ...]}
 _TAG = None
