@@ -68,6 +68,7 @@ __device__ __forceinline__ void tma_load_4d_a(uint32_t dst, const CUtensorMap* m
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 // 2^x for a pair of x <= 0 on the FMA / ALU pipes: x = n + r (round to nearest through the 1.5 * 2^23 trick), degree-3
 // minimax polynomial of 2^r on [-0.5, 0.5] (7.5e-5 relative - P is rounded to bf16, 3.9e-3), exponent patched in with an
 // integer shift-add.  3 FADD2 + 3 FFMA2 + 2 LEA for two results.  CLAMP bounds n at -125 (needed only when the row's

@@ -406,7 +406,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_attn_tma_kernel(const __grid_c
       if (e_valid) {
         if (D == 16) {                               // both threads of the row hold the same 32 columns: split the 16 dims
           const float l = __uint_as_float(o[16]);
-          const float inv = 1.0f / l;
+          const float inv = rcp_approx(l);              // (one MUFU.RCP; `1.0f / l` is a guarded Newton sequence of ~10 instructions)
           float v[8];
 #pragma unroll
           for (int d = 0; d < 8; ++d) v[d] = __uint_as_float(half ? o[8 + d] : o[d]) * inv;
@@ -418,7 +418,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_attn_tma_kernel(const __grid_c
             const int head = half * HPT + hh;        // head within the quad
             const int off = hh * 16 + ((D == 4) ? (hh & 1) * 4 : 0);   // head h's dims start at (h*D) % 8 inside its group
             const float l = __uint_as_float(o[hh * 16 + 8]);
-            const float inv = 1.0f / l;
+            const float inv = rcp_approx(l);              // (one MUFU.RCP; `1.0f / l` is a guarded Newton sequence of ~10 instructions)
             bf16* op = (bf16*)p.out + e_tok * p.ldo + e_quad * 16 + head * D;
             if (D == 4) {
               float v[4];

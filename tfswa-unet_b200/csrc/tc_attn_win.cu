@@ -80,7 +80,6 @@ template <int D> __host__ __device__ constexpr int smem_bytes();   // 34 / 58 KB
 constexpr int POLY_K = TFSWA_WINTC_POLY_K;   // every POLY_K-th element pair on the FMA-pipe polynomial (0 = MUFU only)
 
 // (a __nanosleep in the retry path of the issuer / producer waits measured no difference: 0.735 ms either way)
-__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
 // barrier table (8 bytes each), item ring and the TMEM base pointer sit behind the ones tile
 constexpr int B_FULL = 0, B_EMPTY = NSTAGE, B_Q = 2 * NSTAGE, B_S = B_Q + 2, B_P = B_S + 4, B_O = B_P + 4, B_FREE = B_O + 4,
